@@ -1,0 +1,215 @@
+/*
+ * csmc.h — C-ABI of libcsmc.so, the B200 (sm_100a) sweep engine that replaces the bodies of
+ * ClassicalSpinMC.jl's hot path.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * The reference (pure Julia) has no FFI today; each entry point below names the reference
+ * function whose *body* it replaces (paths relative to the reference repo).  A Julia `ccall`
+ * stub for every export is shown in INTEGRATION.md; `julia/ClassicalSpinMC/src/libcsmc.jl`
+ * holds the real bindings.
+ *
+ * Conventions
+ *   - every function returns int32 status (CSMC_OK == 0); no exception crosses the ABI.
+ *     A human-readable message is available through csmc_last_error().
+ *   - site indices are 1-based on the ABI (Julia convention), basis indices too.
+ *   - spins: N x 3 doubles, row-major  (== Julia `Array{Float64,2}` of size 3 x N).
+ *   - 3x3 matrices: 9 doubles row-major, m11 m12 m13 m21 ... (== `InteractionMatrix`,
+ *     src/interaction_matrix.jl:2-12).
+ *   - cubic / quartic tensors: Julia column-major, element [a,b,c(,d)] (0-based) at
+ *     a + 3*b + 9*c (+ 27*d)   (== `Array{Float64,3}` / `Array{Float64,4}` memory).
+ *   - site order: basis slowest, last lattice dimension fastest (src/lattice.jl:29-33):
+ *     p = 1 + i_D + L_D*(i_{D-1} + ... + L_1*(b-1)),  i_d 0-based cell coordinate.
+ *   - the caller owns every host buffer; the library copies during the call and never
+ *     retains host pointers.  One controlling host thread per handle.
+ *   - all calls are synchronous at return unless the name ends in `_async`.
+ */
+#ifndef CSMC_H
+#define CSMC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSMC_VERSION 100 /* 0.1.0 */
+
+enum {
+    CSMC_OK = 0,
+    CSMC_ERR_INVALID = 1, /* bad argument / inconsistent model            */
+    CSMC_ERR_CUDA = 2,    /* CUDA runtime failure (message has the detail) */
+    CSMC_ERR_NCCL = 3,    /* NCCL failure or NCCL not loadable             */
+    CSMC_ERR_UNSUPPORTED = 4,
+    CSMC_ERR_NOMEM = 5
+};
+
+#define CSMC_MAX_DIM 3
+
+/*
+ * Unit-cell level description of the Hamiltonian and lattice: what `Lattice(shape, uc, S; bc)`
+ * consumes (src/lattice.jl:65-291, src/unit_cell.jl:3-75).  The library derives the per-site
+ * neighbour / coupling tables of the reference in closed form (O(N * terms) instead of the
+ * reference's O(N^2 * terms) `findfirst` scans, src/lattice.jl:196,228-229,273-275).
+ */
+typedef struct csmc_model {
+    int32_t dim;                 /* D, 1..3                                              */
+    int32_t shape[CSMC_MAX_DIM]; /* unit cells per dimension                             */
+    int32_t n_basis;             /* >= 1                                                 */
+    int32_t periodic;            /* 1: bc="periodic", 0: bc="open" (src/lattice.jl:101)  */
+    double S;                    /* spin length                                          */
+    const double *field;         /* n_basis x 3, per-basis h (resolved as lattice.jl:117-140) */
+    const double *onsite;        /* n_basis x 9, per-basis on-site matrix (row-major)    */
+
+    int32_t n_bilinear;          /* N2 = length(uc.bilinear)                             */
+    const int32_t *bil_basis;    /* N2 x 2  (b1,b2), 1-based                             */
+    const int32_t *bil_offset;   /* N2 x D  unit-cell offset of site 2                   */
+    const double *bil_matrix;    /* N2 x 9  row-major                                    */
+
+    int32_t n_cubic;             /* N3                                                   */
+    const int32_t *cub_basis;    /* N3 x 3                                               */
+    const int32_t *cub_offset;   /* N3 x 2 x D  (o2, o3)                                 */
+    const double *cub_tensor;    /* N3 x 27 column-major                                 */
+
+    int32_t n_quartic;           /* N4                                                   */
+    const int32_t *quar_basis;   /* N4 x 4                                               */
+    const int32_t *quar_offset;  /* N4 x 3 x D  (o2, o3, o4)                             */
+    const double *quar_tensor;   /* N4 x 81 column-major                                 */
+} csmc_model;
+
+typedef struct csmc_opts {
+    int32_t device;       /* CUDA device ordinal                                          */
+    int32_t n_replicas;   /* replicas (temperatures) held by THIS handle / GPU, >= 1      */
+    uint64_t seed;        /* Philox key; same seed on every rank of a PT job              */
+    void *stream;         /* cudaStream_t to launch on, or NULL: library creates its own  */
+    int32_t replica_base; /* global index of local replica 0 (PT sharding), else 0        */
+    int32_t flags;        /* CSMC_FLAG_*                                                  */
+} csmc_opts;
+
+#define CSMC_FLAG_FORCE_GENERIC 1 /* use the explicit-index-table kernels even when the      \
+                                     arithmetic-neighbour (structured) kernels apply        */
+#define CSMC_FLAG_NO_GRAPH 2      /* plain stream launches instead of CUDA-graph replay      */
+
+typedef struct csmc_handle csmc_handle;
+
+/* ---- library / handle ------------------------------------------------------------------ */
+int32_t csmc_version(void);
+/* message of the last failure on `h` (or, with h == NULL, of the last failed csmc_create). */
+const char *csmc_last_error(const csmc_handle *h);
+
+/* Replaces: table-building body of `Lattice(...)`, src/lattice.jl:168-288, plus the colouring
+ * of the interaction hypergraph that makes a colour class updatable race-free. */
+int32_t csmc_create(const csmc_model *model, const csmc_opts *opts, csmc_handle **out);
+int32_t csmc_destroy(csmc_handle *h);
+
+int32_t csmc_n_sites(const csmc_handle *h, int64_t *n);
+int32_t csmc_n_replicas(const csmc_handle *h, int32_t *r);
+int32_t csmc_n_colours(const csmc_handle *h, int32_t *c);
+/* colour[N] (0-based colour of site p, reference order) */
+int32_t csmc_get_colouring(const csmc_handle *h, int32_t *colour);
+/* 1 if the arithmetic-neighbour kernels are in use, 0 if the explicit-table kernels are. */
+int32_t csmc_is_structured(const csmc_handle *h, int32_t *flag);
+/* kernels launched on this handle since creation (bench.py's `gpu_launches`). */
+int32_t csmc_launch_count(const csmc_handle *h, int64_t *n);
+
+/* Reference-layout neighbour tables as the library derived them (for parity tests against
+ * lat.bilinear_sites / cubic_sites / quartic_sites, src/lattice.jl:205,238,285):
+ * bil[N x N2], cub[N x N3 x 2], quar[N x N4 x 3]; 1-based, 0 == null slot. Any may be NULL. */
+int32_t csmc_get_tables(const csmc_handle *h, int64_t *bil, int64_t *cub, int64_t *quar);
+
+/* ---- state ------------------------------------------------------------------------------ */
+/* Replaces direct writes to `lattice.spins` (src/lattice.jl:297-301). replica is local, 0-based */
+int32_t csmc_set_spins(csmc_handle *h, int32_t replica, const double *spins);
+int32_t csmc_get_spins(csmc_handle *h, int32_t replica, double *spins);
+/* Device-side `random_spin_orientation` for every site of every replica (src/lattice.jl:76-79,
+ * 306-311), Philox stream (seed, global replica, site). */
+int32_t csmc_randomize_spins(csmc_handle *h, uint64_t seed);
+
+/* ---- Hamiltonian evaluation ------------------------------------------------------------- */
+/* Replaces get_local_field(lattice, point), src/hamiltonian.jl:3-67 (returns H - h). */
+int32_t csmc_local_field(csmc_handle *h, int32_t replica, int64_t site, double out[3]);
+int32_t csmc_local_field_all(csmc_handle *h, int32_t replica, double *out /* N x 3 */);
+/* Replaces energy(lattice, point), src/hamiltonian.jl:139-196, for every site. */
+int32_t csmc_site_energy_all(csmc_handle *h, int32_t replica, double *out /* N */);
+/* Replaces total_energy(lattice), src/hamiltonian.jl:70-132. E[n_replicas]. */
+int32_t csmc_total_energy(csmc_handle *h, double *E);
+/* Replaces the vector sum inside get_magnetization, src/observables.jl:12-18: M3[n_replicas x 3]
+ * (the caller takes the norm). */
+int32_t csmc_magnetization(csmc_handle *h, double *M3);
+
+/* ---- sweeps ------------------------------------------------------------------------------ */
+/* Replaces overrelaxation!(lattice), src/monte_carlo.jl:126-139: n_sweeps colour-ordered sweeps. */
+int32_t csmc_overrelax(csmc_handle *h, int32_t n_sweeps);
+/* Replaces the body of deterministic_updates!, src/monte_carlo.jl:201-213, as colour-ordered
+ * full sweeps s <- -F/|F| * S. */
+int32_t csmc_deterministic(csmc_handle *h, int32_t n_sweeps);
+/* Replaces metropolis!(mc, T), src/metropolis.jl:65-82 (+ calculate_energy_diff!, :94-101):
+ * n_sweeps colour-ordered sweeps at per-replica temperatures T[n_replicas];
+ * accepted[n_replicas] accumulates accepted proposals (may be NULL). */
+int32_t csmc_metropolis(csmc_handle *h, const double *T, int32_t n_sweeps, double *accepted);
+/* Cone-move variant (gaussian_move, src/metropolis.jl:84-87,103-153) with per-replica sigma.
+ * adapt != 0 applies the MetropolisAdaptive rule (src/metropolis.jl:129-131) after each sweep
+ * and writes the new sigma back. */
+int32_t csmc_metropolis_cone(csmc_handle *h, const double *T, double *sigma, int32_t adapt,
+                             int32_t n_sweeps, double *accepted);
+
+/* Replaces the inner `while t < t_thermalization` loop of simulated_annealing!,
+ * src/monte_carlo.jl:169-182, at per-replica temperatures T: for t = 1 .. t_thermalization-1:
+ * overrelaxation sweep (if rate != 0), Metropolis sweep when t % rate == 0 (every t if rate == 0).
+ * accepted[n_replicas] (may be NULL) receives the accepted-proposal totals. */
+int32_t csmc_anneal_temperature(csmc_handle *h, const double *T, int64_t t_thermalization,
+                                int32_t overrelaxation_rate, double *accepted);
+
+/* Steady-state throughput loop used by bench.py: n_cycles x (or_per_cycle overrelaxation sweeps +
+ * metro_per_cycle Metropolis sweeps) at the current temperatures, no host sync inside.
+ * The `_async` form returns after enqueueing on the handle's stream. */
+int32_t csmc_set_temperatures(csmc_handle *h, const double *T);
+int32_t csmc_cycles_async(csmc_handle *h, int64_t n_cycles, int32_t or_per_cycle,
+                          int32_t metro_per_cycle);
+int32_t csmc_sync(csmc_handle *h);
+/* accepted proposals per replica since the last call with reset != 0 */
+int32_t csmc_get_accepted(csmc_handle *h, double *accepted, int32_t reset);
+
+/* ---- parallel tempering (src/monte_carlo.jl:235-398) ------------------------------------ */
+/* The job has n_slots temperature slots T_all[n_slots] (slot == the reference's MPI rank).
+ * This handle's local replica r starts in slot replica_base + r.  Temperatures are exchanged,
+ * configurations never move. */
+int32_t csmc_pt_init(csmc_handle *h, int32_t n_slots, const double *T_all);
+/* Multi-GPU: rank 0 calls csmc_comm_unique_id, the host broadcasts the 128 bytes (e.g. with
+ * torch.distributed / MPI), every rank calls csmc_comm_init.  Single-GPU jobs skip both. */
+int32_t csmc_comm_unique_id(uint8_t id[128]);
+int32_t csmc_comm_init(csmc_handle *h, int32_t n_ranks, int32_t rank, const uint8_t id[128]);
+
+typedef struct csmc_pt_params {
+    int64_t t_thermalization;
+    int64_t t_measurement;
+    int32_t probe_rate;
+    int32_t swap_rate;
+    int32_t overrelaxation_rate;
+    int32_t reserved;
+} csmc_pt_params;
+
+/* Replaces the body of the `while sweep < total_sweeps` loop, src/monte_carlo.jl:295-388, for
+ * sweeps sweep_begin .. sweep_end-1 (host chunks the run at checkpoint / report boundaries):
+ * overrelaxation (:298-300), Metropolis + total_energy when sweep % dosweep == 0 (:302-305),
+ * replica exchange when sweep % swap_rate == 0 (:308-349), E/M probe when
+ * sweep >= t_thermalization and sweep % probe_rate == 0 (:353,368-370). */
+int32_t csmc_pt_run(csmc_handle *h, const csmc_pt_params *p, int64_t sweep_begin,
+                    int64_t sweep_end);
+/* Replaces the exchange block alone (src/monte_carlo.jl:308-349) on fresh energies;
+ * parity = (sweep / swap_rate) % 2.  accepted_pairs[n_slots] (may be NULL): 1 where the
+ * pair starting at that slot swapped. */
+int32_t csmc_pt_exchange(csmc_handle *h, int32_t parity, int32_t *accepted_pairs);
+/* slot_of_replica[n_slots] for ALL global replicas (identical on every rank). */
+int32_t csmc_pt_get_slots(csmc_handle *h, int32_t *slot_of_replica);
+/* Probe series recorded so far, attributed to temperature slots:
+ * E[n_probes x n_slots], M[n_probes x n_slots] (|sum s|). *n_probes is in/out (capacity/count).
+ * Only slots whose replica lives on this rank are filled when no communicator is attached
+ * across ranks; with a communicator every rank holds all slots. */
+int32_t csmc_pt_get_series(csmc_handle *h, int64_t *n_probes, double *E, double *M);
+/* cumulative statistics, per slot: accepted Metropolis proposals and accepted exchanges
+ * (src/monte_carlo.jl:269-274, src/helper.jl:25-78). */
+int32_t csmc_pt_get_stats(csmc_handle *h, double *accepted_local, double *exchanges);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSMC_H */

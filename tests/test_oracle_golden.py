@@ -1,0 +1,135 @@
+"""Pins the CPU oracle against every golden value / known answer the reference's own tests hold
+for the hot path:
+  test/latticetests.jl:6   |s| == S for random initial spins
+  test/latticetests.jl:17  Zeeman: total_energy == -1.0
+  test/latticetests.jl:18  get_local_field == (-1, -0, -0)
+  test/latticetests.jl:30  bilinear: total_energy / size == -2.0
+  test/mctests.jl:49,57    annealed Kitaev-Gamma honeycomb: round(E/N, 4) == -0.6444
+and checks the closed-form table construction against a literal restatement of the reference's
+`findfirst` scan (src/lattice.jl:196,228-229,273-275) on small lattices.
+"""
+import numpy as np
+import pytest
+
+import classicalspinmc.jl_b200 as csm
+from classicalspinmc.jl_b200._abi import ModelData
+from oracle import oracle as orc
+from tests import models
+
+
+def test_norm_spin():
+    # test/latticetests.jl:3-7
+    md = ModelData(_with_basis(csm.Square()), (2, 2), 1.0)
+    lat = orc.OracleLattice(md)
+    s = lat.randomize(seed=42)
+    assert np.all(np.round(np.linalg.norm(s, axis=1), 9) == 1.0)
+
+
+def _with_basis(uc):
+    if len(uc.basis) == 0:
+        csm.addBasisSite(uc, np.zeros(uc.D))  # src/lattice.jl:68-70
+    return uc
+
+
+def test_energy_zeeman_exact():
+    # test/latticetests.jl:10-19
+    uc = csm.Square()
+    h = np.array([1.0, 0.0, 0.0])
+    csm.addZeemanCoupling(uc, 1, h)
+    lat = orc.OracleLattice(ModelData(_with_basis(uc), (1, 1), 1.0))
+    spins = np.array([[1.0, 0.0, 0.0]])
+    assert lat.total_energy(spins) == -1.0
+    f = lat.local_field(spins, 1)
+    assert tuple(f) == (-1.0, -0.0, -0.0)
+
+
+def test_energy_bilinear_exact():
+    # test/latticetests.jl:21-31
+    uc = models.square_heisenberg(J=-1.0, h=None)
+    lat = orc.OracleLattice(ModelData(_with_basis(uc), (2, 2), 1.0))
+    spins = np.tile(np.array([1.0, 0.0, 0.0]), (4, 1))
+    assert lat.total_energy(spins) / lat.N == -2.0
+    bil, _, _ = lat.tables()
+    # on L=2 the +-x neighbours are the same site counted twice
+    assert bil.tolist()[0] == [3, 3, 2, 2]
+
+
+@pytest.mark.parametrize("alg", [0, 1])
+def test_annealing_ground_state(alg):
+    # test/mctests.jl:1-58: honeycomb L=4, K=-1, G=0.2, Gp=-0.02, h=0.1*[111]/sqrt3
+    uc = models.kitaev_honeycomb()
+    lat = orc.OracleLattice(ModelData(uc, (4, 4), 1.0))
+    spins = lat.randomize(seed=7 + alg)
+    T0, T = 1.0, 1e-7
+    temps = orc.annealing_temperatures(T, lambda x: T0 * 0.9 ** x, T0)
+    assert len(temps) == 153
+    lat.simulated_annealing(spins, temps, int(1e4), 10, alg=alg, seed=11 + alg)
+    if alg == 0:
+        lat.deterministic_updates(spins, int(1e6), seed=5)
+    E = lat.total_energy(spins) / lat.N
+    assert round(E, 4) == -0.6444
+
+
+CASES = [
+    ("square", lambda: models.square_heisenberg(), (3, 4), "periodic"),
+    ("square-open", lambda: models.square_heisenberg(), (3, 4), "open"),
+    ("honeycomb", lambda: models.kitaev_honeycomb(J3=0.3), (3, 5), "periodic"),
+    ("pyrochlore", lambda: models.pyrochlore_local(), (2, 3, 2), "periodic"),
+    ("triangular-multispin", lambda: models.triangular_multispin(), (4, 4), "periodic"),
+    ("triangular-multispin-open", lambda: models.triangular_multispin(), (3, 4), "open"),
+    ("mixed-basis", lambda: models.mixed_basis_multispin(), (3, 4), "periodic"),
+    ("mixed-basis-open", lambda: models.mixed_basis_multispin(), (3, 3), "open"),
+]
+
+
+@pytest.mark.parametrize("name,builder,shape,bc", CASES, ids=[c[0] for c in CASES])
+def test_closed_form_tables_match_literal_findfirst(name, builder, shape, bc):
+    md = ModelData(builder(), shape, 1.0, bc)
+    fast = orc.OracleLattice(md, literal=False)
+    slow = orc.OracleLattice(md, literal=True)
+    for a, b in zip(fast.tables(), slow.tables()):
+        assert np.array_equal(a, b)
+    assert np.array_equal(fast.bilinear_matrices(), slow.bilinear_matrices())
+
+
+@pytest.mark.parametrize("name,builder,shape,bc", CASES, ids=[c[0] for c in CASES])
+def test_site_energy_field_consistency(name, builder, shape, bc):
+    """Self-consistency of the (unpinned) multi-spin restatement: with every perspective of a term
+    registered, e_i is linear in s_i through the field: e_i = s_i.(F_i + h_i - O s_i) - s_i.h_i
+    (src/hamiltonian.jl:3-67 vs :139-196), and total_energy equals the weighted site sums."""
+    md = ModelData(builder(), shape, 0.7, bc)
+    lat = orc.OracleLattice(md)
+    s = lat.randomize(seed=3)
+    F = lat.local_field_all(s)
+    e = lat.site_energy_all(s)
+    from classicalspinmc.jl_b200._abi import resolve_field_onsite
+    nb = md.n_basis
+    cells = lat.N // nb
+    basis_of = np.repeat(np.arange(nb), cells)
+    h = md.field[basis_of]
+    O = md.onsite[basis_of].reshape(-1, 3, 3)
+    Os = np.einsum("nab,nb->na", O, s)
+    e_from_field = np.einsum("na,na->n", s, F - Os)
+    assert np.allclose(e, e_from_field, rtol=0, atol=1e-12)
+
+
+def test_multispin_perspectives_sum_rule():
+    """Sum_i e3_i / 3 and Sum_i e4_i / 4 equal the direct per-cell sums."""
+    L = (4, 4)
+    uc = models.triangular_multispin(J=0.0)
+    # J=0 drops the bilinear terms entirely (src/unit_cell.jl:49)
+    assert len(uc.bilinear) == 0
+    md = ModelData(uc, L, 1.0)
+    lat = orc.OracleLattice(md)
+    s = lat.randomize(seed=9)
+    C3 = np.random.default_rng(7).uniform(-0.1, 0.1, (3, 3, 3))
+    R4 = np.random.default_rng(8).uniform(-0.05, 0.05, (3, 3, 3, 3))
+    S = s.reshape(L[0], L[1], 3)
+    direct = 0.0
+    for x in range(L[0]):
+        for y in range(L[1]):
+            s0 = S[x, y]; s1 = S[(x + 1) % L[0], y]; s2 = S[x, (y + 1) % L[1]]
+            s3 = S[(x + 1) % L[0], (y + 1) % L[1]]
+            direct += np.einsum("abc,a,b,c->", C3, s0, s1, s2)
+            direct += np.einsum("abcd,a,b,c,d->", R4, s0, s1, s2, s3)
+    assert abs(lat.total_energy(s) - direct) < 1e-12
