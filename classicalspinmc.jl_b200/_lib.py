@@ -1,0 +1,329 @@
+"""Loader and ctypes prototypes for libcsmc.so (include/csmc.h) plus a thin ``Engine`` wrapper.
+
+There is no CPU fallback: if the shared library is missing or a call fails, a ``CsmcError`` is
+raised.  ``build()`` compiles the library in-tree with nvcc for sm_100a (works without a GPU).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from ._abi import CsmcModel, CsmcOpts, CsmcPtParams, ModelData
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libcsmc.so")
+_LIB = None
+
+# every symbol include/csmc.h declares (tests check the .so exports all of them)
+EXPORTS = [
+    "csmc_version", "csmc_last_error", "csmc_create", "csmc_destroy", "csmc_plan", "csmc_n_sites",
+    "csmc_n_replicas", "csmc_n_colours", "csmc_get_colouring", "csmc_is_structured",
+    "csmc_launch_count", "csmc_get_tables", "csmc_set_spins", "csmc_get_spins",
+    "csmc_randomize_spins", "csmc_local_field", "csmc_local_field_all", "csmc_site_energy_all",
+    "csmc_total_energy", "csmc_magnetization", "csmc_overrelax", "csmc_deterministic",
+    "csmc_metropolis", "csmc_metropolis_cone", "csmc_anneal_temperature", "csmc_set_temperatures",
+    "csmc_cycles_async", "csmc_sync", "csmc_get_accepted", "csmc_pt_init", "csmc_comm_unique_id",
+    "csmc_comm_init", "csmc_pt_run", "csmc_pt_exchange", "csmc_pt_get_slots", "csmc_pt_get_series",
+    "csmc_pt_get_stats",
+]
+
+
+class CsmcError(RuntimeError):
+    pass
+
+
+def build(force: bool = False) -> str:
+    """Compile csrc/ -> libcsmc.so (nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo)."""
+    src_dir = os.path.join(_HERE, "csrc")
+    srcs = [os.path.join(src_dir, f) for f in os.listdir(src_dir) if f.endswith((".cu", ".cuh", ".cpp", ".h"))]
+    srcs.append(os.path.join(os.path.dirname(_HERE), "include", "csmc.h"))
+    stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", src_dir, "-s"] + (["-B"] if force else []))
+    return _SO
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(_SO):
+        raise CsmcError(f"{_SO} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU fallback)")
+    L = C.CDLL(_SO)
+    vp, i32, i64, u64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double
+    P = C.POINTER
+    L.csmc_version.restype = i32
+    L.csmc_last_error.restype = C.c_char_p
+    L.csmc_last_error.argtypes = [vp]
+    L.csmc_create.argtypes = [P(CsmcModel), P(CsmcOpts), P(vp)]
+    L.csmc_destroy.argtypes = [vp]
+    L.csmc_plan.argtypes = [P(CsmcModel), i32, vp, P(i32), P(i32), vp]
+    L.csmc_n_sites.argtypes = [vp, P(i64)]
+    L.csmc_n_replicas.argtypes = [vp, P(i32)]
+    L.csmc_n_colours.argtypes = [vp, P(i32)]
+    L.csmc_get_colouring.argtypes = [vp, vp]
+    L.csmc_is_structured.argtypes = [vp, P(i32)]
+    L.csmc_launch_count.argtypes = [vp, P(i64)]
+    L.csmc_get_tables.argtypes = [vp, vp, vp, vp]
+    L.csmc_set_spins.argtypes = [vp, i32, vp]
+    L.csmc_get_spins.argtypes = [vp, i32, vp]
+    L.csmc_randomize_spins.argtypes = [vp, u64]
+    L.csmc_local_field.argtypes = [vp, i32, i64, vp]
+    L.csmc_local_field_all.argtypes = [vp, i32, vp]
+    L.csmc_site_energy_all.argtypes = [vp, i32, vp]
+    L.csmc_total_energy.argtypes = [vp, vp]
+    L.csmc_magnetization.argtypes = [vp, vp]
+    L.csmc_overrelax.argtypes = [vp, i32]
+    L.csmc_deterministic.argtypes = [vp, i32]
+    L.csmc_metropolis.argtypes = [vp, vp, i32, vp]
+    L.csmc_metropolis_cone.argtypes = [vp, vp, vp, i32, i32, vp]
+    L.csmc_anneal_temperature.argtypes = [vp, vp, i64, i32, vp]
+    L.csmc_set_temperatures.argtypes = [vp, vp]
+    L.csmc_cycles_async.argtypes = [vp, i64, i32, i32]
+    L.csmc_sync.argtypes = [vp]
+    L.csmc_get_accepted.argtypes = [vp, vp, i32]
+    L.csmc_pt_init.argtypes = [vp, i32, vp]
+    L.csmc_comm_unique_id.argtypes = [vp]
+    L.csmc_comm_init.argtypes = [vp, i32, i32, vp]
+    L.csmc_pt_run.argtypes = [vp, P(CsmcPtParams), i64, i64]
+    L.csmc_pt_exchange.argtypes = [vp, i32, vp]
+    L.csmc_pt_get_slots.argtypes = [vp, vp]
+    L.csmc_pt_get_series.argtypes = [vp, P(i64), vp, vp]
+    L.csmc_pt_get_stats.argtypes = [vp, vp, vp]
+    for name in EXPORTS:
+        if name not in ("csmc_last_error",):
+            getattr(L, name).restype = i32
+    _LIB = L
+    return L
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None and a.shape != tuple(shape):
+        raise ValueError(f"expected shape {shape}, got {a.shape}")
+    return a
+
+
+def comm_unique_id() -> bytes:
+    buf = (C.c_uint8 * 128)()
+    rc = lib().csmc_comm_unique_id(buf)
+    if rc:
+        raise CsmcError(f"csmc_comm_unique_id failed ({rc}): {lib().csmc_last_error(None).decode()}")
+    return bytes(buf)
+
+
+def plan(model: ModelData, flags: int = 0):
+    """Host-only colouring / layout plan (csmc_plan): (colour[N], n_colours, structured, storage_pos[N])."""
+    L = lib()
+    col = np.zeros(model.n_sites, np.int32)
+    pos = np.zeros(model.n_sites, np.int32)
+    nc, st = C.c_int32(), C.c_int32()
+    rc = L.csmc_plan(C.byref(model.struct), flags, _p(col), C.byref(nc), C.byref(st), _p(pos))
+    if rc:
+        raise CsmcError(f"csmc_plan failed ({rc}): {L.csmc_last_error(None).decode()}")
+    return col, nc.value, bool(st.value), pos
+
+
+class Engine:
+    """Owns one ``csmc_handle`` (device state of ``n_replicas`` replicas of one lattice model).
+
+    Spin arrays cross this boundary as (N, 3) C-contiguous float64, the memory layout of the
+    reference's ``lattice.spins`` (Julia 3 x N column-major)."""
+
+    def __init__(self, model: ModelData, n_replicas: int = 1, seed: int = 12345, device: int = 0,
+                 stream: int | None = None, replica_base: int = 0, flags: int = 0):
+        self._L = lib()
+        self.model = model
+        opts = CsmcOpts(device=device, n_replicas=n_replicas, seed=seed, stream=stream,
+                        replica_base=replica_base, flags=flags)
+        h = C.c_void_p()
+        rc = self._L.csmc_create(C.byref(model.struct), C.byref(opts), C.byref(h))
+        if rc:
+            raise CsmcError(f"csmc_create failed ({rc}): {self._L.csmc_last_error(None).decode()}")
+        self._h = h
+        self.n_replicas = n_replicas
+        self.replica_base = replica_base
+        self.seed = seed
+        n = C.c_int64()
+        self._ck(self._L.csmc_n_sites(self._h, C.byref(n)))
+        self.N = n.value
+
+    # -- plumbing -----------------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc:
+            raise CsmcError(f"libcsmc error {rc}: {self._L.csmc_last_error(self._h).decode()}")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.csmc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- introspection ------------------------------------------------------------------------
+    @property
+    def n_colours(self):
+        c = C.c_int32()
+        self._ck(self._L.csmc_n_colours(self._h, C.byref(c)))
+        return c.value
+
+    @property
+    def structured(self):
+        c = C.c_int32()
+        self._ck(self._L.csmc_is_structured(self._h, C.byref(c)))
+        return bool(c.value)
+
+    @property
+    def launches(self):
+        c = C.c_int64()
+        self._ck(self._L.csmc_launch_count(self._h, C.byref(c)))
+        return c.value
+
+    def colouring(self):
+        col = np.zeros(self.N, np.int32)
+        self._ck(self._L.csmc_get_colouring(self._h, _p(col)))
+        return col
+
+    def colour_order(self):
+        """1-based site visiting order of one colour-ordered sweep."""
+        return (np.argsort(self.colouring(), kind="stable") + 1).astype(np.int64)
+
+    def tables(self):
+        md = self.model
+        bil = np.zeros((self.N, md.n2), np.int64)
+        cub = np.zeros((self.N, md.n3, 2), np.int64)
+        quar = np.zeros((self.N, md.n4, 3), np.int64)
+        self._ck(self._L.csmc_get_tables(self._h, _p(bil), _p(cub), _p(quar)))
+        return bil, cub, quar
+
+    # -- state --------------------------------------------------------------------------------
+    def set_spins(self, spins, replica=0):
+        s = _f64(spins, (self.N, 3))
+        self._ck(self._L.csmc_set_spins(self._h, replica, _p(s)))
+
+    def get_spins(self, replica=0, out=None):
+        s = np.empty((self.N, 3)) if out is None else out
+        self._ck(self._L.csmc_get_spins(self._h, replica, _p(s)))
+        return s
+
+    def randomize(self, seed):
+        self._ck(self._L.csmc_randomize_spins(self._h, seed))
+
+    # -- Hamiltonian --------------------------------------------------------------------------
+    def local_field(self, site, replica=0):
+        out = np.zeros(3)
+        self._ck(self._L.csmc_local_field(self._h, replica, site, _p(out)))
+        return out
+
+    def local_field_all(self, replica=0):
+        out = np.zeros((self.N, 3))
+        self._ck(self._L.csmc_local_field_all(self._h, replica, _p(out)))
+        return out
+
+    def site_energy_all(self, replica=0):
+        out = np.zeros(self.N)
+        self._ck(self._L.csmc_site_energy_all(self._h, replica, _p(out)))
+        return out
+
+    def total_energy(self):
+        E = np.zeros(self.n_replicas)
+        self._ck(self._L.csmc_total_energy(self._h, _p(E)))
+        return E
+
+    def magnetization_vector(self):
+        M = np.zeros((self.n_replicas, 3))
+        self._ck(self._L.csmc_magnetization(self._h, _p(M)))
+        return M
+
+    # -- sweeps -------------------------------------------------------------------------------
+    def _T(self, T):
+        T = np.broadcast_to(np.asarray(T, dtype=np.float64), (self.n_replicas,))
+        return np.ascontiguousarray(T)
+
+    def overrelax(self, n_sweeps=1):
+        self._ck(self._L.csmc_overrelax(self._h, n_sweeps))
+
+    def deterministic(self, n_sweeps=1):
+        self._ck(self._L.csmc_deterministic(self._h, n_sweeps))
+
+    def metropolis(self, T, n_sweeps=1):
+        acc = np.zeros(self.n_replicas)
+        self._ck(self._L.csmc_metropolis(self._h, _p(self._T(T)), n_sweeps, _p(acc)))
+        return acc
+
+    def metropolis_cone(self, T, sigma, adapt=False, n_sweeps=1):
+        acc = np.zeros(self.n_replicas)
+        sig = self._T(sigma).copy()
+        self._ck(self._L.csmc_metropolis_cone(self._h, _p(self._T(T)), _p(sig), int(adapt), n_sweeps, _p(acc)))
+        return acc, sig
+
+    def anneal_temperature(self, T, t_thermalization, overrelaxation_rate):
+        acc = np.zeros(self.n_replicas)
+        self._ck(self._L.csmc_anneal_temperature(self._h, _p(self._T(T)), t_thermalization,
+                                                 overrelaxation_rate, _p(acc)))
+        return acc
+
+    def set_temperatures(self, T):
+        self._ck(self._L.csmc_set_temperatures(self._h, _p(self._T(T))))
+
+    def cycles_async(self, n_cycles, or_per_cycle, metro_per_cycle):
+        self._ck(self._L.csmc_cycles_async(self._h, n_cycles, or_per_cycle, metro_per_cycle))
+
+    def sync(self):
+        self._ck(self._L.csmc_sync(self._h))
+
+    def accepted(self, reset=False):
+        acc = np.zeros(self.n_replicas)
+        self._ck(self._L.csmc_get_accepted(self._h, _p(acc), int(reset)))
+        return acc
+
+    # -- parallel tempering -------------------------------------------------------------------
+    def comm_init(self, n_ranks, rank, unique_id: bytes):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._ck(self._L.csmc_comm_init(self._h, n_ranks, rank, buf))
+
+    def pt_init(self, T_all):
+        T_all = _f64(T_all)
+        self.n_slots = len(T_all)
+        self._ck(self._L.csmc_pt_init(self._h, len(T_all), _p(T_all)))
+
+    def pt_run(self, params: dict, sweep_begin, sweep_end):
+        p = CsmcPtParams(params["t_thermalization"], params["t_measurement"], params["probe_rate"],
+                         params["swap_rate"], params["overrelaxation_rate"], 0)
+        self._ck(self._L.csmc_pt_run(self._h, C.byref(p), sweep_begin, sweep_end))
+
+    def pt_exchange(self, parity):
+        acc = np.zeros(self.n_slots, np.int32)
+        self._ck(self._L.csmc_pt_exchange(self._h, parity, _p(acc)))
+        return acc
+
+    def pt_slots(self):
+        s = np.zeros(self.n_slots, np.int32)
+        self._ck(self._L.csmc_pt_get_slots(self._h, _p(s)))
+        return s
+
+    def pt_series(self):
+        n = C.c_int64(0)
+        self._ck(self._L.csmc_pt_get_series(self._h, C.byref(n), None, None))
+        cnt = n.value
+        E = np.zeros((cnt, self.n_slots)); M = np.zeros((cnt, self.n_slots))
+        n = C.c_int64(cnt)
+        self._ck(self._L.csmc_pt_get_series(self._h, C.byref(n), _p(E), _p(M)))
+        return E, M
+
+    def pt_stats(self):
+        a = np.zeros(self.n_slots); e = np.zeros(self.n_slots)
+        self._ck(self._L.csmc_pt_get_stats(self._h, _p(a), _p(e)))
+        return a, e

@@ -1,0 +1,778 @@
+// api.cu — the C-ABI of libcsmc.so (include/csmc.h): handle management, launch sequencing, NCCL.
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace csmc;
+
+// ---- NCCL, loaded lazily so single-GPU users need no NCCL at all ------------------------------------
+namespace {
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclFloat64 = 8 };
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    std::string err;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+
+bool load_nccl() {
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    if (g_nccl.lib) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) { g_nccl.err = std::string("cannot load libnccl: ") + dlerror(); return false; }
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(g_nccl.lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(g_nccl.lib, "ncclCommInitRank");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(g_nccl.lib, "ncclCommDestroy");
+    g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(g_nccl.lib, "ncclAllGather");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(g_nccl.lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllGather) {
+        g_nccl.err = "libnccl lacks required symbols";
+        dlclose(g_nccl.lib); g_nccl.lib = nullptr;
+        return false;
+    }
+    return true;
+}
+std::string g_create_error;
+}  // namespace
+
+struct csmc_handle {
+    HostModel hm;
+    // deep copy of the model (for csmc_get_tables)
+    csmc_model model;
+    std::vector<double> m_field, m_onsite, m_bilJ, m_cubT, m_quarT;
+    std::vector<int32_t> m_bilB, m_bilO, m_cubB, m_cubO, m_quarB, m_quarO;
+
+    int device = 0, R = 1, replica_base = 0, flags = 0;
+    unsigned long long seed = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+
+    double *d_spins = nullptr, *d_stage = nullptr, *d_out = nullptr;
+    int32_t *d_nbr = nullptr, *d_ref_of_pos = nullptr;
+    double *d_T = nullptr, *d_sigma = nullptr;
+    unsigned long long *d_acc = nullptr, *d_acc_prev = nullptr, *d_ctr = nullptr;
+    double *d_partials = nullptr;
+    int n_partials = 0;
+    std::vector<int> pass_blocks, partial_base;
+    std::vector<PassSmall> ps;
+    std::vector<PassLarge> pl;
+    bool large = false;
+    unsigned long long metro_ctr = 0;  // Metropolis sweeps enqueued so far (Philox counter)
+    unsigned long long acc_reset[1] = {0};
+    std::vector<unsigned long long> acc_base;  // per-replica counter value at last reset
+
+    // parallel tempering
+    int n_slots = 0;
+    double *d_T_slot = nullptr, *d_meas_all = nullptr, *d_E_last = nullptr, *d_acc_prev_pt = nullptr;
+    double *d_acc_slot = nullptr, *d_exch_slot = nullptr, *d_series_E = nullptr, *d_series_M = nullptr;
+    int *d_slot_of_rep = nullptr, *d_rep_of_slot = nullptr, *d_accepted_pairs = nullptr;
+    long long series_cap = 0, n_probes = 0;
+    ncclComm_t comm = nullptr;
+    int n_ranks = 1, rank = 0;
+
+    // CUDA graph of one bench cycle
+    cudaGraphExec_t cycle_graph = nullptr;
+    int cycle_or = -1, cycle_metro = -1;
+
+    std::string err;
+    long long launches = 0;
+};
+
+namespace {
+
+int fail(csmc_handle *h, int code, const std::string &msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(h, CSMC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));     \
+    } while (0)
+#define CKN(call)                                                                                  \
+    do {                                                                                           \
+        ncclResult_t r_ = (call);                                                                  \
+        if (r_ != 0)                                                                               \
+            return fail(h, CSMC_ERR_NCCL, std::string(#call) + ": " +                              \
+                                              (g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "nccl error")); \
+    } while (0)
+
+template <class T> cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T)); }
+
+template <int UPD>
+void launch_sweep_pass(csmc_handle *h, int colour, const SweepArgs &a) {
+    const int nseg = h->hm.colour_seg_begin[colour + 1] - h->hm.colour_seg_begin[colour];
+    dim3 grid(h->pass_blocks[colour], nseg, h->R), block(TPB);
+    if (h->large) {
+        if (h->hm.structured) k_sweep<PassLarge, true, UPD><<<grid, block, 0, h->stream>>>(h->pl[colour], a);
+        else k_sweep<PassLarge, false, UPD><<<grid, block, 0, h->stream>>>(h->pl[colour], a);
+    } else {
+        if (h->hm.structured) k_sweep<PassSmall, true, UPD><<<grid, block, 0, h->stream>>>(h->ps[colour], a);
+        else k_sweep<PassSmall, false, UPD><<<grid, block, 0, h->stream>>>(h->ps[colour], a);
+    }
+    h->launches++;
+}
+
+SweepArgs sweep_args(csmc_handle *h, unsigned long long ctr_off, bool device_ctr) {
+    SweepArgs a{};
+    a.T = h->d_T; a.sigma = h->d_sigma; a.accepted = h->d_acc;
+    a.ctr_base = device_ctr ? h->d_ctr : nullptr;
+    a.ctr_off = ctr_off; a.seed = h->seed; a.replica_base = h->replica_base;
+    return a;
+}
+
+// one full sweep = every colour once, in colour order
+template <int UPD>
+void enqueue_sweep(csmc_handle *h, unsigned long long ctr_off = 0, bool device_ctr = false) {
+    const SweepArgs a = sweep_args(h, ctr_off, device_ctr);
+    for (int c = 0; c < h->hm.n_colours; ++c) launch_sweep_pass<UPD>(h, c, a);
+}
+
+void enqueue_metropolis(csmc_handle *h, bool cone) {
+    if (cone) enqueue_sweep<UPD_CONE>(h, h->metro_ctr); else enqueue_sweep<UPD_METRO>(h, h->metro_ctr);
+    h->metro_ctr++;
+}
+
+// energy + magnetisation of every local replica into meas[(R) x 8]
+void enqueue_measure(csmc_handle *h, double *meas, bool write_energy) {
+    for (int c = 0; c < h->hm.n_colours; ++c) {
+        const int nseg = h->hm.colour_seg_begin[c + 1] - h->hm.colour_seg_begin[c];
+        dim3 grid(h->pass_blocks[c], nseg, h->R), block(TPB);
+        if (h->large) {
+            if (h->hm.structured) k_energy<PassLarge, true><<<grid, block, 0, h->stream>>>(h->pl[c], h->d_partials, h->n_partials, h->partial_base[c]);
+            else k_energy<PassLarge, false><<<grid, block, 0, h->stream>>>(h->pl[c], h->d_partials, h->n_partials, h->partial_base[c]);
+        } else {
+            if (h->hm.structured) k_energy<PassSmall, true><<<grid, block, 0, h->stream>>>(h->ps[c], h->d_partials, h->n_partials, h->partial_base[c]);
+            else k_energy<PassSmall, false><<<grid, block, 0, h->stream>>>(h->ps[c], h->d_partials, h->n_partials, h->partial_base[c]);
+        }
+        h->launches++;
+    }
+    k_reduce_partials<<<h->R, 256, 0, h->stream>>>(h->d_partials, h->n_partials, h->d_acc, meas, write_energy ? 1 : 0);
+    h->launches++;
+}
+
+void enqueue_eval(csmc_handle *h, int rep, int what, double *out) {
+    for (int c = 0; c < h->hm.n_colours; ++c) {
+        const int nseg = h->hm.colour_seg_begin[c + 1] - h->hm.colour_seg_begin[c];
+        dim3 grid(h->pass_blocks[c], nseg, 1), block(TPB);
+        if (h->large) {
+            if (h->hm.structured) k_eval<PassLarge, true><<<grid, block, 0, h->stream>>>(h->pl[c], rep, what, out);
+            else k_eval<PassLarge, false><<<grid, block, 0, h->stream>>>(h->pl[c], rep, what, out);
+        } else {
+            if (h->hm.structured) k_eval<PassSmall, true><<<grid, block, 0, h->stream>>>(h->ps[c], rep, what, out);
+            else k_eval<PassSmall, false><<<grid, block, 0, h->stream>>>(h->ps[c], rep, what, out);
+        }
+        h->launches++;
+    }
+}
+
+int finish(csmc_handle *h) {
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    return CSMC_OK;
+}
+
+int check_metropolis(csmc_handle *h) {
+    if (h->hm.self_loop)
+        return fail(h, CSMC_ERR_UNSUPPORTED,
+                    "Metropolis: a site interacts with itself on this lattice (offset is a multiple of the "
+                    "lattice size); the single-field dE is not valid there");
+    return CSMC_OK;
+}
+
+int upload_T(csmc_handle *h, const double *T) {
+    for (int r = 0; r < h->R; ++r)
+        if (!(T[r] > 0.0)) return fail(h, CSMC_ERR_INVALID, "temperatures must be > 0");
+    CK(cudaMemcpyAsync(h->d_T, T, sizeof(double) * h->R, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));  // T is caller memory: do not retain the pointer
+    return CSMC_OK;
+}
+
+PtState pt_state(csmc_handle *h) {
+    PtState st{};
+    st.n_slots = h->n_slots; st.n_local = h->R; st.replica_base = h->replica_base;
+    st.T_slot = h->d_T_slot; st.slot_of_rep = h->d_slot_of_rep; st.rep_of_slot = h->d_rep_of_slot;
+    st.meas_all = h->d_meas_all; st.E_last = h->d_E_last; st.acc_prev = h->d_acc_prev_pt;
+    st.acc_slot = h->d_acc_slot; st.exch_slot = h->d_exch_slot; st.T_local = h->d_T;
+    st.accepted_pairs = h->d_accepted_pairs;
+    return st;
+}
+
+void free_pt(csmc_handle *h) {
+    cudaFree(h->d_T_slot); cudaFree(h->d_meas_all); cudaFree(h->d_E_last); cudaFree(h->d_acc_prev_pt);
+    cudaFree(h->d_acc_slot); cudaFree(h->d_exch_slot); cudaFree(h->d_series_E); cudaFree(h->d_series_M);
+    cudaFree(h->d_slot_of_rep); cudaFree(h->d_rep_of_slot); cudaFree(h->d_accepted_pairs);
+    h->d_T_slot = h->d_meas_all = h->d_E_last = h->d_acc_prev_pt = h->d_acc_slot = h->d_exch_slot = nullptr;
+    h->d_series_E = h->d_series_M = nullptr;
+    h->d_slot_of_rep = h->d_rep_of_slot = h->d_accepted_pairs = nullptr;
+    h->series_cap = 0; h->n_probes = 0; h->n_slots = 0;
+}
+
+// measurement + gather across ranks into d_meas_all (in place)
+int enqueue_measure_all(csmc_handle *h, bool write_energy) {
+    double *mine = h->d_meas_all + (size_t)h->replica_base * 8;
+    enqueue_measure(h, mine, write_energy);
+    if (h->comm) {
+        if (h->n_slots != h->R * h->n_ranks || h->replica_base != h->rank * h->R)
+            return fail(h, CSMC_ERR_INVALID, "NCCL gather needs equal replica counts per rank and replica_base == rank * n_replicas");
+        CKN(g_nccl.AllGather(mine, h->d_meas_all, (size_t)h->R * 8, ncclFloat64, h->comm, h->stream));
+    }
+    return CSMC_OK;
+}
+
+}  // namespace
+
+// =========================================================================================================
+extern "C" {
+
+int32_t csmc_version(void) { return CSMC_VERSION; }
+
+const char *csmc_last_error(const csmc_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int32_t csmc_create(const csmc_model *model, const csmc_opts *opts, csmc_handle **out) {
+    csmc_handle *h = nullptr;
+    if (!model || !opts || !out) return fail(nullptr, CSMC_ERR_INVALID, "csmc_create: NULL argument");
+    *out = nullptr;
+    if (opts->n_replicas < 1 || opts->n_replicas > 65535) return fail(nullptr, CSMC_ERR_INVALID, "n_replicas must be 1..65535");
+    h = new (std::nothrow) csmc_handle();
+    if (!h) return fail(nullptr, CSMC_ERR_NOMEM, "out of host memory");
+    std::string e;
+    try {
+        e = build_host_model(model, opts->flags, h->hm);
+    } catch (const std::exception &ex) {
+        e = std::string("model build failed: ") + ex.what();
+    }
+    if (!e.empty()) { delete h; return fail(nullptr, CSMC_ERR_INVALID, e); }
+
+    // deep copy of the model
+    const HostModel &hm = h->hm;
+    const int D = hm.D;
+    h->model = *model;
+    h->m_field.assign(model->field, model->field + 3 * hm.n_basis);
+    h->m_onsite.assign(model->onsite, model->onsite + 9 * hm.n_basis);
+    if (hm.N2) { h->m_bilB.assign(model->bil_basis, model->bil_basis + 2 * hm.N2); h->m_bilO.assign(model->bil_offset, model->bil_offset + D * hm.N2); h->m_bilJ.assign(model->bil_matrix, model->bil_matrix + 9 * hm.N2); }
+    if (hm.N3) { h->m_cubB.assign(model->cub_basis, model->cub_basis + 3 * hm.N3); h->m_cubO.assign(model->cub_offset, model->cub_offset + 2 * D * hm.N3); h->m_cubT.assign(model->cub_tensor, model->cub_tensor + 27 * hm.N3); }
+    if (hm.N4) { h->m_quarB.assign(model->quar_basis, model->quar_basis + 4 * hm.N4); h->m_quarO.assign(model->quar_offset, model->quar_offset + 3 * D * hm.N4); h->m_quarT.assign(model->quar_tensor, model->quar_tensor + 81 * hm.N4); }
+    h->model.field = h->m_field.data(); h->model.onsite = h->m_onsite.data();
+    h->model.bil_basis = h->m_bilB.data(); h->model.bil_offset = h->m_bilO.data(); h->model.bil_matrix = h->m_bilJ.data();
+    h->model.cub_basis = h->m_cubB.data(); h->model.cub_offset = h->m_cubO.data(); h->model.cub_tensor = h->m_cubT.data();
+    h->model.quar_basis = h->m_quarB.data(); h->model.quar_offset = h->m_quarO.data(); h->model.quar_tensor = h->m_quarT.data();
+
+    h->device = opts->device; h->R = opts->n_replicas; h->replica_base = opts->replica_base;
+    h->seed = opts->seed; h->flags = opts->flags;
+    h->large = hm.need_large;
+
+    auto bail = [&](int code, const std::string &msg) { csmc_destroy(h); return fail(nullptr, code, msg); };
+#define CKC(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return bail(CSMC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+    CKC(cudaSetDevice(h->device));
+    if (opts->stream) { h->stream = (cudaStream_t)opts->stream; h->own_stream = false; }
+    else { CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+
+    const size_t npad = hm.npad;
+    CKC(dalloc(&h->d_spins, (size_t)h->R * 3 * npad));
+    CKC(cudaMemsetAsync(h->d_spins, 0, sizeof(double) * h->R * 3 * npad, h->stream));
+    CKC(dalloc(&h->d_stage, (size_t)3 * hm.N));
+    CKC(dalloc(&h->d_out, (size_t)3 * hm.N));
+    CKC(dalloc(&h->d_nbr, hm.nbr.size()));
+    CKC(cudaMemcpyAsync(h->d_nbr, hm.nbr.data(), sizeof(int32_t) * hm.nbr.size(), cudaMemcpyHostToDevice, h->stream));
+    CKC(dalloc(&h->d_ref_of_pos, npad));
+    CKC(cudaMemcpyAsync(h->d_ref_of_pos, hm.ref_of_pos.data(), sizeof(int32_t) * npad, cudaMemcpyHostToDevice, h->stream));
+    CKC(dalloc(&h->d_T, h->R)); CKC(dalloc(&h->d_sigma, h->R));
+    CKC(dalloc(&h->d_acc, h->R)); CKC(dalloc(&h->d_acc_prev, h->R)); CKC(dalloc(&h->d_ctr, 1));
+    CKC(cudaMemsetAsync(h->d_acc, 0, sizeof(unsigned long long) * h->R, h->stream));
+    CKC(cudaMemsetAsync(h->d_acc_prev, 0, sizeof(unsigned long long) * h->R, h->stream));
+    CKC(cudaMemsetAsync(h->d_ctr, 0, sizeof(unsigned long long), h->stream));
+    {
+        std::vector<double> ones(h->R, 1.0), sig(h->R, 60.0);
+        CKC(cudaMemcpyAsync(h->d_T, ones.data(), sizeof(double) * h->R, cudaMemcpyHostToDevice, h->stream));
+        CKC(cudaMemcpyAsync(h->d_sigma, sig.data(), sizeof(double) * h->R, cudaMemcpyHostToDevice, h->stream));
+        CKC(cudaStreamSynchronize(h->stream));
+    }
+    h->acc_base.assign(h->R, 0ULL);
+
+    // per-colour launch geometry and parameter blocks
+    h->pass_blocks.assign(hm.n_colours, 1);
+    h->partial_base.assign(hm.n_colours, 0);
+    h->n_partials = 0;
+    for (int c = 0; c < hm.n_colours; ++c) {
+        int mx = 1;
+        for (int s = hm.colour_seg_begin[c]; s < hm.colour_seg_begin[c + 1]; ++s) mx = std::max(mx, hm.segs[s].count);
+        h->pass_blocks[c] = (mx + TPB - 1) / TPB;
+        h->partial_base[c] = h->n_partials;
+        h->n_partials += h->pass_blocks[c] * (hm.colour_seg_begin[c + 1] - hm.colour_seg_begin[c]);
+    }
+    CKC(dalloc(&h->d_partials, (size_t)h->R * h->n_partials * 4));
+    if (h->large) h->pl.resize(hm.n_colours); else h->ps.resize(hm.n_colours);
+    for (int c = 0; c < hm.n_colours; ++c) {
+        std::string pe;
+        if (h->large) {
+            pe = fill_pass_params(hm, c, h->pl[c]);
+            h->pl[c].spins = h->d_spins; h->pl[c].nbr = h->d_nbr; h->pl[c].ref_of_pos = h->d_ref_of_pos;
+        } else {
+            pe = fill_pass_params(hm, c, h->ps[c]);
+            h->ps[c].spins = h->d_spins; h->ps[c].nbr = h->d_nbr; h->ps[c].ref_of_pos = h->d_ref_of_pos;
+        }
+        if (!pe.empty()) return bail(CSMC_ERR_UNSUPPORTED, pe);
+    }
+#undef CKC
+    *out = h;
+    return CSMC_OK;
+}
+
+int32_t csmc_plan(const csmc_model *model, int32_t flags, int32_t *colour, int32_t *n_colours,
+                  int32_t *structured, int32_t *storage_pos) {
+    if (!model) return fail(nullptr, CSMC_ERR_INVALID, "csmc_plan: NULL model");
+    HostModel hm;
+    std::string e;
+    try {
+        e = build_host_model(model, flags, hm);
+    } catch (const std::exception &ex) {
+        e = std::string("model build failed: ") + ex.what();
+    }
+    if (!e.empty()) return fail(nullptr, CSMC_ERR_INVALID, e);
+    if (colour) std::memcpy(colour, hm.colour_of_site.data(), sizeof(int32_t) * hm.N);
+    if (storage_pos) std::memcpy(storage_pos, hm.pos_of_ref.data(), sizeof(int32_t) * hm.N);
+    if (n_colours) *n_colours = hm.n_colours;
+    if (structured) *structured = hm.structured ? 1 : 0;
+    return CSMC_OK;
+}
+
+int32_t csmc_destroy(csmc_handle *h) {
+    if (!h) return CSMC_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->cycle_graph) cudaGraphExecDestroy(h->cycle_graph);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    free_pt(h);
+    cudaFree(h->d_spins); cudaFree(h->d_stage); cudaFree(h->d_out); cudaFree(h->d_nbr); cudaFree(h->d_ref_of_pos);
+    cudaFree(h->d_T); cudaFree(h->d_sigma); cudaFree(h->d_acc); cudaFree(h->d_acc_prev); cudaFree(h->d_ctr);
+    cudaFree(h->d_partials);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return CSMC_OK;
+}
+
+#define NEED(h_) do { if (!(h_)) return CSMC_ERR_INVALID; } while (0)
+#define NEEDARG(h_, p_) do { if (!(p_)) return fail((csmc_handle *)(h_), CSMC_ERR_INVALID, std::string(__func__) + ": NULL argument"); } while (0)
+
+int32_t csmc_n_sites(const csmc_handle *h, int64_t *n) { NEED(h); NEEDARG(h, n); *n = h->hm.N; return CSMC_OK; }
+int32_t csmc_n_replicas(const csmc_handle *h, int32_t *r) { NEED(h); NEEDARG(h, r); *r = h->R; return CSMC_OK; }
+int32_t csmc_n_colours(const csmc_handle *h, int32_t *c) { NEED(h); NEEDARG(h, c); *c = h->hm.n_colours; return CSMC_OK; }
+int32_t csmc_is_structured(const csmc_handle *h, int32_t *f) { NEED(h); NEEDARG(h, f); *f = h->hm.structured ? 1 : 0; return CSMC_OK; }
+int32_t csmc_launch_count(const csmc_handle *h, int64_t *n) { NEED(h); NEEDARG(h, n); *n = h->launches; return CSMC_OK; }
+
+int32_t csmc_get_colouring(const csmc_handle *h, int32_t *colour) {
+    NEED(h); NEEDARG(h, colour);
+    std::memcpy(colour, h->hm.colour_of_site.data(), sizeof(int32_t) * h->hm.N);
+    return CSMC_OK;
+}
+
+int32_t csmc_get_tables(const csmc_handle *h, int64_t *bil, int64_t *cub, int64_t *quar) {
+    NEED(h);
+    reference_tables(&h->model, bil, cub, quar);
+    return CSMC_OK;
+}
+
+int32_t csmc_set_spins(csmc_handle *h, int32_t replica, const double *spins) {
+    NEED(h); NEEDARG(h, spins);
+    if (replica < 0 || replica >= h->R) return fail(h, CSMC_ERR_INVALID, "replica out of range");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->d_stage, spins, sizeof(double) * 3 * h->hm.N, cudaMemcpyHostToDevice, h->stream));
+    const int npad = h->hm.npad;
+    k_aos_to_soa<<<(npad + 255) / 256, 256, 0, h->stream>>>(h->d_stage, h->d_spins + (size_t)replica * 3 * npad, h->d_ref_of_pos, npad);
+    h->launches++;
+    return finish(h);
+}
+
+int32_t csmc_get_spins(csmc_handle *h, int32_t replica, double *spins) {
+    NEED(h); NEEDARG(h, spins);
+    if (replica < 0 || replica >= h->R) return fail(h, CSMC_ERR_INVALID, "replica out of range");
+    CK(cudaSetDevice(h->device));
+    const int npad = h->hm.npad;
+    k_soa_to_aos<<<(npad + 255) / 256, 256, 0, h->stream>>>(h->d_spins + (size_t)replica * 3 * npad, h->d_stage, h->d_ref_of_pos, npad);
+    h->launches++;
+    CK(cudaMemcpyAsync(spins, h->d_stage, sizeof(double) * 3 * h->hm.N, cudaMemcpyDeviceToHost, h->stream));
+    return finish(h);
+}
+
+int32_t csmc_randomize_spins(csmc_handle *h, uint64_t seed) {
+    NEED(h);
+    CK(cudaSetDevice(h->device));
+    const int npad = h->hm.npad;
+    dim3 grid((npad + 255) / 256, h->R);
+    k_randomize<<<grid, 256, 0, h->stream>>>(h->d_spins, h->d_ref_of_pos, npad, 3LL * npad, h->hm.S, seed, h->replica_base);
+    h->launches++;
+    return finish(h);
+}
+
+int32_t csmc_local_field_all(csmc_handle *h, int32_t replica, double *out) {
+    NEED(h); NEEDARG(h, out);
+    if (replica < 0 || replica >= h->R) return fail(h, CSMC_ERR_INVALID, "replica out of range");
+    CK(cudaSetDevice(h->device));
+    enqueue_eval(h, replica, 0, h->d_out);
+    CK(cudaMemcpyAsync(out, h->d_out, sizeof(double) * 3 * h->hm.N, cudaMemcpyDeviceToHost, h->stream));
+    return finish(h);
+}
+
+int32_t csmc_local_field(csmc_handle *h, int32_t replica, int64_t site, double out[3]) {
+    NEED(h); NEEDARG(h, out);
+    if (replica < 0 || replica >= h->R) return fail(h, CSMC_ERR_INVALID, "replica out of range");
+    if (site < 1 || site > h->hm.N) return fail(h, CSMC_ERR_INVALID, "site out of range (1-based)");
+    CK(cudaSetDevice(h->device));
+    enqueue_eval(h, replica, 0, h->d_out);
+    CK(cudaMemcpyAsync(out, h->d_out + 3 * (site - 1), sizeof(double) * 3, cudaMemcpyDeviceToHost, h->stream));
+    return finish(h);
+}
+
+int32_t csmc_site_energy_all(csmc_handle *h, int32_t replica, double *out) {
+    NEED(h); NEEDARG(h, out);
+    if (replica < 0 || replica >= h->R) return fail(h, CSMC_ERR_INVALID, "replica out of range");
+    CK(cudaSetDevice(h->device));
+    enqueue_eval(h, replica, 1, h->d_out);
+    CK(cudaMemcpyAsync(out, h->d_out, sizeof(double) * h->hm.N, cudaMemcpyDeviceToHost, h->stream));
+    return finish(h);
+}
+
+static int measure_to_host(csmc_handle *h, std::vector<double> &rec) {
+    CK(cudaSetDevice(h->device));
+    double *d_meas = nullptr;
+    CK(dalloc(&d_meas, (size_t)h->R * 8));
+    enqueue_measure(h, d_meas, true);
+    rec.resize((size_t)h->R * 8);
+    cudaError_t e = cudaMemcpyAsync(rec.data(), d_meas, sizeof(double) * h->R * 8, cudaMemcpyDeviceToHost, h->stream);
+    int rc = e == cudaSuccess ? finish(h) : fail(h, CSMC_ERR_CUDA, cudaGetErrorString(e));
+    cudaFree(d_meas);
+    return rc;
+}
+
+int32_t csmc_total_energy(csmc_handle *h, double *E) {
+    NEED(h); NEEDARG(h, E);
+    std::vector<double> rec;
+    int rc = measure_to_host(h, rec);
+    if (rc) return rc;
+    for (int r = 0; r < h->R; ++r) E[r] = rec[8 * r];
+    return CSMC_OK;
+}
+
+int32_t csmc_magnetization(csmc_handle *h, double *M3) {
+    NEED(h); NEEDARG(h, M3);
+    std::vector<double> rec;
+    int rc = measure_to_host(h, rec);
+    if (rc) return rc;
+    for (int r = 0; r < h->R; ++r) for (int k = 0; k < 3; ++k) M3[3 * r + k] = rec[8 * r + 1 + k];
+    return CSMC_OK;
+}
+
+int32_t csmc_overrelax(csmc_handle *h, int32_t n_sweeps) {
+    NEED(h);
+    CK(cudaSetDevice(h->device));
+    for (int s = 0; s < n_sweeps; ++s) enqueue_sweep<UPD_OR>(h);
+    return finish(h);
+}
+
+int32_t csmc_deterministic(csmc_handle *h, int32_t n_sweeps) {
+    NEED(h);
+    CK(cudaSetDevice(h->device));
+    for (int s = 0; s < n_sweeps; ++s) enqueue_sweep<UPD_DET>(h);
+    return finish(h);
+}
+
+int32_t csmc_set_temperatures(csmc_handle *h, const double *T) {
+    NEED(h); NEEDARG(h, T);
+    CK(cudaSetDevice(h->device));
+    return upload_T(h, T);
+}
+
+int32_t csmc_get_accepted(csmc_handle *h, double *accepted, int32_t reset) {
+    NEED(h); NEEDARG(h, accepted);
+    CK(cudaSetDevice(h->device));
+    std::vector<unsigned long long> now(h->R);
+    CK(cudaMemcpyAsync(now.data(), h->d_acc, sizeof(unsigned long long) * h->R, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int r = 0; r < h->R; ++r) { accepted[r] = (double)(now[r] - h->acc_base[r]); if (reset) h->acc_base[r] = now[r]; }
+    return CSMC_OK;
+}
+
+int32_t csmc_metropolis(csmc_handle *h, const double *T, int32_t n_sweeps, double *accepted) {
+    NEED(h); NEEDARG(h, T);
+    int rc = check_metropolis(h); if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    rc = upload_T(h, T); if (rc) return rc;
+    std::vector<double> before(h->R), after(h->R);
+    if (accepted) { rc = csmc_get_accepted(h, before.data(), 0); if (rc) return rc; }
+    for (int s = 0; s < n_sweeps; ++s) enqueue_metropolis(h, false);
+    rc = finish(h); if (rc) return rc;
+    if (accepted) {
+        rc = csmc_get_accepted(h, after.data(), 0); if (rc) return rc;
+        for (int r = 0; r < h->R; ++r) accepted[r] = after[r] - before[r];
+    }
+    return CSMC_OK;
+}
+
+int32_t csmc_metropolis_cone(csmc_handle *h, const double *T, double *sigma, int32_t adapt, int32_t n_sweeps, double *accepted) {
+    NEED(h); NEEDARG(h, T); NEEDARG(h, sigma);
+    int rc = check_metropolis(h); if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    rc = upload_T(h, T); if (rc) return rc;
+    CK(cudaMemcpyAsync(h->d_sigma, sigma, sizeof(double) * h->R, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_acc_prev, h->d_acc, sizeof(unsigned long long) * h->R, cudaMemcpyDeviceToDevice, h->stream));
+    std::vector<double> before(h->R), after(h->R);
+    if (accepted) { rc = csmc_get_accepted(h, before.data(), 0); if (rc) return rc; }
+    for (int s = 0; s < n_sweeps; ++s) {
+        enqueue_metropolis(h, true);
+        if (adapt) { k_adapt_sigma<<<(h->R + 127) / 128, 128, 0, h->stream>>>(h->d_sigma, h->d_acc, h->d_acc_prev, (double)h->hm.N, h->R); h->launches++; }
+    }
+    CK(cudaMemcpyAsync(sigma, h->d_sigma, sizeof(double) * h->R, cudaMemcpyDeviceToHost, h->stream));
+    rc = finish(h); if (rc) return rc;
+    if (accepted) {
+        rc = csmc_get_accepted(h, after.data(), 0); if (rc) return rc;
+        for (int r = 0; r < h->R; ++r) accepted[r] = after[r] - before[r];
+    }
+    return CSMC_OK;
+}
+
+// ---- cycles: CUDA-graph replay of (or_per_cycle OR sweeps + metro_per_cycle Metropolis sweeps) --------
+static int build_cycle_graph(csmc_handle *h, int orc, int mc) {
+    if (h->cycle_graph && h->cycle_or == orc && h->cycle_metro == mc) return CSMC_OK;
+    if (h->cycle_graph) { cudaGraphExecDestroy(h->cycle_graph); h->cycle_graph = nullptr; }
+    cudaGraph_t graph = nullptr;
+    const long long before = h->launches;
+    CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    for (int s = 0; s < orc; ++s) enqueue_sweep<UPD_OR>(h);
+    for (int s = 0; s < mc; ++s) enqueue_sweep<UPD_METRO>(h, (unsigned long long)s, true);
+    if (mc > 0) { k_add_u64<<<1, 1, 0, h->stream>>>(h->d_ctr, (unsigned long long)mc); h->launches++; }
+    CK(cudaStreamEndCapture(h->stream, &graph));
+    h->launches = before;  // capture enqueues nothing
+    cudaError_t e = cudaGraphInstantiate(&h->cycle_graph, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(h, CSMC_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    h->cycle_or = orc; h->cycle_metro = mc;
+    return CSMC_OK;
+}
+
+static long long cycle_launches(const csmc_handle *h, int orc, int mc) {
+    return (long long)(orc + mc) * h->hm.n_colours + (mc > 0 ? 1 : 0);
+}
+
+int32_t csmc_cycles_async(csmc_handle *h, int64_t n_cycles, int32_t orc, int32_t mc) {
+    NEED(h);
+    if (n_cycles < 0 || orc < 0 || mc < 0) return fail(h, CSMC_ERR_INVALID, "negative cycle counts");
+    if (mc > 0) { int rc = check_metropolis(h); if (rc) return rc; }
+    CK(cudaSetDevice(h->device));
+    if (h->flags & CSMC_FLAG_NO_GRAPH) {
+        for (int64_t c = 0; c < n_cycles; ++c) {
+            for (int s = 0; s < orc; ++s) enqueue_sweep<UPD_OR>(h);
+            for (int s = 0; s < mc; ++s) enqueue_metropolis(h, false);
+        }
+        CK(cudaGetLastError());
+        return CSMC_OK;
+    }
+    // the graph reads the sweep counter from device memory: bring it up to date first
+    CK(cudaMemcpyAsync(h->d_ctr, &h->metro_ctr, sizeof(unsigned long long), cudaMemcpyHostToDevice, h->stream));
+    int rc = build_cycle_graph(h, orc, mc); if (rc) return rc;
+    for (int64_t c = 0; c < n_cycles; ++c) CK(cudaGraphLaunch(h->cycle_graph, h->stream));
+    h->metro_ctr += (unsigned long long)n_cycles * mc;
+    h->launches += n_cycles * cycle_launches(h, orc, mc);
+    CK(cudaGetLastError());
+    return CSMC_OK;
+}
+
+int32_t csmc_sync(csmc_handle *h) { NEED(h); CK(cudaSetDevice(h->device)); return finish(h); }
+
+int32_t csmc_anneal_temperature(csmc_handle *h, const double *T, int64_t t_thermalization, int32_t rate, double *accepted) {
+    NEED(h); NEEDARG(h, T);
+    if (rate < 0) return fail(h, CSMC_ERR_INVALID, "overrelaxation_rate must be >= 0");
+    int rc = check_metropolis(h); if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    rc = upload_T(h, T); if (rc) return rc;
+    std::vector<double> before(h->R), after(h->R);
+    if (accepted) { rc = csmc_get_accepted(h, before.data(), 0); if (rc) return rc; }
+    const int64_t iters = t_thermalization - 1;  // src/monte_carlo.jl:169-172: t = 1 .. t_thermalization-1
+    if (iters > 0) {
+        if (rate == 0) {
+            rc = csmc_cycles_async(h, iters, 0, 1); if (rc) return rc;       // :178-180
+        } else {
+            // t % rate == 0 closes a block of `rate` OR sweeps followed by one Metropolis sweep (:173-177)
+            rc = csmc_cycles_async(h, iters / rate, rate, 1); if (rc) return rc;
+            rc = csmc_cycles_async(h, 1, (int32_t)(iters % rate), 0); if (rc) return rc;
+        }
+    }
+    rc = finish(h); if (rc) return rc;
+    if (accepted) {
+        rc = csmc_get_accepted(h, after.data(), 0); if (rc) return rc;
+        for (int r = 0; r < h->R; ++r) accepted[r] = after[r] - before[r];
+    }
+    return CSMC_OK;
+}
+
+// ---- parallel tempering ----------------------------------------------------------------------------------
+int32_t csmc_pt_init(csmc_handle *h, int32_t n_slots, const double *T_all) {
+    NEED(h); NEEDARG(h, T_all);
+    if (n_slots < h->replica_base + h->R) return fail(h, CSMC_ERR_INVALID, "n_slots smaller than replica_base + n_replicas");
+    for (int s = 0; s < n_slots; ++s) if (!(T_all[s] > 0.0)) return fail(h, CSMC_ERR_INVALID, "temperatures must be > 0");
+    CK(cudaSetDevice(h->device));
+    free_pt(h);
+    h->n_slots = n_slots;
+    CK(dalloc(&h->d_T_slot, n_slots)); CK(dalloc(&h->d_meas_all, (size_t)n_slots * 8)); CK(dalloc(&h->d_E_last, n_slots));
+    CK(dalloc(&h->d_acc_prev_pt, n_slots)); CK(dalloc(&h->d_acc_slot, n_slots)); CK(dalloc(&h->d_exch_slot, n_slots));
+    CK(dalloc(&h->d_slot_of_rep, n_slots)); CK(dalloc(&h->d_rep_of_slot, n_slots)); CK(dalloc(&h->d_accepted_pairs, n_slots));
+    std::vector<int> ident(n_slots);
+    for (int s = 0; s < n_slots; ++s) ident[s] = s;
+    CK(cudaMemcpyAsync(h->d_T_slot, T_all, sizeof(double) * n_slots, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_slot_of_rep, ident.data(), sizeof(int) * n_slots, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_rep_of_slot, ident.data(), sizeof(int) * n_slots, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->d_meas_all, 0, sizeof(double) * 8 * n_slots, h->stream));
+    CK(cudaMemsetAsync(h->d_E_last, 0, sizeof(double) * n_slots, h->stream));
+    CK(cudaMemsetAsync(h->d_acc_prev_pt, 0, sizeof(double) * n_slots, h->stream));
+    CK(cudaMemsetAsync(h->d_acc_slot, 0, sizeof(double) * n_slots, h->stream));
+    CK(cudaMemsetAsync(h->d_exch_slot, 0, sizeof(double) * n_slots, h->stream));
+    CK(cudaMemsetAsync(h->d_accepted_pairs, 0, sizeof(int) * n_slots, h->stream));
+    CK(cudaMemcpyAsync(h->d_T, T_all + h->replica_base, sizeof(double) * h->R, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    // E = total_energy(mc.lattice) before the loop (src/monte_carlo.jl:265); acc_prev = current counters
+    int rc = enqueue_measure_all(h, true); if (rc) return rc;
+    PtState st = pt_state(h);
+    k_pt_update<<<(n_slots + 127) / 128, 128, 0, h->stream>>>(st); h->launches++;
+    CK(cudaMemsetAsync(h->d_acc_slot, 0, sizeof(double) * n_slots, h->stream));
+    return finish(h);
+}
+
+int32_t csmc_comm_unique_id(uint8_t id[128]) {
+    if (!id) return CSMC_ERR_INVALID;
+    if (!load_nccl()) return fail(nullptr, CSMC_ERR_NCCL, g_nccl.err);
+    ncclUniqueId u;
+    if (g_nccl.GetUniqueId(&u) != 0) return fail(nullptr, CSMC_ERR_NCCL, "ncclGetUniqueId failed");
+    std::memcpy(id, u.internal, 128);
+    return CSMC_OK;
+}
+
+int32_t csmc_comm_init(csmc_handle *h, int32_t n_ranks, int32_t rank, const uint8_t id[128]) {
+    NEED(h); NEEDARG(h, id);
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(h, CSMC_ERR_INVALID, "bad rank / n_ranks");
+    if (!load_nccl()) return fail(h, CSMC_ERR_NCCL, g_nccl.err);
+    CK(cudaSetDevice(h->device));
+    if (h->comm) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
+    ncclUniqueId u;
+    std::memcpy(u.internal, id, 128);
+    CKN(g_nccl.CommInitRank(&h->comm, n_ranks, u, rank));
+    h->n_ranks = n_ranks; h->rank = rank;
+    return CSMC_OK;
+}
+
+static int ensure_series(csmc_handle *h, long long need) {
+    if (need <= h->series_cap) return CSMC_OK;
+    long long cap = std::max<long long>(need, std::max<long long>(1024, 2 * h->series_cap));
+    double *nE = nullptr, *nM = nullptr;
+    CK(dalloc(&nE, (size_t)cap * h->n_slots)); CK(dalloc(&nM, (size_t)cap * h->n_slots));
+    if (h->n_probes > 0) {
+        CK(cudaMemcpyAsync(nE, h->d_series_E, sizeof(double) * h->n_probes * h->n_slots, cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaMemcpyAsync(nM, h->d_series_M, sizeof(double) * h->n_probes * h->n_slots, cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    cudaFree(h->d_series_E); cudaFree(h->d_series_M);
+    h->d_series_E = nE; h->d_series_M = nM; h->series_cap = cap;
+    return CSMC_OK;
+}
+
+int32_t csmc_pt_run(csmc_handle *h, const csmc_pt_params *p, int64_t sweep_begin, int64_t sweep_end) {
+    NEED(h); NEEDARG(h, p);
+    if (h->n_slots == 0) return fail(h, CSMC_ERR_INVALID, "csmc_pt_init has not been called");
+    if (p->swap_rate < 1 || p->probe_rate < 1 || p->overrelaxation_rate < 0) return fail(h, CSMC_ERR_INVALID, "bad PT parameters");
+    int rc = check_metropolis(h); if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    const int rate = p->overrelaxation_rate;
+    const int dosweep = rate == 0 ? 1 : rate;                                   // src/monte_carlo.jl:289-293
+    // series capacity for the probes of this chunk
+    long long probes = 0;
+    for (int64_t s = std::max<int64_t>(sweep_begin, p->t_thermalization); s < sweep_end; ++s) if (s % p->probe_rate == 0) ++probes;
+    rc = ensure_series(h, h->n_probes + probes); if (rc) return rc;
+    PtState st = pt_state(h);
+    const int nb = (h->n_slots + 127) / 128;
+    for (int64_t sweep = sweep_begin; sweep < sweep_end; ++sweep) {
+        if (rate != 0) enqueue_sweep<UPD_OR>(h);                                // :298-300
+        const bool metro = (sweep % dosweep == 0);
+        if (metro) {                                                            // :302-305
+            enqueue_metropolis(h, false);
+            rc = enqueue_measure_all(h, true); if (rc) return rc;
+            k_pt_update<<<nb, 128, 0, h->stream>>>(st); h->launches++;
+            if (h->n_slots > 1 && sweep % p->swap_rate == 0) {                  // :308-349
+                const long long k = sweep / p->swap_rate;
+                k_pt_exchange<<<1, 128, 0, h->stream>>>(st, (int)(k % 2), (unsigned long long)k, h->seed); h->launches++;
+            }
+        }
+        if (sweep >= p->t_thermalization && sweep % p->probe_rate == 0) {       // :353,368-370
+            if (!metro) { rc = enqueue_measure_all(h, false); if (rc) return rc; }
+            k_pt_probe<<<nb, 128, 0, h->stream>>>(st, h->d_series_E, h->d_series_M, h->n_probes); h->launches++;
+            h->n_probes++;
+        }
+        if ((sweep & 63) == 63) CK(cudaGetLastError());
+    }
+    return finish(h);
+}
+
+int32_t csmc_pt_exchange(csmc_handle *h, int32_t parity, int32_t *accepted_pairs) {
+    NEED(h);
+    if (h->n_slots == 0) return fail(h, CSMC_ERR_INVALID, "csmc_pt_init has not been called");
+    CK(cudaSetDevice(h->device));
+    int rc = enqueue_measure_all(h, true); if (rc) return rc;
+    PtState st = pt_state(h);
+    k_pt_update<<<(h->n_slots + 127) / 128, 128, 0, h->stream>>>(st); h->launches++;
+    k_pt_exchange<<<1, 128, 0, h->stream>>>(st, parity & 1, (unsigned long long)(parity), h->seed); h->launches++;
+    if (accepted_pairs) CK(cudaMemcpyAsync(accepted_pairs, h->d_accepted_pairs, sizeof(int) * h->n_slots, cudaMemcpyDeviceToHost, h->stream));
+    return finish(h);
+}
+
+int32_t csmc_pt_get_slots(csmc_handle *h, int32_t *slot_of_replica) {
+    NEED(h); NEEDARG(h, slot_of_replica);
+    if (h->n_slots == 0) return fail(h, CSMC_ERR_INVALID, "csmc_pt_init has not been called");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(slot_of_replica, h->d_slot_of_rep, sizeof(int) * h->n_slots, cudaMemcpyDeviceToHost, h->stream));
+    return finish(h);
+}
+
+int32_t csmc_pt_get_series(csmc_handle *h, int64_t *n_probes, double *E, double *M) {
+    NEED(h); NEEDARG(h, n_probes);
+    if (h->n_slots == 0) return fail(h, CSMC_ERR_INVALID, "csmc_pt_init has not been called");
+    CK(cudaSetDevice(h->device));
+    const long long n = std::min<long long>(*n_probes, h->n_probes);
+    if (E && n > 0) CK(cudaMemcpyAsync(E, h->d_series_E, sizeof(double) * n * h->n_slots, cudaMemcpyDeviceToHost, h->stream));
+    if (M && n > 0) CK(cudaMemcpyAsync(M, h->d_series_M, sizeof(double) * n * h->n_slots, cudaMemcpyDeviceToHost, h->stream));
+    *n_probes = h->n_probes;
+    return finish(h);
+}
+
+int32_t csmc_pt_get_stats(csmc_handle *h, double *accepted_local, double *exchanges) {
+    NEED(h);
+    if (h->n_slots == 0) return fail(h, CSMC_ERR_INVALID, "csmc_pt_init has not been called");
+    CK(cudaSetDevice(h->device));
+    if (accepted_local) CK(cudaMemcpyAsync(accepted_local, h->d_acc_slot, sizeof(double) * h->n_slots, cudaMemcpyDeviceToHost, h->stream));
+    if (exchanges) CK(cudaMemcpyAsync(exchanges, h->d_exch_slot, sizeof(double) * h->n_slots, cudaMemcpyDeviceToHost, h->stream));
+    return finish(h);
+}
+
+}  // extern "C"

@@ -100,6 +100,13 @@ const char *csmc_last_error(const csmc_handle *h);
 int32_t csmc_create(const csmc_model *model, const csmc_opts *opts, csmc_handle **out);
 int32_t csmc_destroy(csmc_handle *h);
 
+/* Host-only planning step of csmc_create (no CUDA call, usable without a GPU): colours the
+ * interaction hypergraph and reports what csmc_create would set up.  colour[N] (reference site
+ * order, may be NULL), *n_colours, *structured (1: arithmetic-neighbour kernels apply),
+ * storage_pos[N] (may be NULL): position of each site in the colour-major device layout. */
+int32_t csmc_plan(const csmc_model *model, int32_t flags, int32_t *colour, int32_t *n_colours,
+                  int32_t *structured, int32_t *storage_pos);
+
 int32_t csmc_n_sites(const csmc_handle *h, int64_t *n);
 int32_t csmc_n_replicas(const csmc_handle *h, int32_t *r);
 int32_t csmc_n_colours(const csmc_handle *h, int32_t *c);

@@ -1,0 +1,297 @@
+"""GPU parity tests: the CUDA path (through the C-ABI of libcsmc.so) against the CPU oracle on the
+same seeded inputs.  Tolerances (BASELINE.json north_star):
+  * local fields / energies on the same configuration: <= 1e-12 relative
+    (energies relative to sum |e_i|, SURVEY.md section 7 "energy summation conditioning");
+  * overrelaxation / deterministic updates in the same colour order: <= 1e-12 per component;
+  * Metropolis with the shared Philox stream: same accept decisions, spins <= 1e-12.
+"""
+import numpy as np
+import pytest
+
+from classicalspinmc.jl_b200 import _lib
+from classicalspinmc.jl_b200._abi import FLAG_FORCE_GENERIC, FLAG_NO_GRAPH, ModelData
+from oracle import oracle as orc
+from tests import models
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+CASES = [
+    ("square-8x8", lambda: models.square_heisenberg(), (8, 8), "periodic", 1.0),
+    ("square-2x2", lambda: models.square_heisenberg(), (2, 2), "periodic", 1.0),
+    ("square-3x5", lambda: models.square_heisenberg(), (3, 5), "periodic", 1.0),
+    ("square-11x13", lambda: models.square_heisenberg(), (11, 13), "periodic", 1.0),
+    ("square-open-5x6", lambda: models.square_heisenberg(), (5, 6), "open", 1.0),
+    ("honeycomb-6x4", lambda: models.kitaev_honeycomb(J3=0.25), (6, 4), "periodic", 1.0),
+    ("pyrochlore-3x2x4", lambda: models.pyrochlore_local(), (3, 2, 4), "periodic", 0.5),
+    ("triangular-multispin-8x4", lambda: models.triangular_multispin(onsite=np.diag([0.1, -0.2, 0.3])), (8, 4), "periodic", 1.0),
+    ("triangular-multispin-open", lambda: models.triangular_multispin(), (5, 6), "open", 1.0),
+    ("mixed-basis-4x6", lambda: models.mixed_basis_multispin(), (4, 6), "periodic", 0.8),
+    ("mixed-basis-open-5x3", lambda: models.mixed_basis_multispin(), (5, 3), "open", 0.8),
+    ("chain-open-17", lambda: models.chain_heisenberg(), (17,), "open", 1.0),
+]
+IDS = [c[0] for c in CASES]
+MODES = [0, FLAG_FORCE_GENERIC]
+
+
+def _setup(builder, shape, bc, S, flags=0, n_replicas=1, seed=12345):
+    md = ModelData(builder(), shape, S, bc)
+    lat = orc.OracleLattice(md)
+    eng = _lib.Engine(md, n_replicas=n_replicas, seed=seed, flags=flags)
+    return md, lat, eng
+
+
+def test_reference_golden_values_through_the_abi():
+    # test/latticetests.jl:10-31 through libcsmc
+    import classicalspinmc.jl_b200 as csm
+    uc = csm.Square()
+    csm.addZeemanCoupling(uc, 1, np.array([1.0, 0.0, 0.0]))
+    eng = _lib.Engine(ModelData(uc, (1, 1), 1.0))
+    eng.set_spins(np.array([[1.0, 0.0, 0.0]]))
+    assert eng.total_energy()[0] == -1.0
+    assert tuple(eng.local_field(1)) == (-1.0, -0.0, -0.0)
+    eng2 = _lib.Engine(ModelData(models.square_heisenberg(h=None), (2, 2), 1.0))
+    eng2.set_spins(np.tile([1.0, 0.0, 0.0], (4, 1)))
+    assert eng2.total_energy()[0] / 4 == -2.0
+
+
+@pytest.mark.parametrize("name,builder,shape,bc,S", CASES, ids=IDS)
+def test_tables_and_layout(name, builder, shape, bc, S):
+    md, lat, eng = _setup(builder, shape, bc, S)
+    for a, b in zip(eng.tables(), lat.tables()):
+        assert np.array_equal(a, b)
+    s = lat.randomize(seed=5)
+    eng.set_spins(s)
+    assert np.array_equal(eng.get_spins(), s)          # layout round trip is bit exact
+    eng.randomize(77)
+    assert np.allclose(eng.get_spins(), lat.randomize(seed=77, replica=0), rtol=0, atol=2e-15)
+
+
+@pytest.mark.parametrize("flags", MODES, ids=["structured", "generic"])
+@pytest.mark.parametrize("name,builder,shape,bc,S", CASES, ids=IDS)
+def test_field_and_energy_parity(name, builder, shape, bc, S, flags):
+    md, lat, eng = _setup(builder, shape, bc, S, flags)
+    s = lat.randomize(seed=21)
+    eng.set_spins(s)
+    F_ref = lat.local_field_all(s)
+    F = eng.local_field_all()
+    scale = np.abs(F_ref).max() + 1e-300
+    assert np.abs(F - F_ref).max() <= TOL * scale
+    e_ref = lat.site_energy_all(s)
+    e = eng.site_energy_all()
+    assert np.abs(e - e_ref).max() <= TOL * (np.abs(e_ref).max() + 1e-300)
+    E_ref, A = lat.total_energy(s, with_abs=True)
+    E = eng.total_energy()[0]
+    assert abs(E - E_ref) <= TOL * max(A, 1e-300)
+    M_ref = lat.magnetization(s, vector=True)
+    M = eng.magnetization_vector()[0]
+    assert np.abs(M - M_ref).max() <= TOL * lat.N * S
+    # single-site query
+    p = lat.N // 2 + 1
+    assert np.abs(eng.local_field(p) - F_ref[p - 1]).max() <= TOL * scale
+
+
+@pytest.mark.parametrize("flags", MODES, ids=["structured", "generic"])
+@pytest.mark.parametrize("name,builder,shape,bc,S", CASES, ids=IDS)
+def test_overrelaxation_parity_colour_order(name, builder, shape, bc, S, flags):
+    md, lat, eng = _setup(builder, shape, bc, S, flags)
+    s = lat.randomize(seed=33)
+    eng.set_spins(s)
+    order = eng.colour_order()
+    k = 3
+    eng.overrelax(k)
+    lat.overrelax(s, order, k)
+    assert np.abs(eng.get_spins() - s).max() <= TOL * S
+
+
+@pytest.mark.parametrize("flags", MODES, ids=["structured", "generic"])
+@pytest.mark.parametrize("name,builder,shape,bc,S", CASES, ids=IDS)
+def test_deterministic_parity_colour_order(name, builder, shape, bc, S, flags):
+    md, lat, eng = _setup(builder, shape, bc, S, flags)
+    s = lat.randomize(seed=34)
+    eng.set_spins(s)
+    order = eng.colour_order()
+    eng.deterministic(2)
+    lat.deterministic(s, order, 2)
+    out = eng.get_spins()
+    assert np.abs(out - s).max() <= TOL * S
+    assert np.allclose(np.linalg.norm(out, axis=1), S, rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize("flags", MODES, ids=["structured", "generic"])
+@pytest.mark.parametrize("T", [0.05, 1.0])
+@pytest.mark.parametrize("name,builder,shape,bc,S", CASES, ids=IDS)
+def test_metropolis_same_stream_parity(name, builder, shape, bc, S, T, flags):
+    """One and two Metropolis sweeps with the shared Philox stream: identical accept decisions."""
+    if name == "square-2x2":
+        pytest.skip("L=2 periodic: duplicated neighbours are fine, covered by OR parity")
+    seed = 424242
+    md, lat, eng = _setup(builder, shape, bc, S, flags, seed=seed)
+    s = lat.randomize(seed=35)
+    eng.set_spins(s)
+    order = eng.colour_order()
+    acc_ref = 0.0
+    for sweep in range(2):
+        acc_ref += lat.metropolis_philox(s, order, T, seed, 0, sweep)
+    acc = eng.metropolis(T, 2)[0]
+    assert acc == acc_ref
+    assert np.abs(eng.get_spins() - s).max() <= TOL * S
+
+
+@pytest.mark.parametrize("name,builder,shape,bc,S", CASES[:6], ids=IDS[:6])
+def test_cone_metropolis_same_stream_parity(name, builder, shape, bc, S):
+    if name == "square-2x2":
+        pytest.skip("see above")
+    seed = 99
+    md, lat, eng = _setup(builder, shape, bc, S, seed=seed)
+    s = lat.randomize(seed=36)
+    eng.set_spins(s)
+    order = eng.colour_order()
+    sigma = 0.7
+    acc_ref = lat.metropolis_philox(s, order, 0.5, seed, 0, 0, sigma=sigma)
+    acc, sig = eng.metropolis_cone(0.5, sigma, adapt=True, n_sweeps=1)
+    assert acc[0] == acc_ref
+    assert np.abs(eng.get_spins() - s).max() <= TOL * S
+    assert abs(sig[0] - orc.adapt_sigma(sigma, acc_ref, lat.N)) <= 1e-14
+
+
+def test_multi_replica_independence_and_streams():
+    """Replicas are independent chains with distinct Philox streams keyed by the global replica id."""
+    seed = 7
+    md = ModelData(models.kitaev_honeycomb(), (6, 6), 1.0)
+    lat = orc.OracleLattice(md)
+    eng = _lib.Engine(md, n_replicas=3, seed=seed, replica_base=4)
+    T = np.array([0.3, 0.7, 1.5])
+    refs = []
+    for r in range(3):
+        s = lat.randomize(seed=100 + r)
+        eng.set_spins(s, replica=r)
+        refs.append(s)
+    order = eng.colour_order()
+    eng.overrelax(2)
+    acc = eng.metropolis(T, 1)
+    for r in range(3):
+        lat.overrelax(refs[r], order, 2)
+        a = lat.metropolis_philox(refs[r], order, T[r], seed, 4 + r, 0)
+        assert acc[r] == a
+        assert np.abs(eng.get_spins(r) - refs[r]).max() <= TOL
+    E = eng.total_energy()
+    for r in range(3):
+        E_ref, A = lat.total_energy(refs[r], with_abs=True)
+        assert abs(E[r] - E_ref) <= TOL * A
+
+
+def test_self_interaction_is_reported():
+    md = ModelData(models.square_heisenberg(), (1, 4), 1.0)   # offset (1,0) wraps onto the site itself
+    eng = _lib.Engine(md)
+    lat = orc.OracleLattice(md)
+    s = lat.randomize(seed=3)
+    eng.set_spins(s)
+    assert np.abs(eng.local_field_all() - lat.local_field_all(s)).max() <= 1e-12
+    with pytest.raises(_lib.CsmcError, match="interacts with itself"):
+        eng.metropolis(1.0, 1)
+
+
+def test_graph_and_plain_launch_agree():
+    """csmc_cycles_async: CUDA-graph replay and plain stream launches give identical chains."""
+    md = ModelData(models.square_heisenberg(), (16, 16), 1.0)
+    lat = orc.OracleLattice(md)
+    s0 = lat.randomize(seed=8)
+    outs = []
+    for flags in (0, FLAG_NO_GRAPH):
+        eng = _lib.Engine(md, seed=5, flags=flags)
+        eng.set_spins(s0)
+        eng.set_temperatures(0.8)
+        eng.cycles_async(3, 4, 1)
+        eng.cycles_async(2, 4, 1)
+        eng.sync()
+        outs.append((eng.get_spins().copy(), eng.accepted()[0]))
+    assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1]
+    # and both equal the oracle run in colour order with the same stream
+    eng = _lib.Engine(md, seed=5)
+    order = eng.colour_order()
+    s = s0.copy()
+    acc = 0.0
+    for c in range(5):
+        lat.overrelax(s, order, 4)
+        acc += lat.metropolis_philox(s, order, 0.8, 5, 0, c)
+    assert acc == outs[0][1]
+    assert np.abs(outs[0][0] - s).max() <= 1e-10   # 25 sweeps: rounding differences amplified by the dynamics
+
+
+def test_anneal_temperature_schedule_matches_reference_loop():
+    """csmc_anneal_temperature == the `while t < t_thermalization` loop of src/monte_carlo.jl:169-182."""
+    md = ModelData(models.kitaev_honeycomb(), (4, 4), 1.0)
+    lat = orc.OracleLattice(md)
+    for rate, t_th in ((3, 11), (0, 5), (10, 7)):
+        eng = _lib.Engine(md, seed=17)
+        s = lat.randomize(seed=9)
+        eng.set_spins(s)
+        order = eng.colour_order()
+        acc = eng.anneal_temperature(0.6, t_th, rate)[0]
+        ctr, acc_ref = 0, 0.0
+        for t in range(1, t_th):
+            do_metro = True
+            if rate != 0:
+                lat.overrelax(s, order, 1)
+                do_metro = (t % rate == 0)
+            if do_metro:
+                acc_ref += lat.metropolis_philox(s, order, 0.6, 17, 0, ctr)
+                ctr += 1
+        assert acc == acc_ref
+        assert np.abs(eng.get_spins() - s).max() <= 1e-10
+
+
+def test_exchange_decisions_match_oracle():
+    """csmc_pt_exchange against src/monte_carlo.jl:311-331 restated in the oracle, pair by pair."""
+    seed = 31337
+    md = ModelData(models.kitaev_honeycomb(), (4, 4), 1.0)
+    lat = orc.OracleLattice(md)
+    R = 7
+    T = np.geomspace(0.2, 2.0, R)
+    eng = _lib.Engine(md, n_replicas=R, seed=seed)
+    for r in range(R):
+        eng.set_spins(lat.randomize(seed=50 + r), replica=r)
+    eng.pt_init(T)
+    E = eng.total_energy()
+    slot_of_rep = np.arange(R)
+    for parity in (0, 1, 0, 1):
+        acc = eng.pt_exchange(parity)
+        rep_of_slot = np.argsort(slot_of_rep)
+        for a in range(parity, R - 1, 2):
+            ra, rb = rep_of_slot[a], rep_of_slot[a + 1]
+            r4 = orc.philox(seed, a, 0xFFFFFFFF, parity, 3)
+            u = float(((int(r4[0]) << 32 | int(r4[1])) >> 11) * 2.0 ** -53)
+            expect = orc.exchange_accept(T[a], E[ra], T[a + 1], E[rb], u)
+            assert bool(acc[a]) == expect
+            if expect:
+                slot_of_rep[ra], slot_of_rep[rb] = a + 1, a
+        assert np.array_equal(eng.pt_slots(), slot_of_rep)
+
+
+def test_full_size_properties_square_1024():
+    """BASELINE config C2 at full size (L=1024): size-independent properties."""
+    md = ModelData(models.square_heisenberg(), (1024, 1024), 1.0)
+    eng = _lib.Engine(md, seed=1)
+    assert eng.structured and eng.n_colours == 2
+    eng.randomize(12345)
+    s0 = eng.get_spins()
+    assert np.allclose(np.linalg.norm(s0, axis=1), 1.0, rtol=0, atol=1e-14)
+    E0 = eng.total_energy()[0]
+    F = eng.local_field_all()
+    h = np.array([0.0, 0.0, 0.1])
+    # checksum of checksums: E = sum_i s_i.(F_i - h)/2 for a bilinear + Zeeman model
+    E_chk = 0.5 * np.einsum("na,na->", s0, F - h)
+    assert abs(E0 - E_chk) <= 1e-12 * np.abs(np.einsum("na,na->n", s0, F)).sum()
+    eng.overrelax(10)
+    s1 = eng.get_spins()
+    assert np.allclose(np.linalg.norm(s1, axis=1), 1.0, rtol=0, atol=1e-12)   # reflections keep |s|
+    E1 = eng.total_energy()[0]
+    assert abs(E1 - E0) <= 1e-9 * md.n_sites                                  # microcanonical
+    assert np.abs(s1 - s0).max() > 0.1
+    acc = eng.metropolis(1.0, 1)[0]
+    assert 0.2 * md.n_sites < acc < 0.9 * md.n_sites
+    eng.deterministic(200)
+    E2 = eng.total_energy()[0] / md.n_sites
+    assert E2 < -1.5    # ferromagnet: aligning to the local field drives E/N towards -2.1
