@@ -184,7 +184,11 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     md, cfg = workload_model(args.workload, args.L)
-    stream = torch.cuda.current_stream()
+    # a real (non-NULL) stream: a NULL cudaStream_t in csmc_opts means "library creates its own", and
+    # torch.cuda.Event only sees work on the stream it is recorded on
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     eng = _lib.Engine(md, n_replicas=1, seed=12345 + rank, device=local_rank, stream=stream.cuda_stream)
     N = eng.N
     n_col = eng.n_colours

@@ -19,7 +19,8 @@ _LIB = None
 
 # every symbol include/csmc.h declares (tests check the .so exports all of them)
 EXPORTS = [
-    "csmc_version", "csmc_last_error", "csmc_create", "csmc_destroy", "csmc_plan", "csmc_n_sites",
+    "csmc_version", "csmc_last_error", "csmc_create", "csmc_destroy", "csmc_plan", "csmc_reference_tables",
+    "csmc_n_sites",
     "csmc_n_replicas", "csmc_n_colours", "csmc_get_colouring", "csmc_is_structured",
     "csmc_launch_count", "csmc_get_tables", "csmc_set_spins", "csmc_get_spins",
     "csmc_randomize_spins", "csmc_local_field", "csmc_local_field_all", "csmc_site_energy_all",
@@ -62,6 +63,7 @@ def lib():
     L.csmc_create.argtypes = [P(CsmcModel), P(CsmcOpts), P(vp)]
     L.csmc_destroy.argtypes = [vp]
     L.csmc_plan.argtypes = [P(CsmcModel), i32, vp, P(i32), P(i32), vp]
+    L.csmc_reference_tables.argtypes = [P(CsmcModel), vp, vp, vp]
     L.csmc_n_sites.argtypes = [vp, P(i64)]
     L.csmc_n_replicas.argtypes = [vp, P(i32)]
     L.csmc_n_colours.argtypes = [vp, P(i32)]
@@ -130,6 +132,19 @@ def plan(model: ModelData, flags: int = 0):
     if rc:
         raise CsmcError(f"csmc_plan failed ({rc}): {L.csmc_last_error(None).decode()}")
     return col, nc.value, bool(st.value), pos
+
+
+def reference_tables(model: ModelData):
+    """Host-only closed-form neighbour tables in the reference's layout (1-based, 0 == null)."""
+    L = lib()
+    N = model.n_sites
+    bil = np.zeros((N, model.n2), np.int64)
+    cub = np.zeros((N, model.n3, 2), np.int64)
+    quar = np.zeros((N, model.n4, 3), np.int64)
+    rc = L.csmc_reference_tables(C.byref(model.struct), _p(bil), _p(cub), _p(quar))
+    if rc:
+        raise CsmcError(f"csmc_reference_tables failed ({rc}): {L.csmc_last_error(None).decode()}")
+    return bil, cub, quar
 
 
 class Engine:

@@ -362,6 +362,20 @@ int32_t csmc_plan(const csmc_model *model, int32_t flags, int32_t *colour, int32
     return CSMC_OK;
 }
 
+int32_t csmc_reference_tables(const csmc_model *model, int64_t *bil, int64_t *cub, int64_t *quar) {
+    if (!model) return fail(nullptr, CSMC_ERR_INVALID, "csmc_reference_tables: NULL model");
+    HostModel hm;
+    std::string e;
+    try {
+        e = build_host_model(model, CSMC_FLAG_FORCE_GENERIC, hm);  // validates the model
+        if (e.empty()) reference_tables(model, bil, cub, quar);
+    } catch (const std::exception &ex) {
+        e = std::string("model build failed: ") + ex.what();
+    }
+    if (!e.empty()) return fail(nullptr, CSMC_ERR_INVALID, e);
+    return CSMC_OK;
+}
+
 int32_t csmc_destroy(csmc_handle *h) {
     if (!h) return CSMC_OK;
     cudaSetDevice(h->device);

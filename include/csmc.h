@@ -107,6 +107,11 @@ int32_t csmc_destroy(csmc_handle *h);
 int32_t csmc_plan(const csmc_model *model, int32_t flags, int32_t *colour, int32_t *n_colours,
                   int32_t *structured, int32_t *storage_pos);
 
+/* Host-only: the per-site neighbour tables of the reference's Lattice constructor in closed form
+ * (lat.bilinear_sites / cubic_sites / quartic_sites, src/lattice.jl:176-286): bil[N x N2],
+ * cub[N x N3 x 2], quar[N x N4 x 3]; 1-based, 0 == null slot.  Any pointer may be NULL. */
+int32_t csmc_reference_tables(const csmc_model *model, int64_t *bil, int64_t *cub, int64_t *quar);
+
 int32_t csmc_n_sites(const csmc_handle *h, int64_t *n);
 int32_t csmc_n_replicas(const csmc_handle *h, int32_t *r);
 int32_t csmc_n_colours(const csmc_handle *h, int32_t *c);

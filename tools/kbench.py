@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""Per-kernel timing of the pass kernels (CUDA events on the launching stream) for the BASELINE
+workloads.  Used while tuning; the judged numbers come from bench.py."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from bench import B_ALG, workload_model  # noqa: E402
+from classicalspinmc.jl_b200 import _lib  # noqa: E402
+
+
+def time_cycles(eng, stream, n, orc, mc):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eng.cycles_async(max(2, n // 10), orc, mc)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    eng.cycles_async(n, orc, mc)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workloads", default="C2,C2:4096,C3:256:8,C4:32:16,C5:512:1")
+    ap.add_argument("--n", type=int, default=200)
+    ap.add_argument("--flags", type=int, default=0)
+    args = ap.parse_args()
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    peak = 6547.8
+    for spec in args.workloads.split(","):
+        parts = spec.split(":")
+        name = parts[0]
+        L = int(parts[1]) if len(parts) > 1 else None
+        R = int(parts[2]) if len(parts) > 2 else 1
+        md, cfg = workload_model(name, L)
+        eng = _lib.Engine(md, n_replicas=R, seed=1, stream=stream.cuda_stream, flags=args.flags)
+        eng.randomize(7)
+        eng.set_temperatures(np.geomspace(0.5, 2.0, R))
+        N, C = eng.N, eng.n_colours
+        balg = B_ALG.get(C, 24.0 * (C + 1))
+        out = {"workload": spec, "N": N, "R": R, "colours": C, "structured": eng.structured}
+        for label, orc, mc in (("or", 1, 0), ("metro", 0, 1), ("cycle10+1", 10, 1)):
+            n = args.n if label != "cycle10+1" else max(args.n // 10, 5)
+            dt = time_cycles(eng, stream, n, orc, mc)
+            upd = n * (orc + mc) * N * R
+            out[label] = {"Gupd_s": upd / dt / 1e9, "us_per_pass": dt / (n * (orc + mc) * C) * 1e6,
+                          "GBs_alg": upd * balg / dt / 1e9, "frac": upd * balg / dt / 1e9 / peak}
+        print(json.dumps(out))
+        eng.close()
+
+
+if __name__ == "__main__":
+    main()
