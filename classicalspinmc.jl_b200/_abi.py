@@ -60,6 +60,8 @@ class CsmcPtParams(C.Structure):
 
 FLAG_FORCE_GENERIC = 1
 FLAG_NO_GRAPH = 2
+FLAG_JIT = 4
+FLAG_NO_JIT = 8
 
 
 def resolve_field_onsite(uc):

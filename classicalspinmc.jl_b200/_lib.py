@@ -22,7 +22,7 @@ EXPORTS = [
     "csmc_version", "csmc_last_error", "csmc_create", "csmc_destroy", "csmc_plan", "csmc_reference_tables",
     "csmc_n_sites",
     "csmc_n_replicas", "csmc_n_colours", "csmc_get_colouring", "csmc_is_structured",
-    "csmc_launch_count", "csmc_get_tables", "csmc_set_spins", "csmc_get_spins",
+    "csmc_kernel_mode", "csmc_jit_check", "csmc_launch_count", "csmc_get_tables", "csmc_set_spins", "csmc_get_spins",
     "csmc_randomize_spins", "csmc_local_field", "csmc_local_field_all", "csmc_site_energy_all",
     "csmc_total_energy", "csmc_magnetization", "csmc_overrelax", "csmc_deterministic",
     "csmc_metropolis", "csmc_metropolis_cone", "csmc_anneal_temperature", "csmc_set_temperatures",
@@ -70,6 +70,8 @@ def lib():
     L.csmc_get_colouring.argtypes = [vp, vp]
     L.csmc_is_structured.argtypes = [vp, P(i32)]
     L.csmc_launch_count.argtypes = [vp, P(i64)]
+    L.csmc_kernel_mode.argtypes = [vp, P(i32)]
+    L.csmc_jit_check.argtypes = [P(CsmcModel), i32, vp, i64, P(i64), vp, i64]
     L.csmc_get_tables.argtypes = [vp, vp, vp, vp]
     L.csmc_set_spins.argtypes = [vp, i32, vp]
     L.csmc_get_spins.argtypes = [vp, i32, vp]
@@ -132,6 +134,20 @@ def plan(model: ModelData, flags: int = 0):
     if rc:
         raise CsmcError(f"csmc_plan failed ({rc}): {L.csmc_last_error(None).decode()}")
     return col, nc.value, bool(st.value), pos
+
+
+def jit_check(model: ModelData, compile: bool = True):
+    """Host-only: generate (and optionally NVRTC-compile for sm_100a) the specialised kernel source of
+    ``model``.  Returns (source, log); raises CsmcError when generation or compilation fails."""
+    L = lib()
+    n = C.c_int64(0)
+    cap = 1 << 22
+    src = C.create_string_buffer(cap)
+    log = C.create_string_buffer(1 << 16)
+    rc = L.csmc_jit_check(C.byref(model.struct), int(compile), src, cap, C.byref(n), log, 1 << 16)
+    if rc:
+        raise CsmcError(f"csmc_jit_check failed ({rc}): {L.csmc_last_error(None).decode()}")
+    return src.value.decode(), log.value.decode()
 
 
 def reference_tables(model: ModelData):
@@ -199,6 +215,13 @@ class Engine:
         c = C.c_int32()
         self._ck(self._L.csmc_is_structured(self._h, C.byref(c)))
         return bool(c.value)
+
+    @property
+    def kernel_mode(self):
+        """0 explicit-table, 1 arithmetic-neighbour (ahead of time), 2 runtime-specialised (NVRTC)."""
+        c = C.c_int32()
+        self._ck(self._L.csmc_kernel_mode(self._h, C.byref(c)))
+        return c.value
 
     @property
     def launches(self):

@@ -90,6 +90,12 @@ struct csmc_handle {
     ncclComm_t comm = nullptr;
     int n_ranks = 1, rank = 0;
 
+    // runtime-specialised kernels
+    bool jit = false;
+    cudaLibrary_t jit_lib = nullptr;
+    std::vector<cudaKernel_t> jit_sweep[4], jit_energy;
+    std::string jit_note;
+
     // CUDA graph of one bench cycle
     cudaGraphExec_t cycle_graph = nullptr;
     int cycle_or = -1, cycle_metro = -1;
@@ -124,7 +130,10 @@ template <int UPD>
 void launch_sweep_pass(csmc_handle *h, int colour, const SweepArgs &a) {
     const int nseg = h->hm.colour_seg_begin[colour + 1] - h->hm.colour_seg_begin[colour];
     dim3 grid(h->pass_blocks[colour], nseg, h->R), block(TPB);
-    if (h->large) {
+    if (h->jit) {
+        void *args[] = {(void *)&h->d_spins, (void *)&a};
+        cudaLaunchKernel((const void *)h->jit_sweep[UPD][colour], grid, block, args, 0, h->stream);
+    } else if (h->large) {
         if (h->hm.structured) k_sweep<PassLarge, true, UPD><<<grid, block, 0, h->stream>>>(h->pl[colour], a);
         else k_sweep<PassLarge, false, UPD><<<grid, block, 0, h->stream>>>(h->pl[colour], a);
     } else {
@@ -159,7 +168,10 @@ void enqueue_measure(csmc_handle *h, double *meas, bool write_energy) {
     for (int c = 0; c < h->hm.n_colours; ++c) {
         const int nseg = h->hm.colour_seg_begin[c + 1] - h->hm.colour_seg_begin[c];
         dim3 grid(h->pass_blocks[c], nseg, h->R), block(TPB);
-        if (h->large) {
+        if (h->jit) {
+            void *args[] = {(void *)&h->d_spins, (void *)&h->d_partials, (void *)&h->n_partials, (void *)&h->partial_base[c]};
+            cudaLaunchKernel((const void *)h->jit_energy[c], grid, block, args, 0, h->stream);
+        } else if (h->large) {
             if (h->hm.structured) k_energy<PassLarge, true><<<grid, block, 0, h->stream>>>(h->pl[c], h->d_partials, h->n_partials, h->partial_base[c]);
             else k_energy<PassLarge, false><<<grid, block, 0, h->stream>>>(h->pl[c], h->d_partials, h->n_partials, h->partial_base[c]);
         } else {
@@ -339,6 +351,47 @@ int32_t csmc_create(const csmc_model *model, const csmc_opts *opts, csmc_handle 
         }
         if (!pe.empty()) return bail(CSMC_ERR_UNSUPPORTED, pe);
     }
+    // runtime specialisation
+    {
+        const bool want = !(h->flags & CSMC_FLAG_NO_JIT) && hm.structured &&
+                          ((h->flags & CSMC_FLAG_JIT) || (int64_t)hm.N * h->R >= 32768);
+        if ((h->flags & CSMC_FLAG_JIT) && !hm.structured)
+            return bail(CSMC_ERR_UNSUPPORTED, "CSMC_FLAG_JIT: the model has no periodic colouring pattern (explicit-table kernels only)");
+        if (want) {
+            std::string err, log;
+            std::vector<char> cubin;
+            try {
+                const std::string src = jit_generate_source(hm);
+                err = jit_compile(src, cubin, log);
+            } catch (const std::exception &ex) {
+                err = std::string("code generation failed: ") + ex.what();
+            }
+            if (err.empty()) {
+                cudaError_t ce = cudaLibraryLoadData(&h->jit_lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+                if (ce != cudaSuccess) err = std::string("cudaLibraryLoadData: ") + cudaGetErrorString(ce);
+            }
+            if (err.empty()) {
+                for (int u = 0; u < 4 && err.empty(); ++u) {
+                    h->jit_sweep[u].resize(hm.n_colours);
+                    for (int c = 0; c < hm.n_colours; ++c) {
+                        const std::string nm = "csmc_sweep_c" + std::to_string(c) + "_u" + std::to_string(u);
+                        if (cudaLibraryGetKernel(&h->jit_sweep[u][c], h->jit_lib, nm.c_str()) != cudaSuccess) { err = "kernel not found: " + nm; break; }
+                    }
+                }
+                h->jit_energy.resize(hm.n_colours);
+                for (int c = 0; c < hm.n_colours && err.empty(); ++c) {
+                    const std::string nm = "csmc_energy_c" + std::to_string(c);
+                    if (cudaLibraryGetKernel(&h->jit_energy[c], h->jit_lib, nm.c_str()) != cudaSuccess) err = "kernel not found: " + nm;
+                }
+            }
+            if (err.empty()) h->jit = true;
+            else {
+                cudaGetLastError();
+                if (h->flags & CSMC_FLAG_JIT) return bail(CSMC_ERR_UNSUPPORTED, "runtime specialisation failed: " + err);
+                h->jit_note = err;   // ahead-of-time kernels stay in use; csmc_kernel_mode reports it
+            }
+        }
+    }
 #undef CKC
     *out = h;
     return CSMC_OK;
@@ -381,6 +434,7 @@ int32_t csmc_destroy(csmc_handle *h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->cycle_graph) cudaGraphExecDestroy(h->cycle_graph);
+    if (h->jit_lib) cudaLibraryUnload(h->jit_lib);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     free_pt(h);
     cudaFree(h->d_spins); cudaFree(h->d_stage); cudaFree(h->d_out); cudaFree(h->d_nbr); cudaFree(h->d_ref_of_pos);
@@ -398,6 +452,36 @@ int32_t csmc_n_sites(const csmc_handle *h, int64_t *n) { NEED(h); NEEDARG(h, n);
 int32_t csmc_n_replicas(const csmc_handle *h, int32_t *r) { NEED(h); NEEDARG(h, r); *r = h->R; return CSMC_OK; }
 int32_t csmc_n_colours(const csmc_handle *h, int32_t *c) { NEED(h); NEEDARG(h, c); *c = h->hm.n_colours; return CSMC_OK; }
 int32_t csmc_is_structured(const csmc_handle *h, int32_t *f) { NEED(h); NEEDARG(h, f); *f = h->hm.structured ? 1 : 0; return CSMC_OK; }
+int32_t csmc_kernel_mode(const csmc_handle *h, int32_t *mode) {
+    NEED(h); NEEDARG(h, mode);
+    *mode = h->jit ? 2 : (h->hm.structured ? 1 : 0);
+    if (!h->jit && !h->jit_note.empty()) const_cast<csmc_handle *>(h)->err = "runtime specialisation unavailable: " + h->jit_note;
+    return CSMC_OK;
+}
+
+int32_t csmc_jit_check(const csmc_model *model, int32_t compile, char *source, int64_t source_cap,
+                       int64_t *source_len, char *log, int64_t log_cap) {
+    if (!model) return fail(nullptr, CSMC_ERR_INVALID, "csmc_jit_check: NULL model");
+    HostModel hm;
+    std::string e, src, lg;
+    try {
+        e = build_host_model(model, 0, hm);
+        if (e.empty() && !hm.structured) e = "model has no periodic colouring pattern: explicit-table kernels only";
+        if (e.empty()) src = jit_generate_source(hm);
+        if (e.empty() && compile) {
+            std::vector<char> cubin;
+            e = jit_compile(src, cubin, lg);
+        }
+    } catch (const std::exception &ex) {
+        e = std::string("jit check failed: ") + ex.what();
+    }
+    if (source_len) *source_len = (int64_t)src.size();
+    if (source && source_cap > 0) { std::strncpy(source, src.c_str(), (size_t)source_cap - 1); source[source_cap - 1] = 0; }
+    if (log && log_cap > 0) { std::strncpy(log, lg.c_str(), (size_t)log_cap - 1); log[log_cap - 1] = 0; }
+    if (!e.empty()) return fail(nullptr, CSMC_ERR_UNSUPPORTED, e);
+    return CSMC_OK;
+}
+
 int32_t csmc_launch_count(const csmc_handle *h, int64_t *n) { NEED(h); NEEDARG(h, n); *n = h->launches; return CSMC_OK; }
 
 int32_t csmc_get_colouring(const csmc_handle *h, int32_t *colour) {

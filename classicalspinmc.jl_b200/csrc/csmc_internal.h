@@ -110,6 +110,10 @@ std::string build_host_model(const csmc_model *m, int flags, HostModel &out);
 // reference-layout tables (1-based, 0 == null), for csmc_get_tables
 void reference_tables(const csmc_model *m, int64_t *bil, int64_t *cub, int64_t *quar);
 
+// runtime specialisation (jit.cpp): model -> CUDA C++ source -> sm_100a cubin (NVRTC); "" on success
+std::string jit_generate_source(const HostModel &hm);
+std::string jit_compile(const std::string &src, std::vector<char> &cubin, std::string &log);
+
 template <class P>
 std::string fill_pass_params(const HostModel &hm, int colour, P &p);
 

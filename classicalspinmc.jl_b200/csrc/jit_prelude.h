@@ -1,0 +1,166 @@
+// jit_prelude.h — static part of the runtime-specialised kernel source (compiled with NVRTC for
+// sm_100a at csmc_create time, see jit.cpp).  The model-specific part (one `struct SegK` per
+// colouring class with fully unrolled interaction terms, literal coefficients and constant
+// geometry, plus the extern "C" kernels) is generated and appended to this text.
+//
+// The arithmetic is the same as the ahead-of-time kernels in kernels.cuh; what changes is that
+// every per-class constant is a compile-time literal, so the generated SASS carries no index-table
+// or coefficient loads and no term loops.
+#pragma once
+
+static const char *kJitPrelude = R"CSMCJIT(
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+
+enum { UPD_OR = 0, UPD_DET = 1, UPD_METRO = 2, UPD_CONE = 3 };
+enum { TAG_PROPOSE = 0, TAG_ACCEPT = 1, TAG_INIT = 2, TAG_EXCHANGE = 3 };
+#define TPB 256
+
+struct SweepArgs {
+    const double *T;
+    const double *sigma;
+    unsigned long long *accepted;
+    const unsigned long long *ctr_base;
+    unsigned long long ctr_off;
+    unsigned long long seed;
+    int replica_base;
+};
+
+struct u4 { uint32_t x, y, z, w; };
+__device__ __forceinline__ u4 philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    u4 r; r.x = c0; r.y = c1; r.z = c2; r.w = c3;
+    return r;
+}
+__device__ __forceinline__ u4 philox_stream(unsigned long long seed, uint32_t c0, uint32_t c1, unsigned long long ctr, uint32_t tag) {
+    return philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), c0, c1, (uint32_t)ctr, (uint32_t)((ctr >> 32) << 8) | tag);
+}
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
+    return (double)((((unsigned long long)hi << 32) | lo) >> 11) * 0x1.0p-53;
+}
+__device__ __forceinline__ void random_orientation(double S, double u1, double u2, double &x, double &y, double &z) {
+    double sn, cs;
+    sincospi(2.0 * u1, &sn, &cs);
+    const double zz = 2.0 * u2 - 1.0;
+    const double r = sqrt(1.0 - zz * zz);
+    x = S * (r * cs); y = S * (r * sn); z = S * zz;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// one site of one colour pass; SEG supplies the constant geometry, Zeeman / on-site constants and
+// the unrolled neighbour-field accumulation
+template <int UPD, class SEG>
+__device__ __forceinline__ void sweep_site(double *__restrict__ spins, const SweepArgs &a) {
+    const int idx = blockIdx.x * TPB + threadIdx.x;
+    const int rep = blockIdx.z;
+    double *sx = spins + (size_t)rep * (3ull * NPAD), *sy = sx + NPAD, *sz = sy + NPAD;
+    bool accepted = false;
+    if (idx < SEG::COUNT) {
+        int m0, m1, m2;
+        SEG::locate(idx, m0, m1, m2);
+        const int pos = SEG::START + idx;
+        const double s0 = sx[pos], s1 = sy[pos], s2 = sz[pos];
+        double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+        if (UPD == UPD_OR || UPD == UPD_DET) {
+            if (SEG::ONSITE) {
+                g0 = 2 * (SEG::O0 * s0 + SEG::O1 * s1 + SEG::O2 * s2);
+                g1 = 2 * (SEG::O3 * s0 + SEG::O4 * s1 + SEG::O5 * s2);
+                g2 = 2 * (SEG::O6 * s0 + SEG::O7 * s1 + SEG::O8 * s2);
+            }
+        }
+        SEG::field(sx, sy, sz, m0, m1, m2, g0, g1, g2, g0, g1, g2, g0, g1, g2);
+        const double F0 = g0 - SEG::H0, F1 = g1 - SEG::H1, F2 = g2 - SEG::H2;
+        if (UPD == UPD_OR) {
+            if (!(F0 == 0.0 && F1 == 0.0 && F2 == 0.0)) {
+                const double proj = 2.0 * (s0 * F0 + s1 * F1 + s2 * F2) / (F0 * F0 + F1 * F1 + F2 * F2);
+                sx[pos] = -s0 + proj * F0; sy[pos] = -s1 + proj * F1; sz[pos] = -s2 + proj * F2;
+            }
+        } else if (UPD == UPD_DET) {
+            if (!(F0 == 0.0 && F1 == 0.0 && F2 == 0.0)) {
+                const double nrm = sqrt(F0 * F0 + F1 * F1 + F2 * F2);
+                sx[pos] = -F0 / nrm * SPIN_S; sy[pos] = -F1 / nrm * SPIN_S; sz[pos] = -F2 / nrm * SPIN_S;
+            }
+        } else {
+            const unsigned long long ctr = (a.ctr_base ? *a.ctr_base : 0ULL) + a.ctr_off;
+            const uint32_t site = SEG::site(m0, m1, m2);
+            const uint32_t grep = (uint32_t)(a.replica_base + rep);
+            const u4 r = philox_stream(a.seed, site, grep, ctr, TAG_PROPOSE);
+            double n0, n1, n2;
+            random_orientation(SPIN_S, u53(r.x, r.y), u53(r.z, r.w), n0, n1, n2);
+            if (UPD == UPD_CONE) {
+                const double sg = a.sigma[rep];
+                n0 = s0 + sg * n0; n1 = s1 + sg * n1; n2 = s2 + sg * n2;
+                const double nrm = sqrt(n0 * n0 + n1 * n1 + n2 * n2);
+                n0 = n0 / nrm * SPIN_S; n1 = n1 / nrm * SPIN_S; n2 = n2 / nrm * SPIN_S;
+            }
+            double dE = (n0 - s0) * F0 + (n1 - s1) * F1 + (n2 - s2) * F2;
+            if (SEG::ONSITE) {
+                const double en = n0 * (SEG::O0 * n0 + SEG::O1 * n1 + SEG::O2 * n2) + n1 * (SEG::O3 * n0 + SEG::O4 * n1 + SEG::O5 * n2) +
+                                  n2 * (SEG::O6 * n0 + SEG::O7 * n1 + SEG::O8 * n2);
+                const double eo = s0 * (SEG::O0 * s0 + SEG::O1 * s1 + SEG::O2 * s2) + s1 * (SEG::O3 * s0 + SEG::O4 * s1 + SEG::O5 * s2) +
+                                  s2 * (SEG::O6 * s0 + SEG::O7 * s1 + SEG::O8 * s2);
+                dE += en - eo;
+            }
+            accepted = dE < 0.0;
+            if (!accepted) {
+                const u4 q = philox_stream(a.seed, site, grep, ctr, TAG_ACCEPT);
+                accepted = u53(q.x, q.y) < exp(-dE / a.T[rep]);
+            }
+            if (accepted) { sx[pos] = n0; sy[pos] = n1; sz[pos] = n2; }
+        }
+    }
+    if (UPD == UPD_METRO || UPD == UPD_CONE) {
+        const unsigned ballot = __ballot_sync(0xffffffffu, accepted);
+        if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(a.accepted + rep, (unsigned long long)__popc(ballot));
+    }
+}
+
+template <class SEG>
+__device__ __forceinline__ void energy_site(const double *__restrict__ spins, double (&v)[4]) {
+    const int idx = blockIdx.x * TPB + threadIdx.x;
+    const int rep = blockIdx.z;
+    const double *sx = spins + (size_t)rep * (3ull * NPAD), *sy = sx + NPAD, *sz = sy + NPAD;
+    if (idx < SEG::COUNT) {
+        int m0, m1, m2;
+        SEG::locate(idx, m0, m1, m2);
+        const int pos = SEG::START + idx;
+        const double s0 = sx[pos], s1 = sy[pos], s2 = sz[pos];
+        double a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0, c0 = 0, c1 = 0, c2 = 0;
+        SEG::field(sx, sy, sz, m0, m1, m2, a0, a1, a2, b0, b1, b2, c0, c1, c2);
+        double e = (s0 * a0 + s1 * a1 + s2 * a2) / 2 + (s0 * b0 + s1 * b1 + s2 * b2) / 3 +
+                   (s0 * c0 + s1 * c1 + s2 * c2) / 4 - (s0 * SEG::H0 + s1 * SEG::H1 + s2 * SEG::H2);
+        if (SEG::ONSITE)
+            e += s0 * (SEG::O0 * s0 + SEG::O1 * s1 + SEG::O2 * s2) + s1 * (SEG::O3 * s0 + SEG::O4 * s1 + SEG::O5 * s2) +
+                 s2 * (SEG::O6 * s0 + SEG::O7 * s1 + SEG::O8 * s2);
+        v[0] = e; v[1] = s0; v[2] = s1; v[3] = s2;
+    }
+}
+
+__device__ __forceinline__ void energy_block_reduce(const double (&v)[4], double *__restrict__ partials, int n_partials, int partial_base) {
+    __shared__ double sh[4][TPB / 32];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double w = warp_sum(v[k]);
+        if ((threadIdx.x & 31) == 0) sh[k][threadIdx.x >> 5] = w;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < TPB / 32; ++w) t += sh[threadIdx.x][w];
+        const size_t slot = (size_t)blockIdx.z * n_partials + partial_base + (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+        partials[slot * 4 + threadIdx.x] = t;
+    }
+}
+)CSMCJIT";

@@ -1,0 +1,244 @@
+"""Output files — mirror of src/hdf5.jl's writers/readers (layout in SURVEY.md section 5).
+
+h5py is not available in the build image, so two backends are provided with the same group /
+dataset / attribute names: real HDF5 through ``h5py`` when it can be imported, and otherwise a
+``.npz`` container whose keys are the HDF5 paths (``unit_cell/bilinear/(1,2),(0, -1)`` ...) and whose
+attributes live under ``@attrs/<name>``.  File names keep the reference's ``.h5`` / ``.h5.params``
+suffixes either way (src/monte_carlo.jl:96-99).  The Julia package (julia/ClassicalSpinMC) writes real
+HDF5 through HDF5.jl.
+"""
+from __future__ import annotations
+
+import ast
+import os
+
+import numpy as np
+
+try:  # pragma: no cover - not installed in the build image
+    import h5py
+except Exception:  # noqa: BLE001
+    h5py = None
+
+
+# ---- tiny container abstraction ---------------------------------------------------------------------
+class _NpzFile:
+    """dict-of-arrays stand-in for an HDF5 file: keys are paths, attributes are '@attrs/<name>'."""
+
+    def __init__(self, filename, mode):
+        self.filename, self.mode = filename, mode
+        self.data = {}
+        if mode in ("r", "r+") and os.path.exists(filename):
+            with np.load(filename, allow_pickle=False) as z:
+                self.data = {k: z[k] for k in z.files}
+        elif mode in ("r", "r+"):
+            raise FileNotFoundError(filename)
+
+    def close(self):
+        if self.mode != "r":
+            with open(self.filename, "wb") as f:
+                np.savez(f, **self.data)
+
+
+def _open(filename, mode):
+    if h5py is not None:
+        return h5py.File(filename, mode)
+    return _NpzFile(filename, mode)
+
+
+def _set(f, path, value):
+    if h5py is not None and not isinstance(f, _NpzFile):
+        if path in f:
+            del f[path]
+        f[path] = value
+    else:
+        f.data[path] = np.asarray(value)
+
+
+def _get(f, path):
+    if h5py is not None and not isinstance(f, _NpzFile):
+        return f[path][()]
+    return f.data[path]
+
+
+def _set_attr(f, name, value):
+    if h5py is not None and not isinstance(f, _NpzFile):
+        f.attrs[name] = value
+    else:
+        f.data["@attrs/" + name] = np.asarray(value)
+
+
+def _get_attr(f, name):
+    if h5py is not None and not isinstance(f, _NpzFile):
+        return f.attrs[name]
+    v = f.data["@attrs/" + name]
+    return v.item() if v.shape == () else v
+
+
+def _keys(f, group):
+    if h5py is not None and not isinstance(f, _NpzFile):
+        return list(f[group].keys()) if group in f else []
+    pre = group.rstrip("/") + "/"
+    return sorted({k[len(pre):].split("/")[0] for k in f.data if k.startswith(pre)})
+
+
+def _julia_tuple(t):
+    """string(offset) of a Julia NTuple: '(0, -1)'; 1-tuples print as '(1,)'."""
+    t = tuple(int(v) for v in t)
+    return "(" + ", ".join(str(v) for v in t) + ("," if len(t) == 1 else "") + ")"
+
+
+# ---- params file (src/hdf5.jl:36-147) -------------------------------------------------------------------
+def dump_unit_cell(f, uc):
+    """src/hdf5.jl:36-76"""
+    _set(f, "unit_cell/lattice_vectors", np.stack(uc.lattice_vectors, axis=1))   # columns = a_i
+    _set(f, "unit_cell/basis", np.stack(uc.basis, axis=0))                        # n_basis x D
+    for b, vec in uc.field:
+        _set(f, f"unit_cell/field/{b}", vec)
+    for b, mat in uc.onsite:
+        _set(f, f"unit_cell/onsite/{b}", mat)
+    for b1, b2, mat, off in uc.bilinear:
+        _set(f, f"unit_cell/bilinear/({b1},{b2}),{_julia_tuple(off)}", mat)           # :60
+    for b1, b2, b3, mat, o2, o3 in uc.cubic:
+        _set(f, f"unit_cell/cubic/({b1},{b2},{b3}),{_julia_tuple(o2)},{_julia_tuple(o3)}", mat)   # :67
+    for b1, b2, b3, b4, mat, o2, o3, o4 in uc.quartic:
+        _set(f, f"unit_cell/quartic/({b1},{b2},{b3},{b4}),{_julia_tuple(o2)},{_julia_tuple(o3)},{_julia_tuple(o4)}", mat)  # :74
+
+
+def dump_metadata(f, mc):
+    """src/hdf5.jl:125-137"""
+    dump_unit_cell(f, mc.lattice.unit_cell)
+    _set(f, "lattice/size", np.array(mc.lattice.shape, dtype=np.int64))
+    _set(f, "lattice/S", mc.lattice.S)
+    _set(f, "lattice/bc", np.array(mc.lattice.bc))
+    for k, v in mc.parameters._asdict().items():
+        _set_attr(f, k, v)
+
+
+def create_params_file(mc, filename):
+    """src/hdf5.jl:142-147"""
+    f = _open(filename, "w")
+    dump_metadata(f, mc)
+    f.close()
+    return filename
+
+
+def write_attributes(filename, d):
+    """src/hdf5.jl:27-31"""
+    f = _open(filename, "r+")
+    for k, v in d.items():
+        _set_attr(f, k, v)
+    f.close()
+
+
+def read_unit_cell(f):
+    """src/hdf5.jl:81-120"""
+    from .unit_cell import UnitCell
+    lv = np.asarray(_get(f, "unit_cell/lattice_vectors"))
+    uc = UnitCell(*[lv[:, i] for i in range(lv.shape[1])])
+    for row in np.atleast_2d(_get(f, "unit_cell/basis")):
+        uc.basis.append(np.array(row, dtype=np.float64))
+    for key in _keys(f, "unit_cell/field"):
+        uc.field.append((int(key), np.array(_get(f, f"unit_cell/field/{key}"))))
+    for key in _keys(f, "unit_cell/onsite"):
+        uc.onsite.append((int(key), np.array(_get(f, f"unit_cell/onsite/{key}"))))
+    for key in _keys(f, "unit_cell/bilinear"):
+        (b1, b2), off = ast.literal_eval(key)                                    # eval(Meta.parse(key)), :103
+        uc.bilinear.append((b1, b2, np.array(_get(f, f"unit_cell/bilinear/{key}")), tuple(off)))
+    for key in _keys(f, "unit_cell/cubic"):
+        (b1, b2, b3), o2, o3 = ast.literal_eval(key)
+        uc.cubic.append((b1, b2, b3, np.array(_get(f, f"unit_cell/cubic/{key}")), tuple(o2), tuple(o3)))
+    for key in _keys(f, "unit_cell/quartic"):
+        (b1, b2, b3, b4), o2, o3, o4 = ast.literal_eval(key)
+        uc.quartic.append((b1, b2, b3, b4, np.array(_get(f, f"unit_cell/quartic/{key}")), tuple(o2), tuple(o3), tuple(o4)))
+    return uc
+
+
+def read_lattice(f):
+    """src/hdf5.jl:152-159; ``f`` is an open file object or a filename."""
+    from .lattice import Lattice
+    own = isinstance(f, (str, os.PathLike))
+    fid = _open(f, "r") if own else f
+    size = tuple(int(v) for v in _get(fid, "lattice/size"))
+    uc = read_unit_cell(fid)
+    S = float(_get(fid, "lattice/S"))
+    bc = _get(fid, "lattice/bc")
+    bc = bc.decode() if isinstance(bc, bytes) else str(bc)
+    if own:
+        fid.close()
+    return Lattice(size, uc, S, bc=bc)
+
+
+# ---- configuration file (src/hdf5.jl:164-270) ---------------------------------------------------------
+def _spins_for_file(spins):
+    """Julia writes its 3 x N column-major array; h5py readers see (N, 3) (util/load.py:88-93)."""
+    return np.ascontiguousarray(np.asarray(spins).T)
+
+
+def initialize_hdf5(mc, paramsfile, outpath=None, T=None, spins=None):
+    """src/hdf5.jl:164-171"""
+    f = _open(outpath or mc.outpath, "w")
+    _set_attr(f, "T", float(mc.T if T is None else T))
+    _set_attr(f, "paramsfile", paramsfile)
+    _set(f, "spins", _spins_for_file(mc.lattice.spins if spins is None else spins))
+    _set(f, "site_positions", np.ascontiguousarray(mc.lattice.site_positions.T))
+    f.close()
+
+
+def write_MC_checkpoint(mc, outpath=None, spins=None):
+    """src/hdf5.jl:176-180: overwrite dataset ``spins`` in the configuration file."""
+    f = _open(outpath or mc.outpath, "r+")
+    _set(f, "spins", _spins_for_file(mc.lattice.spins if spins is None else spins))
+    f.close()
+
+
+def write_initial_configuration(filename, mc, spins=None, T=None, config_path=None):
+    """src/hdf5.jl:185-194"""
+    src = _open(config_path or mc.outpath, "r")
+    paramsfile = _get_attr(src, "paramsfile")
+    src.close()
+    f = _open(filename, "w")
+    _set_attr(f, "T", float(mc.T if T is None else T))
+    _set_attr(f, "paramsfile", paramsfile)
+    _set(f, "spins", _spins_for_file(mc.lattice.spins if spins is None else spins))
+    f.close()
+
+
+def write_final_observables(mc, outpath=None, spins=None, observables=None, T=None):
+    """src/hdf5.jl:204-239 (without the optional spin_correlations group)."""
+    from .observables import _specific_heat, _susceptibility
+    obs = mc.observables if observables is None else observables
+    T = float(mc.T if T is None else T)
+    f = _open(outpath or mc.outpath, "r+")
+    _set(f, "spins", _spins_for_file(mc.lattice.spins if spins is None else spins))
+    heat, dheat = _specific_heat(obs.energy, T, mc.lattice.size)
+    chi, dchi = _susceptibility(obs.magnetization, T, mc.lattice.size)
+    vals = {
+        "specific_heat": heat, "specific_heat_err": abs(dheat / heat) if heat != 0 else np.nan,      # :220-221
+        "susceptibility": chi, "susceptibility_err": abs(dchi / chi) if chi != 0 else np.nan,         # :222-223
+        "magnetization": obs.magnetization.mean(1), "magnetization_err": obs.magnetization.std_error(1),
+        "energy": obs.energy.mean(1), "energy_err": obs.energy.std_error(1),                          # :224-227
+    }
+    for k, v in vals.items():
+        _set(f, f"observables/{k}", v)
+    f.close()
+    return vals
+
+
+def overwrite_keys(fid, d):
+    """src/hdf5.jl:244-252"""
+    for k, v in d.items():
+        _set(fid, k, v)
+
+
+def read_spin_configuration(lat, filename):
+    """src/hdf5.jl:266-270"""
+    f = _open(filename, "r")
+    lat.spins[:, :] = np.asarray(_get(f, "spins")).T
+    f.close()
+
+
+def read_observables(filename):
+    f = _open(filename, "r")
+    out = {k: float(np.asarray(_get(f, f"observables/{k}"))) for k in _keys(f, "observables")}
+    f.close()
+    return out

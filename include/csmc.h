@@ -87,6 +87,13 @@ typedef struct csmc_opts {
 #define CSMC_FLAG_FORCE_GENERIC 1 /* use the explicit-index-table kernels even when the      \
                                      arithmetic-neighbour (structured) kernels apply        */
 #define CSMC_FLAG_NO_GRAPH 2      /* plain stream launches instead of CUDA-graph replay      */
+#define CSMC_FLAG_JIT 4           /* require the runtime-specialised (NVRTC) kernels: fail     \
+                                     csmc_create if they cannot be built                      */
+#define CSMC_FLAG_NO_JIT 8        /* never specialise at run time (ahead-of-time kernels only) */
+/* Default: models whose colouring is a periodic pattern get kernels specialised for that model
+ * (unrolled terms, literal coefficients, constant geometry; compiled for sm_100a with NVRTC at
+ * csmc_create) when n_sites * n_replicas >= 32768; smaller problems are launch-latency bound and
+ * use the ahead-of-time kernels. */
 
 typedef struct csmc_handle csmc_handle;
 
@@ -119,6 +126,14 @@ int32_t csmc_n_colours(const csmc_handle *h, int32_t *c);
 int32_t csmc_get_colouring(const csmc_handle *h, int32_t *colour);
 /* 1 if the arithmetic-neighbour kernels are in use, 0 if the explicit-table kernels are. */
 int32_t csmc_is_structured(const csmc_handle *h, int32_t *flag);
+/* which pass kernels this handle launches: 0 explicit-table, 1 arithmetic-neighbour (both ahead of
+ * time), 2 runtime-specialised for this model (NVRTC, sm_100a). */
+int32_t csmc_kernel_mode(const csmc_handle *h, int32_t *mode);
+/* Host-only (no GPU needed): generate the specialised kernel source for `model` and, if
+ * compile != 0, compile it with NVRTC for sm_100a.  source/log may be NULL; *_cap are buffer sizes;
+ * *source_len receives the full source length.  Used by build checks and tests. */
+int32_t csmc_jit_check(const csmc_model *model, int32_t compile, char *source, int64_t source_cap,
+                       int64_t *source_len, char *log, int64_t log_cap);
 /* kernels launched on this handle since creation (bench.py's `gpu_launches`). */
 int32_t csmc_launch_count(const csmc_handle *h, int64_t *n);
 

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from classicalspinmc.jl_b200 import _lib
-from classicalspinmc.jl_b200._abi import FLAG_FORCE_GENERIC, FLAG_NO_GRAPH, ModelData
+from classicalspinmc.jl_b200._abi import FLAG_FORCE_GENERIC, FLAG_JIT, FLAG_NO_GRAPH, FLAG_NO_JIT, ModelData
 from oracle import oracle as orc
 from tests import models
 
@@ -32,13 +32,21 @@ CASES = [
     ("chain-open-17", lambda: models.chain_heisenberg(), (17,), "open", 1.0),
 ]
 IDS = [c[0] for c in CASES]
-MODES = [0, FLAG_FORCE_GENERIC]
+# kernel families: ahead-of-time arithmetic-neighbour, ahead-of-time explicit-table, runtime-specialised
+MODES = [FLAG_NO_JIT, FLAG_FORCE_GENERIC, FLAG_JIT]
+MODE_IDS = ["structured", "generic", "jit"]
 
 
 def _setup(builder, shape, bc, S, flags=0, n_replicas=1, seed=12345):
     md = ModelData(builder(), shape, S, bc)
+    if flags & FLAG_JIT and not _lib.plan(md)[2]:
+        pytest.skip("no periodic colouring pattern: explicit-table kernels only")
     lat = orc.OracleLattice(md)
     eng = _lib.Engine(md, n_replicas=n_replicas, seed=seed, flags=flags)
+    if flags & FLAG_JIT:
+        assert eng.kernel_mode == 2
+    elif flags & FLAG_FORCE_GENERIC:
+        assert eng.kernel_mode == 0
     return md, lat, eng
 
 
@@ -68,7 +76,7 @@ def test_tables_and_layout(name, builder, shape, bc, S):
     assert np.allclose(eng.get_spins(), lat.randomize(seed=77, replica=0), rtol=0, atol=2e-15)
 
 
-@pytest.mark.parametrize("flags", MODES, ids=["structured", "generic"])
+@pytest.mark.parametrize("flags", MODES, ids=MODE_IDS)
 @pytest.mark.parametrize("name,builder,shape,bc,S", CASES, ids=IDS)
 def test_field_and_energy_parity(name, builder, shape, bc, S, flags):
     md, lat, eng = _setup(builder, shape, bc, S, flags)
@@ -92,7 +100,7 @@ def test_field_and_energy_parity(name, builder, shape, bc, S, flags):
     assert np.abs(eng.local_field(p) - F_ref[p - 1]).max() <= TOL * scale
 
 
-@pytest.mark.parametrize("flags", MODES, ids=["structured", "generic"])
+@pytest.mark.parametrize("flags", MODES, ids=MODE_IDS)
 @pytest.mark.parametrize("name,builder,shape,bc,S", CASES, ids=IDS)
 def test_overrelaxation_parity_colour_order(name, builder, shape, bc, S, flags):
     md, lat, eng = _setup(builder, shape, bc, S, flags)
@@ -105,7 +113,7 @@ def test_overrelaxation_parity_colour_order(name, builder, shape, bc, S, flags):
     assert np.abs(eng.get_spins() - s).max() <= TOL * S
 
 
-@pytest.mark.parametrize("flags", MODES, ids=["structured", "generic"])
+@pytest.mark.parametrize("flags", MODES, ids=MODE_IDS)
 @pytest.mark.parametrize("name,builder,shape,bc,S", CASES, ids=IDS)
 def test_deterministic_parity_colour_order(name, builder, shape, bc, S, flags):
     md, lat, eng = _setup(builder, shape, bc, S, flags)
@@ -119,7 +127,7 @@ def test_deterministic_parity_colour_order(name, builder, shape, bc, S, flags):
     assert np.allclose(np.linalg.norm(out, axis=1), S, rtol=0, atol=1e-13)
 
 
-@pytest.mark.parametrize("flags", MODES, ids=["structured", "generic"])
+@pytest.mark.parametrize("flags", MODES, ids=MODE_IDS)
 @pytest.mark.parametrize("T", [0.05, 1.0])
 @pytest.mark.parametrize("name,builder,shape,bc,S", CASES, ids=IDS)
 def test_metropolis_same_stream_parity(name, builder, shape, bc, S, T, flags):
@@ -199,7 +207,7 @@ def test_graph_and_plain_launch_agree():
     lat = orc.OracleLattice(md)
     s0 = lat.randomize(seed=8)
     outs = []
-    for flags in (0, FLAG_NO_GRAPH):
+    for flags in (0, FLAG_NO_GRAPH, FLAG_JIT, FLAG_JIT | FLAG_NO_GRAPH):
         eng = _lib.Engine(md, seed=5, flags=flags)
         eng.set_spins(s0)
         eng.set_temperatures(0.8)
@@ -208,6 +216,8 @@ def test_graph_and_plain_launch_agree():
         eng.sync()
         outs.append((eng.get_spins().copy(), eng.accepted()[0]))
     assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1]
+    assert np.array_equal(outs[2][0], outs[3][0]) and outs[2][1] == outs[3][1]
+    assert outs[2][1] == outs[0][1] and np.abs(outs[2][0] - outs[0][0]).max() <= 1e-6
     # and both equal the oracle run in colour order with the same stream
     eng = _lib.Engine(md, seed=5)
     order = eng.colour_order()
@@ -277,6 +287,7 @@ def test_full_size_properties_square_1024():
     md = ModelData(models.square_heisenberg(), (1024, 1024), 1.0)
     eng = _lib.Engine(md, seed=1)
     assert eng.structured and eng.n_colours == 2
+    assert eng.kernel_mode == 2, "BASELINE config C2 must run on the runtime-specialised kernels"
     eng.randomize(12345)
     s0 = eng.get_spins()
     assert np.allclose(np.linalg.norm(s0, axis=1), 1.0, rtol=0, atol=1e-14)
