@@ -1,0 +1,171 @@
+"""Statistical parity (BASELINE.json north_star, correctness part 3): thermal averages from the GPU
+Markov chain agree with exact results and with the oracle's CPU run of the reference algorithm within
+their statistical error bars.  The chains differ by construction (colour-ordered sweeps + Philox on
+the GPU, random sites with replacement + xoshiro in the reference), so agreement is in distribution.
+Error bars come from a binning analysis of the measured series; thresholds are 5 sigma."""
+import math
+
+import numpy as np
+import pytest
+
+import classicalspinmc.jl_b200 as csm
+from classicalspinmc.jl_b200 import _lib
+from classicalspinmc.jl_b200._abi import FLAG_JIT, ModelData
+from oracle import oracle as orc
+from tests import models
+
+pytestmark = pytest.mark.gpu
+
+
+def binned_error(x, nbins=32):
+    x = np.asarray(x, dtype=float)
+    n = len(x) // nbins * nbins
+    b = x[:n].reshape(nbins, -1).mean(axis=1)
+    return b.mean(), b.std(ddof=1) / math.sqrt(nbins)
+
+
+def langevin(x):
+    return 1.0 / math.tanh(x) - 1.0 / x
+
+
+@pytest.mark.parametrize("kind", ["uniform", "cone"])
+def test_free_spins_follow_the_langevin_function(kind):
+    """Non-interacting spins in a field: <s_z> = S L(h S / T) exactly."""
+    h, S, T = 0.7, 1.0, 0.5
+    uc = csm.Square()
+    csm.addZeemanCoupling(uc, 1, np.array([0.0, 0.0, h]))
+    md = ModelData(uc, (64, 64), S)
+    eng = _lib.Engine(md, seed=11, flags=FLAG_JIT)
+    eng.randomize(3)
+    run = (lambda n: eng.metropolis(T, n)) if kind == "uniform" else (lambda n: eng.metropolis_cone(T, 1.5, False, n)[0])
+    run(100)
+    mz = []
+    for _ in range(320):
+        run(2)
+        mz.append(eng.magnetization_vector()[0][2] / md.n_sites)
+    mean, err = binned_error(mz)
+    exact = S * langevin(h * S / T)
+    assert abs(mean - exact) < 5 * err + 1e-4, (mean, exact, err)
+
+
+def test_open_heisenberg_chain_matches_fisher():
+    """Open classical Heisenberg chain (Fisher 1964): E / bond = -|J| S^2 L(|J| S^2 / T)."""
+    J, S, Lc = -1.0, 1.0, 64
+    md = ModelData(models.chain_heisenberg(J), (Lc,), S, "open")
+    Ts = np.array([0.3, 0.6, 1.2, 2.4])
+    R = 64                      # 16 independent chains per temperature
+    T_all = np.repeat(Ts, R // len(Ts))
+    eng = _lib.Engine(md, n_replicas=R, seed=5)
+    eng.randomize(9)
+    eng.set_temperatures(T_all)
+    eng.cycles_async(300, 2, 1)
+    series = []
+    for _ in range(160):
+        eng.cycles_async(5, 2, 1)
+        series.append(eng.total_energy() / (Lc - 1))
+    series = np.array(series)
+    for k, T in enumerate(Ts):
+        cols = series[:, k * 16:(k + 1) * 16].mean(axis=1)
+        mean, err = binned_error(cols, 16)
+        exact = -abs(J) * S * S * langevin(abs(J) * S * S / T)
+        assert abs(mean - exact) < 5 * err + 2e-4, (T, mean, exact, err)
+
+
+def test_thermal_averages_match_reference_algorithm():
+    """Kitaev-Gamma honeycomb L=6 at T=0.4: E/N, |M|/N, specific heat and Metropolis acceptance from the
+    GPU chain vs the oracle's run of the reference algorithm (random-site Metropolis + sequential
+    overrelaxation), both through the reference's parallel_tempering loop with one temperature."""
+    md = ModelData(models.kitaev_honeycomb(), (6, 6), 1.0)
+    N = md.n_sites
+    T = 0.4
+    p = dict(t_thermalization=2000, t_measurement=40000, probe_rate=10, swap_rate=10 ** 9, overrelaxation_rate=5)
+    lat = orc.OracleLattice(md)
+    s = lat.randomize(seed=1)
+    E_ref, M_ref, acc_ref, _ = lat.parallel_tempering(s, [T], p["t_thermalization"], p["t_measurement"],
+                                                      p["probe_rate"], p["swap_rate"], p["overrelaxation_rate"], seed=77)
+    eng = _lib.Engine(md, n_replicas=1, seed=99)
+    eng.set_spins(lat.randomize(seed=2))
+    eng.pt_init([T])
+    eng.pt_run(p, 0, p["t_thermalization"] + p["t_measurement"])
+    E, M = eng.pt_series()
+    acc, _ = eng.pt_stats()
+    assert E.shape == E_ref.shape == (p["t_measurement"] // p["probe_rate"], 1)
+    for a, b, scale in ((E[:, 0] / N, E_ref[:, 0] / N, 1), (M[:, 0] / N, M_ref[:, 0] / N, 1)):
+        ma, ea = binned_error(a)
+        mb, eb = binned_error(b)
+        assert abs(ma - mb) < 5 * math.hypot(ea, eb), (ma, mb, ea, eb)
+    # specific heat c = (<E^2> - <E>^2) / (T^2 N), src/observables.jl:42; error from bin-to-bin scatter
+    def cv(x):
+        bins = x[: len(x) // 32 * 32].reshape(32, -1)
+        c = bins.var(axis=1) / (T * T * N)
+        return c.mean(), c.std(ddof=1) / math.sqrt(32)
+    ca, ea = cv(E[:, 0])
+    cb, eb = cv(E_ref[:, 0])
+    assert abs(ca - cb) < 5 * math.hypot(ea, eb), (ca, cb, ea, eb)
+    # acceptance rate of uniform proposals is a thermal average too
+    n_metro = (p["t_thermalization"] + p["t_measurement"]) // p["overrelaxation_rate"]
+    ra, rb = acc[0] / (n_metro * N), acc_ref[0] / (n_metro * N)
+    assert abs(ra - rb) < 0.01, (ra, rb)
+
+
+def test_parallel_tempering_matches_reference_algorithm():
+    """Replica exchange: per-temperature <E> and exchange acceptance of the device loop (temperatures
+    swapped) vs the oracle's reference loop (configurations swapped, src/monte_carlo.jl:308-349)."""
+    md = ModelData(models.kitaev_honeycomb(), (4, 4), 1.0)
+    N = md.n_sites
+    Ts = np.geomspace(0.15, 1.0, 6)
+    R = len(Ts)
+    p = dict(t_thermalization=2000, t_measurement=30000, probe_rate=10, swap_rate=10, overrelaxation_rate=5)
+    lat = orc.OracleLattice(md)
+    spins = np.concatenate([lat.randomize(seed=10 + r) for r in range(R)])
+    E_ref, M_ref, acc_ref, ex_ref = lat.parallel_tempering(spins, Ts, p["t_thermalization"], p["t_measurement"],
+                                                           p["probe_rate"], p["swap_rate"], p["overrelaxation_rate"], seed=5)
+    eng = _lib.Engine(md, n_replicas=R, seed=1234)
+    for r in range(R):
+        eng.set_spins(lat.randomize(seed=40 + r), replica=r)
+    eng.pt_init(Ts)
+    total = p["t_thermalization"] + p["t_measurement"]
+    eng.pt_run(p, 0, total // 2)
+    eng.pt_run(p, total // 2, total)           # chunked runs continue the same loop
+    E, M = eng.pt_series()
+    acc, ex = eng.pt_stats()
+    assert E.shape == E_ref.shape
+    for k in range(R):
+        ma, ea = binned_error(E[:, k] / N)
+        mb, eb = binned_error(E_ref[:, k] / N)
+        assert abs(ma - mb) < 5 * math.hypot(ea, eb) + 1e-4, (k, ma, mb, ea, eb)
+    n_attempt = total // p["swap_rate"]
+    rate, rate_ref = ex / n_attempt, ex_ref / n_attempt
+    assert np.all(np.abs(rate - rate_ref) < 0.05), (rate, rate_ref)
+    assert sorted(eng.pt_slots().tolist()) == list(range(R))
+    assert ex.sum() > 0 and np.all(acc > 0)
+
+
+def test_annealing_reaches_the_reference_ground_state_energy():
+    """test/mctests.jl:43-50 through the host mirror: simulated_annealing! + deterministic_updates! on
+    the Kitaev-Gamma honeycomb, round(E/N, digits=4) == -0.6444."""
+    uc = models.kitaev_honeycomb()
+    lat = csm.Lattice((4, 4), uc, 1, rng=np.random.default_rng(5))
+    T0, T = 1.0, 1e-7
+    params = {"t_thermalization": int(1e4), "overrelaxation_rate": 10, "t_deterministic": int(1e6)}
+    mc = csm.MonteCarlo(T, lat, params, seed=2)
+    before = lat.spins.copy()
+    csm.simulated_annealing(mc, lambda x: T0 * 0.9 ** x, T0)
+    csm.deterministic_updates(mc)
+    E = csm.energy_density(mc.lattice)
+    assert round(E, 4) == -0.6444
+    assert np.array_equal(lat.spins, before)        # the user's lattice is not mutated (deepcopy, :74)
+    assert np.allclose(np.linalg.norm(mc.lattice.spins, axis=0), 1.0, atol=1e-9)
+
+
+def test_readme_example_square_lattice():
+    """README.md:28-88 (C1): square Heisenberg L=4, J=-I, h=0.1 z, annealing + deterministic updates:
+    the ferromagnet aligned with the field, E/N = -2 - 0.1 exactly."""
+    uc = models.square_heisenberg(J=-1.0, h=(0.0, 0.0, 0.1))
+    lat = csm.Lattice((4, 4), uc, 1.0, bc="periodic", rng=np.random.default_rng(1))
+    mc = csm.MonteCarlo(1e-7, lat, {"t_thermalization": int(1e4), "t_deterministic": int(1e5), "overrelaxation_rate": 10}, seed=3)
+    csm.simulated_annealing(mc, lambda x: 1.0 * 0.9 ** x, 1.0)
+    csm.deterministic_updates(mc)
+    assert abs(csm.energy_density(mc.lattice) - (-2.1)) < 1e-6
+    assert abs(csm.get_magnetization(mc.lattice) - 16.0) < 1e-5
+    assert np.allclose(mc.lattice.spins[2], 1.0, atol=1e-5)

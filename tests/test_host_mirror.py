@@ -1,0 +1,192 @@
+"""CPU tests of the host-side mirror of the reference's Julia layer: UnitCell / Lattice tables,
+parameter buffer, observables (binning), output-file layout, parallel-tempering bookkeeping."""
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+import classicalspinmc.jl_b200 as csm
+from classicalspinmc.jl_b200 import hdf5 as h5
+from classicalspinmc.jl_b200 import parallel
+from classicalspinmc.jl_b200._abi import ModelData, resolve_field_onsite
+from classicalspinmc.jl_b200.observables import ErrorPropagator, _specific_heat
+from oracle import oracle as orc
+from tests import models
+
+
+def test_zero_couplings_are_dropped():
+    # src/unit_cell.jl:38,49,60,72
+    uc = csm.Square()
+    csm.addBilinear(uc, 1, 1, np.zeros((3, 3)), (1, 0))
+    csm.addOnSite(uc, 1, np.zeros((3, 3)))
+    csm.addCubic(uc, 1, 1, 1, np.zeros((3, 3, 3)))
+    csm.addQuartic(uc, 1, 1, 1, 1, np.zeros((3, 3, 3, 3)))
+    assert not uc.bilinear and not uc.onsite and not uc.cubic and not uc.quartic
+
+
+def test_lattice_adds_default_basis_and_normalises_spins():
+    # src/lattice.jl:68-70 and test/latticetests.jl:3-7
+    uc = csm.Square()
+    lat = csm.Lattice((2, 2), uc, 1.0)
+    assert len(uc.basis) == 1 and lat.size == 4 and lat.spins.shape == (3, 4)
+    assert np.all(np.round(np.linalg.norm(lat.spins, axis=0), 9) == 1.0)
+    fm = csm.Lattice((3, 3), csm.Square(), 0.5, initialCondition="fm")
+    assert np.allclose(fm.spins, fm.spins[:, :1]) and np.allclose(np.linalg.norm(fm.spins, axis=0), 0.5)
+    with pytest.raises(ValueError, match="Invalid boundary condition option"):
+        csm.Lattice((2, 2), csm.Square(), 1.0, bc="twisted")
+
+
+def test_site_order_and_positions():
+    # src/lattice.jl:29-51: basis slowest, last lattice index fastest
+    uc = csm.Honeycomb()
+    lat = csm.Lattice((2, 3), uc, 1.0)
+    idx = csm.lattice.site_indices((2, 3), 2)
+    assert idx[0] == (1, 1, 1) and idx[1] == (1, 1, 2) and idx[3] == (1, 2, 1) and idx[6] == (2, 1, 1)
+    a1, a2 = uc.lattice_vectors
+    for p, (b, i, j) in enumerate(idx):
+        expect = (i - 1) * a1 + (j - 1) * a2 + uc.basis[b - 1]
+        assert np.allclose(lat.site_positions[:, p], expect)
+
+
+@pytest.mark.parametrize("bc", ["periodic", "open"])
+def test_lattice_tables_match_oracle(bc):
+    """Public table fields (lat.bilinear_sites, ..., src/lattice.jl:14-22) vs the oracle's literal
+    restatement of the reference constructor."""
+    uc = models.mixed_basis_multispin()
+    lat = csm.Lattice((3, 4), uc, 0.8, bc=bc)
+    o = orc.OracleLattice(ModelData(uc, (3, 4), 0.8, bc), literal=True)
+    bil, cub, quar = o.tables()
+    assert np.array_equal(lat.bilinear_sites, bil)
+    assert np.array_equal(lat.cubic_sites, cub)
+    assert np.array_equal(lat.quartic_sites, quar)
+    assert np.array_equal(lat.bilinear_matrices.reshape(lat.size, -1, 9), o.bilinear_matrices())
+    # field / onsite per site
+    md = lat._model
+    b_of = np.repeat(np.arange(md.n_basis), lat.size // md.n_basis)
+    assert np.array_equal(lat.field, md.field[b_of])
+    # energy from the public tables (plain numpy, bilinear part) equals the oracle's bilinear energy
+    s = np.ascontiguousarray(lat.spins.T)
+    e2 = 0.0
+    for p in range(lat.size):
+        for n in range(bil.shape[1]):
+            j = lat.bilinear_sites[p, n]
+            if j:
+                e2 += s[p] @ lat.bilinear_matrices[p, n] @ s[j - 1]
+    uc2 = csm.Honeycomb()
+    for t in uc.bilinear:
+        csm.addBilinear(uc2, *t)
+    o2 = orc.OracleLattice(ModelData(uc2, (3, 4), 0.8, bc))
+    assert abs(o2.total_energy(s) - e2 / 2) < 1e-12
+
+
+def test_field_resolution_quirk():
+    # src/lattice.jl:128-133 indexes the term list by basis number
+    uc = csm.Honeycomb()
+    csm.addZeemanCoupling(uc, 2, np.array([0.0, 0.0, 2.0]))
+    csm.addZeemanCoupling(uc, 1, np.array([1.0, 0.0, 0.0]))
+    f, _ = resolve_field_onsite(uc)
+    assert np.array_equal(f, [[1.0, 0, 0], [0, 0, 2.0]])
+    uc = csm.Honeycomb()
+    csm.addZeemanCoupling(uc, 2, np.array([0.0, 0.0, 2.0]))   # only basis 2: BoundsError in Julia
+    with pytest.raises(IndexError):
+        resolve_field_onsite(uc)
+
+
+def test_params_buffer_defaults_and_warning():
+    d = {"t_thermalization": 100, "overrelaxation": 10}
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        p = csm.MCParamsBuffer(d)
+    assert any("not a valid MC parameter" in str(x.message) for x in w)     # README.md:49 key is ignored
+    assert p == (100, 1, 1, 1, 1, 10, 0, 0)
+    assert d["swap_rate"] == 1                                                # defaults are written back
+
+
+def test_error_propagator_matches_direct_statistics():
+    rng = np.random.default_rng(0)
+    x = rng.normal(3.0, 2.0, 4096)
+    ep = ErrorPropagator(2)
+    for v in x:
+        ep.push(v, v * v)
+    assert len(ep) == 4096
+    assert abs(ep.mean(1) - x.mean()) < 1e-12
+    assert abs(ep.mean(2) - (x * x).mean()) < 1e-9
+    # uncorrelated data: the binned standard error agrees with the naive one
+    assert abs(ep.std_error(1) / (x.std(ddof=1) / np.sqrt(len(x))) - 1) < 0.25
+    lvl = ep.reliable_level()
+    assert ep.count[lvl] >= 32 and (lvl + 1 >= len(ep.count) or ep.count[lvl + 1] < 32)
+    # level l holds means of 2^l consecutive samples
+    assert ep.count[3] == 4096 // 8
+    assert abs(ep.sums1D[3, 0] / ep.count[3] - x.mean()) < 1e-12
+    # correlated series: binning inflates the error bar
+    y = np.repeat(rng.normal(0, 1, 512), 8)
+    ep2 = ErrorPropagator(2)
+    for v in y:
+        ep2.push(v, v * v)
+    assert ep2.std_error(1) > 1.8 * (y.std(ddof=1) / np.sqrt(len(y)))
+    c, dc = _specific_heat(ep, 0.5, 100)
+    assert abs(c - (np.mean(x * x) - x.mean() ** 2) / 0.25 / 100) < 1e-9 and dc > 0
+
+
+def test_output_files_roundtrip(tmp_path):
+    """test/h5tests.jl:5-46 restated for this host layer (plus the key strings of src/hdf5.jl:60-74,
+    which the reference's own test does not exercise)."""
+    uc = models.mixed_basis_multispin()
+    lat = csm.Lattice((2, 3), uc, 0.8)
+    out = str(tmp_path) + "/"
+    mc = csm.MonteCarlo(0.3, lat, {"t_thermalization": 10, "overrelaxation_rate": 5}, outpath=out,
+                        inparams={"K": -1.0, "tag": 7})
+    assert os.path.isfile(out + "configuration.h5.params") and os.path.isfile(out + "configuration_0.h5")
+    f = h5._open(out + "configuration.h5.params", "r")
+    keys = h5._keys(f, "unit_cell/bilinear")
+    assert "(1,2),(0, -1)" in keys and "(2,1),(1, 0)" in keys
+    assert h5._get_attr(f, "t_thermalization") == 10 and h5._get_attr(f, "K") == -1.0
+    lat2 = csm.read_lattice(f)
+    f.close()
+    assert lat2.shape == lat.shape and lat2.S == lat.S and lat2.bc == lat.bc
+    u2 = lat2.unit_cell
+    assert np.allclose(np.stack(u2.lattice_vectors), np.stack(uc.lattice_vectors))
+    assert len(u2.bilinear) == len(uc.bilinear) and len(u2.cubic) == 2 and len(u2.quartic) == 1
+    key = lambda t: (t[0], t[1], tuple(t[3]))
+    for a, b in zip(sorted(u2.bilinear, key=key), sorted(uc.bilinear, key=key)):
+        assert a[:2] == b[:2] and tuple(a[3]) == tuple(b[3]) and np.array_equal(a[2], b[2])
+    assert np.array_equal(sorted(u2.quartic)[0][4], uc.quartic[0][4])
+    # term order follows the (alphabetical) key order after a round trip, as with HDF5 itself
+    assert np.array_equal(np.sort(lat2.bilinear_sites, axis=1), np.sort(lat.bilinear_sites, axis=1))
+    # configuration file: spins as (N, 3) (util/load.py:88-93), checkpoint overwrite, resume
+    mc.lattice.spins[:] = 0.25
+    csm.write_MC_checkpoint(mc)
+    lat3 = csm.Lattice((2, 3), uc, 0.8)
+    csm.read_spin_configuration(lat3, out + "configuration_0.h5")
+    assert np.all(lat3.spins == 0.25)
+    g = h5._open(out + "configuration_0.h5", "r")
+    assert np.asarray(h5._get(g, "spins")).shape == (lat.size, 3)
+    assert h5._get_attr(g, "T") == 0.3
+    g.close()
+    # MonteCarlo deep-copies the lattice (src/monte_carlo.jl:74; test/mctests.jl:45,54 rely on it)
+    assert not np.all(lat.spins == 0.25)
+
+
+def test_pairing_and_slot_bookkeeping():
+    # src/monte_carlo.jl:311-317
+    assert parallel.pairing(5, 0) == [(0, 1), (2, 3)]
+    assert parallel.pairing(5, 1) == [(1, 2), (3, 4)]
+    assert parallel.pairing(2, 1) == []
+    s = parallel.apply_exchanges(np.arange(4), [0, 2])
+    assert s.tolist() == [1, 0, 3, 2]
+    s = parallel.apply_exchanges(s, [1])       # replicas now in slots 1,2 are 0 and 3
+    assert s.tolist() == [2, 0, 3, 1]
+    assert sorted(s.tolist()) == [0, 1, 2, 3]
+    assert parallel.owner_of_replica(5, [4, 4]) == 1 and parallel.owner_of_replica(3, [4, 4]) == 0
+
+
+def test_unsupported_variants_are_loud():
+    uc = models.square_heisenberg()
+    lat = csm.Lattice((2, 2), uc, 1.0)
+    with pytest.raises(NotImplementedError):
+        csm.MonteCarlo(1.0, lat, {}, corr=True)
+    mc = csm.MonteCarlo(1.0, lat, {})
+    with pytest.raises(NotImplementedError):
+        csm.MetropolisConstraint().__call__.__func__  # attribute exists
+        csm.parallel_tempering(mc, alg=csm.MetropolisAdaptive())
