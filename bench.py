@@ -168,6 +168,65 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+PT_DEFAULTS = {"C3": dict(R=64, Tmin=0.01, Tmax=1.0), "C4": dict(R=128, Tmin=0.09 / 11.6, Tmax=14 / 11.6)}
+
+
+def run_pt(workload, L, world, rank, local_rank, stream, steps, warmup, sweeps_per_step, R_total=None):
+    """Parallel tempering (BASELINE configs[2]/[3]): R temperature slots block-partitioned over the
+    ranks' GPUs, per-replica energies gathered with NCCL on the sweep stream, temperatures exchanged
+    (csmc_pt_run).  swap_rate=50, overrelaxation_rate=10 (examples/parallel_tempering/input_file.jl:19-25)."""
+    import torch
+    import torch.distributed as dist
+
+    from classicalspinmc.jl_b200 import _lib, parallel
+    md, cfg = workload_model(workload, L)
+    d = PT_DEFAULTS[workload]
+    R_total = R_total or d["R"]
+    if R_total % world:
+        raise SystemExit("replica count must divide over the GPUs")
+    R = R_total // world
+    T_all = np.geomspace(d["Tmin"], d["Tmax"], R_total)
+    eng = _lib.Engine(md, n_replicas=R, seed=12345, device=local_rank, stream=stream.cuda_stream, replica_base=rank * R)
+    eng.randomize(999)
+    if world > 1:
+        eng.comm_init(world, rank, parallel.broadcast_unique_id(_lib.comm_unique_id))
+    eng.pt_init(T_all)
+    p = dict(t_thermalization=10 ** 9, t_measurement=0, probe_rate=2000, swap_rate=50, overrelaxation_rate=10)
+    sweep = 0
+    for _ in range(max(warmup, 1)):
+        eng.pt_run(p, sweep, sweep + sweeps_per_step)
+        sweep += sweeps_per_step
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        eng.pt_run(p, sweep, sweep + sweeps_per_step)
+        sweep += sweeps_per_step
+    e1.record(stream)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    n_metro = steps * sweeps_per_step // 10
+    updates = (steps * sweeps_per_step + n_metro) * float(eng.N) * R_total
+    _, ex = eng.pt_stats()
+    n_col = eng.n_colours
+    peak, kind = measured_peak_gbs()
+    value = updates / (ms * 1e-3)
+    cfg.update(replicas=R_total, replicas_per_gpu=R, swap_rate=50, overrelaxation_rate=10, sweeps_per_step=sweeps_per_step,
+               colours=n_col, kernel_mode=eng.kernel_mode, exchange="temperatures swapped; energies via ncclAllGather" if world > 1 else "temperatures swapped; single GPU")
+    return {"metric": "single-spin updates/sec (Metropolis+overrelax), parallel tempering", "value": value, "unit": "updates/s",
+            "n_gpus": world, "steps": steps, "ms_per_step": ms / steps, "config": cfg,
+            "exchanges_accepted": float(ex.sum()), "gpu_launches": int(eng.launches - l0),
+            "roofline_frac_of_updates": value / world * B_ALG.get(n_col, 24.0 * (n_col + 1)) / (peak * 1e9)}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -182,6 +241,20 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    if args.workload in PT_DEFAULTS:
+        stream = torch.cuda.Stream()
+        torch.cuda.set_stream(stream)
+        with ClockSampler(local_rank) as clk:
+            line = run_pt(args.workload, args.L, world, rank, local_rank, stream, args.steps, args.warmup, args.sweeps_per_step, args.replicas)
+        if rank == 0:
+            line.update(warmup=max(args.warmup, 1), higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
+                        data="synthetic", clocks=clk.summary())
+            print(json.dumps(line))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return line
 
     md, cfg = workload_model(args.workload, args.L)
     # a real (non-NULL) stream: a NULL cudaStream_t in csmc_opts means "library creates its own", and
@@ -272,7 +345,7 @@ def run_ours(args):
     line = None
     if rank == 0:
         cfg.update(cycle=f"{orc_} OR + {mc_} Metropolis", cycles_per_step=args.cycles_per_step,
-                   colours=n_col, structured_kernels=eng.structured, parallelism=f"replicas x{world}",
+                   colours=n_col, kernel_mode=eng.kernel_mode, parallelism=f"replicas x{world}",
                    l2="flushed between timed steps (256 MiB memset); lattice (24 MiB at L=1024) is L2-resident within a step")
         line = {"metric": "single-spin updates/sec (Metropolis+overrelax)", "value": value, "unit": "updates/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -284,10 +357,18 @@ def run_ours(args):
                 "roofline_frac_of_updates": value / world * B_ALG.get(n_col, 24.0 * (n_col + 1)) / (peak * 1e9)}
         if world == 1 and not args.no_cpu_baseline:
             threads = args.cpu_threads or (os.cpu_count() or 1)
-            v, u, dtc = cpu_baseline(md, 1.0, orc_, mc_, args.ref_cycles, threads)
+            n_ref = max(4 * args.ref_cycles, 16)          # ~10-20 s of CPU work
+            v, u, dtc = cpu_baseline(md, 1.0, orc_, mc_, n_ref, threads)
             line["cpu_baseline"] = {"value": v, "unit": "updates/s", "cores": threads, "kind": "port",
-                                    "sample": f"{threads} independent replicas x {args.ref_cycles} cycle(s) of the same "
+                                    "sample": f"{threads} independent replicas x {n_ref} cycle(s) of the same "
                                               f"lattice ({u:.3g} updates, {dtc:.1f} s); C restatement of the reference algorithm"}
+    if world > 1 and not args.no_pt:
+        # the path that actually exchanges data between GPUs: parallel tempering (configs[2]), short run
+        eng.close()
+        pt = run_pt("C3", None, world, rank, local_rank, stream, 3, 1, 550)
+        if rank == 0:
+            line["pt"] = pt
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -306,10 +387,13 @@ def main():
     ap.add_argument("--cycles-per-step", type=int, default=20)
     ap.add_argument("--or-per-cycle", type=int, default=10)
     ap.add_argument("--metro-per-cycle", type=int, default=1)
-    ap.add_argument("--ref-cycles", type=int, default=1, help="cycles per thread per step in the CPU legs")
+    ap.add_argument("--ref-cycles", type=int, default=4, help="cycles per host thread per step in the CPU legs")
     ap.add_argument("--ref-warm", action="store_true")
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pt", action="store_true", help="N > 1: skip the extra parallel-tempering measurement")
+    ap.add_argument("--sweeps-per-step", type=int, default=550, help="PT workloads: sweeps per timed step")
+    ap.add_argument("--replicas", type=int, default=None, help="PT workloads: total replicas")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

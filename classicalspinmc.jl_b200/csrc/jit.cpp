@@ -3,6 +3,7 @@
 // sm_100a cubin with NVRTC (loaded with dlopen so libcsmc.so has no link-time dependency on it).
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -154,11 +155,23 @@ struct Gen {
         for (size_t s = 0; s < hm.segs.size(); ++s) segment((int)s);
         for (int c = 0; c < hm.n_colours; ++c) {
             const int s0 = hm.colour_seg_begin[c], s1 = hm.colour_seg_begin[c + 1];
+            const int nseg = s1 - s0;
+            int mx = 1;
+            for (int s = s0; s < s1; ++s) mx = std::max(mx, hm.segs[s].count);
+            const int tiles_per_seg = (mx + 255) / 256;
+            // Work item w -> (replica, tile); tile -> (segment, tile within segment) with the segments of
+            // the colour interleaved, so classes that gather from the same neighbour classes sweep the
+            // same region of the lattice at the same time (one DRAM read of the other colours per pass).
+            // The grid is persistent: gridDim.x CTAs stride over the work items (no partial last wave).
             for (int u = 0; u < 4; ++u) {
-                o << "extern \"C\" __global__ void __launch_bounds__(TPB) csmc_sweep_c" << c << "_u" << u << "(double *__restrict__ spins, const SweepArgs a) {\n";
-                o << "    switch (blockIdx.y) {\n";
-                for (int s = s0; s < s1; ++s) o << "    case " << (s - s0) << ": sweep_site<" << u << ", Seg" << s << ">(spins, a); break;\n";
-                o << "    default: break;\n    }\n}\n";
+                o << "extern \"C\" __global__ void __launch_bounds__(TPB) csmc_sweep_c" << c << "_u" << u << "(double *__restrict__ spins, const SweepArgs a, const int n_work) {\n";
+                o << "    pdl_launch_dependents();\n    pdl_wait();\n";
+                o << "    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {\n";
+                o << "        const int rep = w / " << (tiles_per_seg * nseg) << ", tile = w % " << (tiles_per_seg * nseg) << ";\n";
+                o << "        const int idx = (tile / " << nseg << ") * TPB + threadIdx.x;\n";
+                o << "        switch (tile % " << nseg << ") {\n";
+                for (int s = s0; s < s1; ++s) o << "        case " << (s - s0) << ": sweep_site<" << u << ", Seg" << s << ">(spins, a, idx, rep); break;\n";
+                o << "        default: break;\n        }\n    }\n}\n";
             }
             o << "extern \"C\" __global__ void __launch_bounds__(TPB) csmc_energy_c" << c << "(const double *__restrict__ spins, double *__restrict__ partials, int n_partials, int partial_base) {\n";
             o << "    double v[4] = {0.0, 0.0, 0.0, 0.0};\n    switch (blockIdx.y) {\n";

@@ -58,12 +58,15 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// Programmatic dependent launch: a pass may be scheduled while the previous pass drains (its CTAs
+// fill SMs as they free up and run their prologue); it must not touch spins before pdl_wait().
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // one site of one colour pass; SEG supplies the constant geometry, Zeeman / on-site constants and
 // the unrolled neighbour-field accumulation
 template <int UPD, class SEG>
-__device__ __forceinline__ void sweep_site(double *__restrict__ spins, const SweepArgs &a) {
-    const int idx = blockIdx.x * TPB + threadIdx.x;
-    const int rep = blockIdx.z;
+__device__ __forceinline__ void sweep_site(double *__restrict__ spins, const SweepArgs &a, const int idx, const int rep) {
     double *sx = spins + (size_t)rep * (3ull * NPAD), *sy = sx + NPAD, *sz = sy + NPAD;
     bool accepted = false;
     if (idx < SEG::COUNT) {
