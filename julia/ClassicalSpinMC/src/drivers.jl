@@ -1,0 +1,247 @@
+# MonteCarlo object and the three drivers.  Schedules follow src/monte_carlo.jl:157-398 of the
+# reference; sweeps run on the GPU.  MPI is optional: with MPI.jl loaded and initialised, each rank is
+# one process per GPU holding `length(T)` temperature slots (T may be a scalar, as in the reference).
+
+struct SimulationParameters
+    t_thermalization::Int64
+    t_deterministic::Int64
+    t_measurement::Int64
+    probe_rate::Int64
+    swap_rate::Int64
+    overrelaxation_rate::Int64
+    report_interval::Int64
+    checkpoint_rate::Int64
+end
+
+function MCParamsBuffer(dict::Dict{String,Int64})::SimulationParameters
+    names = String.(collect(fieldnames(SimulationParameters)))
+    defaults = (1, 1, 1, 1, 1, 10, 0, 0)
+    for (k, v) in zip(names, defaults)
+        haskey(dict, k) || (dict[k] = v)
+    end
+    for k in keys(dict)
+        k in names || @warn "'$k' not a valid MC parameter; ignoring"
+    end
+    return SimulationParameters((dict[k] for k in names)...)
+end
+
+mutable struct MonteCarlo
+    T::Float64
+    temperatures::Vector{Float64}
+    parameters::SimulationParameters
+    lattice::Lattice
+    observables::Observables
+    observables_all::Vector{Observables}
+    replica_spins::Vector{Matrix{Float64}}
+    lambda::Float64
+    weight::Float64
+    constraint::Function
+    outpath::String
+    outdir::String
+    outprefix::String
+    sigma::Real
+    sigma0::Real
+    corr::Bool
+    momentum_vectors::Array{Float64,2}
+    seed::UInt64
+    engine::Union{Nothing,Engine}
+    rank::Int
+    comm_size::Int
+end
+
+# hooks a host program overrides when it runs under MPI.jl (kept as plain functions so the package
+# loads without MPI):  comm_rank(), comm_size(), allgather_temperatures(T), bcast_bytes(v), barrier()
+comm_rank() = 0
+comm_size() = 1
+allgather_temperatures(T::Vector{Float64}) = T
+bcast_bytes(v::Vector{UInt8}) = v
+barrier() = nothing
+
+function MonteCarlo(T::Union{Float64,Vector{Float64}}, lattice::Lattice{D}, parameters::Dict{String,Int64};
+                    constraint::Function=x -> 0.0, weight::Float64=0.0, outpath::String="", outprefix::String="configuration",
+                    inparams::Dict{String,<:Any}=Dict{String,Any}(), overwrite::Bool=true, sigma0::Real=60,
+                    corr::Bool=false, ks::Matrix{Float64}=Matrix{Float64}(undef, D, 0), seed::UInt64=rand(UInt64) >> 1) where {D}
+    corr && error("equal-time structure factor (corr=true) is not part of this drop-in")
+    temps = T isa Float64 ? [T] : copy(T)
+    lat = deepcopy(lattice)
+    lat.engine = nothing
+    mc = MonteCarlo(temps[1], temps, MCParamsBuffer(parameters), lat, Observables(), [Observables() for _ in temps],
+                    [r == 1 ? lat.spins : copy(lat.spins) for r in eachindex(temps)], 0.0, weight, constraint, "", outpath, outprefix,
+                    sigma0, sigma0, corr, ks, seed, nothing, comm_rank(), comm_size())
+    mc.observables = mc.observables_all[1]
+    if length(outpath) > 0
+        mc.rank == 0 && !isdir(outpath) && mkdir(outpath)
+        barrier()
+        mc.outpath = string(outpath, outprefix, "_", mc.rank, ".h5")
+        paramsfile = string(outpath, outprefix, ".h5.params")
+        if mc.rank == 0 && !isfile(paramsfile) && overwrite
+            create_params_file(mc, paramsfile)
+            isempty(inparams) || write_attributes(paramsfile, inparams)
+        end
+        if !isfile(mc.outpath) && overwrite
+            println("Creating new file $(basename(mc.outpath)) for output on rank $(mc.rank)")
+            initialize_hdf5(mc, paramsfile)
+        end
+    end
+    return mc
+end
+
+function device!(mc::MonteCarlo; replica_base=0)
+    R = length(mc.temperatures)
+    if mc.engine === nothing || mc.engine.n_replicas != R || mc.engine.replica_base != replica_base
+        model, buffers = pack_model(mc.lattice.unit_cell, mc.lattice.shape, mc.lattice.S, mc.lattice.bc)
+        mc.engine = create_engine(model, buffers; n_replicas=R, seed=mc.seed, replica_base=replica_base,
+                                  device=parse(Int, get(ENV, "LOCAL_RANK", "0")))
+    end
+    return mc.engine
+end
+function upload!(mc::MonteCarlo; kw...)
+    e = device!(mc; kw...)
+    mc.replica_spins[1] = mc.lattice.spins
+    for (r, s) in enumerate(mc.replica_spins)
+        set_spins!(e, s, r - 1)
+    end
+    return e
+end
+function download!(mc::MonteCarlo)
+    for (r, s) in enumerate(mc.replica_spins)
+        get_spins!(mc.engine, s, r - 1)
+    end
+    mc.lattice.spins = mc.replica_spins[1]
+end
+
+# --- the `alg` plug-in seam (src/metropolis.jl:181-199) ------------------------------------------------------
+metropolis!(mc::MonteCarlo, T::Float64)::Float64 = metropolis_sweeps!(device!(mc), fill(T, length(mc.temperatures)))[1]
+function metropolis_adaptive!(mc::MonteCarlo, T::Float64)::Float64
+    sig = fill(Float64(mc.sigma), length(mc.temperatures))
+    acc = metropolis_cone_sweeps!(device!(mc), fill(T, length(sig)), sig, true)
+    mc.sigma = sig[1]
+    return acc[1]
+end
+metropolis_fixed_cone!(mc::MonteCarlo, T::Float64)::Float64 =
+    metropolis_cone_sweeps!(device!(mc), fill(T, length(mc.temperatures)), fill(Float64(mc.sigma), length(mc.temperatures)), false)[1]
+unsupported_constraint!(mc::MonteCarlo, T::Float64)::Float64 =
+    error("MetropolisConstraint variants are not part of the device path (the reference's metropolis_constraint! calls an undefined e_diff)")
+
+const AlgWrapper = FunctionWrapper{Float64,Tuple{MonteCarlo,Float64}}
+Metropolis() = AlgWrapper(metropolis!)
+MetropolisAdaptive() = AlgWrapper(metropolis_adaptive!)
+MetropolisFixedCone() = AlgWrapper(metropolis_fixed_cone!)
+MetropolisConstraint() = AlgWrapper(unsupported_constraint!)
+MetropolisConstraintAdaptive() = AlgWrapper(unsupported_constraint!)
+is_plain_metropolis(alg::AlgWrapper) = alg.obj[] === metropolis!
+
+# --- simulated annealing (src/monte_carlo.jl:157-190) ---------------------------------------------------------
+function simulated_annealing!(mc::MonteCarlo, schedule::Function, T0::Float64=1.0; alg::AlgWrapper=Metropolis())
+    p = mc.parameters
+    T, time = T0, 1
+    out = length(mc.outpath) > 0
+    accept_total = p.t_thermalization * mc.lattice.size
+    p.overrelaxation_rate != 0 && (accept_total /= p.overrelaxation_rate)
+    e = upload!(mc)
+    while T > mc.T
+        R = 0.0
+        mc.sigma = mc.sigma0
+        if is_plain_metropolis(alg)
+            R = anneal_temperature!(e, fill(T, e.n_replicas), p.t_thermalization, p.overrelaxation_rate)[1]
+        else
+            for t in 1:(p.t_thermalization-1)
+                if p.overrelaxation_rate != 0
+                    overrelax!(e)
+                    t % p.overrelaxation_rate == 0 && (R += alg(mc, T))
+                else
+                    R += alg(mc, T)
+                end
+            end
+        end
+        println("Acceptance rate at T=$T: $(round(R/accept_total*100, digits=5)) % ")
+        T = schedule(time)
+        time += 1
+        if out
+            download!(mc)
+            write_MC_checkpoint(mc)
+        end
+    end
+    download!(mc)
+end
+
+# --- deterministic updates (src/monte_carlo.jl:201-213) as colour-ordered full sweeps -----------------------
+function deterministic_updates!(mc::MonteCarlo)
+    n_sweeps = cld(max(mc.parameters.t_deterministic - 1, 0), mc.lattice.size)
+    e = upload!(mc)
+    done = 0
+    while done < n_sweeps
+        k = min(4096, n_sweeps - done)
+        deterministic!(e, k)
+        done += k
+    end
+    download!(mc)
+end
+
+# --- parallel tempering (src/monte_carlo.jl:235-398) ------------------------------------------------------------
+function parallel_tempering!(mc::MonteCarlo, saveIC::Vector{Int64}=Int64[]; alg::AlgWrapper=Metropolis())
+    is_plain_metropolis(alg) || error("parallel_tempering! on the device supports alg=Metropolis()")
+    p = mc.parameters
+    rank, nranks = comm_rank(), comm_size()
+    R = length(mc.temperatures)
+    T_all = allgather_temperatures(mc.temperatures)
+    n_slots = length(T_all)
+    n_slots == 1 && @warn "a single temperature slot; no replica exchanges will occur!"
+    base = rank * R
+    out = length(mc.outdir) > 0
+    e = upload!(mc; replica_base=base)
+    if nranks > 1
+        id = rank == 0 ? comm_unique_id() : zeros(UInt8, 128)
+        comm_init!(e, nranks, rank, bcast_bytes(id))
+    end
+    pt_init!(e, T_all)
+    slotfile(s) = string(mc.outdir, mc.outprefix, "_", s, ".h5")
+    rank == 0 && @printf("Running sweeps on %s.\n", Dates.format(Dates.now(), "dd u yyyy HH:MM:SS"))
+    total = p.t_thermalization + p.t_measurement
+    cp = CsmcPtParams(p.t_thermalization, p.t_measurement, p.probe_rate, p.swap_rate, p.overrelaxation_rate, 0)
+    sweep = 0
+    buf = similar(mc.lattice.spins)
+    while sweep < total
+        nxt = total
+        if p.checkpoint_rate > 0
+            c = cld(max(sweep, p.t_thermalization), p.checkpoint_rate) * p.checkpoint_rate
+            c < total && (nxt = min(nxt, c + 1))
+        end
+        p.report_interval > 0 && (nxt = min(nxt, (sweep ÷ p.report_interval + 1) * p.report_interval))
+        pt_run!(e, cp, sweep, nxt)
+        last = nxt - 1
+        if out && p.checkpoint_rate > 0 && last >= p.t_thermalization && last % p.checkpoint_rate == 0
+            slots = pt_slots(e, n_slots)
+            for r in 1:R
+                get_spins!(e, buf, r - 1)
+                s = slots[base+r]
+                write_spins(slotfile(s), buf)
+                if s in saveIC
+                    step = (last - p.t_thermalization) ÷ p.checkpoint_rate
+                    write_initial_configuration(string(mc.outdir, "IC_", s, "/IC_", step, ".h5"), T_all[s+1], slotfile(s), buf)
+                end
+            end
+        end
+        sweep = nxt
+        if p.report_interval > 0 && sweep % p.report_interval == 0 && rank == 0
+            acc, exch = pt_stats(e, n_slots)
+            @printf("Sweep %d / %d (%.1f%%)\n", sweep, total, 100.0 * sweep / total)
+            for k in 1:n_slots
+                @printf("\t\tsimulation %d accepted updates : %.0f\texchanges : %.0f\n", k - 1, acc[k], exch[k])
+            end
+        end
+    end
+    E, M = pt_series(e, n_slots)
+    for r in 1:R, k in 1:size(E, 2)
+        update_observables!(mc.observables_all[r], E[base+r, k], M[base+r, k])
+    end
+    download!(mc)          # configurations stay with their replicas; slots = pt_slots(e, n_slots)
+    if out
+        slots = pt_slots(e, n_slots)
+        for r in 1:R
+            write_final_observables(slotfile(slots[base+r]), mc.replica_spins[r], mc.observables_all[findfirst(==(slots[base+r]), base:base+R-1) === nothing ? r : slots[base+r]-base+1], T_all[slots[base+r]+1], mc.lattice.size)
+        end
+    end
+    rank == 0 && @printf("Simulation finished on %s.\n", Dates.format(Dates.now(), "dd u yyyy HH:MM:SS"))
+    return
+end

@@ -1,0 +1,146 @@
+# ccall layer over include/csmc.h.  Every wrapper names the C export it binds.
+
+const libcsmc = get(ENV, "CSMC_LIB", "libcsmc.so")
+
+struct CsmcModel
+    dim::Int32
+    shape::NTuple{3,Int32}
+    n_basis::Int32
+    periodic::Int32
+    S::Float64
+    field::Ptr{Float64}
+    onsite::Ptr{Float64}
+    n_bilinear::Int32
+    bil_basis::Ptr{Int32}
+    bil_offset::Ptr{Int32}
+    bil_matrix::Ptr{Float64}
+    n_cubic::Int32
+    cub_basis::Ptr{Int32}
+    cub_offset::Ptr{Int32}
+    cub_tensor::Ptr{Float64}
+    n_quartic::Int32
+    quar_basis::Ptr{Int32}
+    quar_offset::Ptr{Int32}
+    quar_tensor::Ptr{Float64}
+end
+
+struct CsmcOpts
+    device::Int32
+    n_replicas::Int32
+    seed::UInt64
+    stream::Ptr{Cvoid}
+    replica_base::Int32
+    flags::Int32
+end
+
+struct CsmcPtParams
+    t_thermalization::Int64
+    t_measurement::Int64
+    probe_rate::Int32
+    swap_rate::Int32
+    overrelaxation_rate::Int32
+    reserved::Int32
+end
+
+"Owns a `csmc_handle*`; destroyed by the finalizer."
+mutable struct Engine
+    ptr::Ptr{Cvoid}
+    n_sites::Int
+    n_replicas::Int
+    replica_base::Int
+    buffers::Any            # host arrays the model struct pointed into (kept alive until create returns)
+    function Engine(ptr, n_sites, n_replicas, replica_base, buffers)
+        e = new(ptr, n_sites, n_replicas, replica_base, buffers)
+        finalizer(x -> (x.ptr == C_NULL || ccall((:csmc_destroy, libcsmc), Int32, (Ptr{Cvoid},), x.ptr); x.ptr = C_NULL), e)
+        return e
+    end
+end
+
+last_error(p::Ptr{Cvoid}) = unsafe_string(ccall((:csmc_last_error, libcsmc), Cstring, (Ptr{Cvoid},), p))
+check(e::Engine, rc) = rc == 0 ? nothing : error("libcsmc: " * last_error(e.ptr))
+check(::Nothing, rc) = rc == 0 ? nothing : error("libcsmc: " * last_error(C_NULL))
+
+function create_engine(model::CsmcModel, buffers; n_replicas=1, seed=rand(UInt64) >> 1, device=0, replica_base=0, flags=0)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    opts = CsmcOpts(device, n_replicas, seed, C_NULL, replica_base, flags)
+    GC.@preserve buffers begin
+        check(nothing, ccall((:csmc_create, libcsmc), Int32, (Ref{CsmcModel}, Ref{CsmcOpts}, Ref{Ptr{Cvoid}}), Ref(model), Ref(opts), h))
+    end
+    n = Ref{Int64}(0)
+    ccall((:csmc_n_sites, libcsmc), Int32, (Ptr{Cvoid}, Ref{Int64}), h[], n)
+    return Engine(h[], Int(n[]), n_replicas, replica_base, nothing)
+end
+
+# --- state ---------------------------------------------------------------------------------------------
+set_spins!(e::Engine, spins::Matrix{Float64}, replica=0) =
+    check(e, ccall((:csmc_set_spins, libcsmc), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}), e.ptr, replica, spins))
+get_spins!(e::Engine, spins::Matrix{Float64}, replica=0) =
+    check(e, ccall((:csmc_get_spins, libcsmc), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}), e.ptr, replica, spins))
+
+# --- Hamiltonian -----------------------------------------------------------------------------------------
+function local_field(e::Engine, site::Integer, replica=0)
+    out = zeros(3)
+    check(e, ccall((:csmc_local_field, libcsmc), Int32, (Ptr{Cvoid}, Int32, Int64, Ptr{Float64}), e.ptr, replica, site, out))
+    return (out[1], out[2], out[3])
+end
+function total_energies(e::Engine)
+    E = zeros(e.n_replicas)
+    check(e, ccall((:csmc_total_energy, libcsmc), Int32, (Ptr{Cvoid}, Ptr{Float64}), e.ptr, E))
+    return E
+end
+function magnetization_vectors(e::Engine)
+    M = zeros(3, e.n_replicas)
+    check(e, ccall((:csmc_magnetization, libcsmc), Int32, (Ptr{Cvoid}, Ptr{Float64}), e.ptr, M))
+    return M
+end
+
+# --- sweeps ------------------------------------------------------------------------------------------------
+overrelax!(e::Engine, n=1) = check(e, ccall((:csmc_overrelax, libcsmc), Int32, (Ptr{Cvoid}, Int32), e.ptr, n))
+deterministic!(e::Engine, n=1) = check(e, ccall((:csmc_deterministic, libcsmc), Int32, (Ptr{Cvoid}, Int32), e.ptr, n))
+function metropolis_sweeps!(e::Engine, T::Vector{Float64}, n=1)
+    acc = zeros(e.n_replicas)
+    check(e, ccall((:csmc_metropolis, libcsmc), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int32, Ptr{Float64}), e.ptr, T, n, acc))
+    return acc
+end
+function metropolis_cone_sweeps!(e::Engine, T::Vector{Float64}, sigma::Vector{Float64}, adapt::Bool, n=1)
+    acc = zeros(e.n_replicas)
+    check(e, ccall((:csmc_metropolis_cone, libcsmc), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Ptr{Float64}),
+                   e.ptr, T, sigma, adapt ? 1 : 0, n, acc))
+    return acc
+end
+function anneal_temperature!(e::Engine, T::Vector{Float64}, t_thermalization::Integer, rate::Integer)
+    acc = zeros(e.n_replicas)
+    check(e, ccall((:csmc_anneal_temperature, libcsmc), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Ptr{Float64}),
+                   e.ptr, T, t_thermalization, rate, acc))
+    return acc
+end
+
+# --- parallel tempering --------------------------------------------------------------------------------------
+function comm_unique_id()
+    id = zeros(UInt8, 128)
+    check(nothing, ccall((:csmc_comm_unique_id, libcsmc), Int32, (Ptr{UInt8},), id))
+    return id
+end
+comm_init!(e::Engine, n_ranks, rank, id::Vector{UInt8}) =
+    check(e, ccall((:csmc_comm_init, libcsmc), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{UInt8}), e.ptr, n_ranks, rank, id))
+pt_init!(e::Engine, T_all::Vector{Float64}) =
+    check(e, ccall((:csmc_pt_init, libcsmc), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}), e.ptr, length(T_all), T_all))
+pt_run!(e::Engine, p::CsmcPtParams, sweep_begin, sweep_end) =
+    check(e, ccall((:csmc_pt_run, libcsmc), Int32, (Ptr{Cvoid}, Ref{CsmcPtParams}, Int64, Int64), e.ptr, Ref(p), sweep_begin, sweep_end))
+function pt_slots(e::Engine, n_slots)
+    s = zeros(Int32, n_slots)
+    check(e, ccall((:csmc_pt_get_slots, libcsmc), Int32, (Ptr{Cvoid}, Ptr{Int32}), e.ptr, s))
+    return s
+end
+function pt_series(e::Engine, n_slots)
+    n = Ref{Int64}(0)
+    check(e, ccall((:csmc_pt_get_series, libcsmc), Int32, (Ptr{Cvoid}, Ref{Int64}, Ptr{Float64}, Ptr{Float64}), e.ptr, n, C_NULL, C_NULL))
+    E = zeros(n_slots, n[]); M = zeros(n_slots, n[])      # column k = probe k (C layout [probe][slot])
+    check(e, ccall((:csmc_pt_get_series, libcsmc), Int32, (Ptr{Cvoid}, Ref{Int64}, Ptr{Float64}, Ptr{Float64}), e.ptr, n, E, M))
+    return E, M
+end
+function pt_stats(e::Engine, n_slots)
+    a = zeros(n_slots); x = zeros(n_slots)
+    check(e, ccall((:csmc_pt_get_stats, libcsmc), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), e.ptr, a, x))
+    return a, x
+end
