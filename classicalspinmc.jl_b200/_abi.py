@@ -62,7 +62,7 @@ FLAG_FORCE_GENERIC = 1
 FLAG_NO_GRAPH = 2
 FLAG_JIT = 4
 FLAG_NO_JIT = 8
-FLAG_NO_PDL = 16
+FLAG_PDL = 16
 
 
 def resolve_field_onsite(uc):

@@ -94,7 +94,6 @@ struct csmc_handle {
     bool jit = false;
     cudaLibrary_t jit_lib = nullptr;
     std::vector<cudaKernel_t> jit_sweep[4], jit_energy;
-    int jit_grid[4] = {0, 0, 0, 0};   // persistent grid size per update kind: SMs x resident CTAs
     std::string jit_note;
 
     // CUDA graph of one bench cycle
@@ -132,19 +131,17 @@ void launch_sweep_pass(csmc_handle *h, int colour, const SweepArgs &a) {
     const int nseg = h->hm.colour_seg_begin[colour + 1] - h->hm.colour_seg_begin[colour];
     dim3 grid(h->pass_blocks[colour], nseg, h->R), block(TPB);
     if (h->jit) {
-        // persistent grid striding over (replica, tile) work items, launched with programmatic stream
-        // serialization so its CTAs can be scheduled while the previous pass drains
-        int n_work = h->pass_blocks[colour] * nseg * h->R;
-        void *args[] = {(void *)&h->d_spins, (void *)&a, (void *)&n_work};
+        // segments of the colour are interleaved along blockIdx.x (see jit.cpp)
+        void *args[] = {(void *)&h->d_spins, (void *)&a};
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(std::min(n_work, h->jit_grid[UPD]), 1, 1);
+        cfg.gridDim = dim3(h->pass_blocks[colour] * nseg, 1, h->R);
         cfg.blockDim = block;
         cfg.stream = h->stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = (h->flags & CSMC_FLAG_NO_PDL) ? 0 : 1;
+        cfg.numAttrs = (h->flags & CSMC_FLAG_PDL) ? 1 : 0;
         cudaLaunchKernelExC(&cfg, (const void *)h->jit_sweep[UPD][colour], args);
     } else if (h->large) {
         if (h->hm.structured) k_sweep<PassLarge, true, UPD><<<grid, block, 0, h->stream>>>(h->pl[colour], a);
@@ -374,7 +371,7 @@ int32_t csmc_create(const csmc_model *model, const csmc_opts *opts, csmc_handle 
             std::string err, log;
             std::vector<char> cubin;
             try {
-                const std::string src = jit_generate_source(hm);
+                const std::string src = jit_generate_source(hm, (h->flags & CSMC_FLAG_PDL) != 0);
                 err = jit_compile(src, cubin, log);
             } catch (const std::exception &ex) {
                 err = std::string("code generation failed: ") + ex.what();
@@ -395,18 +392,6 @@ int32_t csmc_create(const csmc_model *model, const csmc_opts *opts, csmc_handle 
                 for (int c = 0; c < hm.n_colours && err.empty(); ++c) {
                     const std::string nm = "csmc_energy_c" + std::to_string(c);
                     if (cudaLibraryGetKernel(&h->jit_energy[c], h->jit_lib, nm.c_str()) != cudaSuccess) err = "kernel not found: " + nm;
-                }
-            }
-            if (err.empty()) {
-                cudaDeviceProp prop;
-                cudaGetDeviceProperties(&prop, h->device);
-                for (int u = 0; u < 4; ++u) {
-                    int per_sm = 0;
-                    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)h->jit_sweep[u][0], TPB, 0) != cudaSuccess || per_sm < 1) {
-                        cudaGetLastError();
-                        per_sm = 4;
-                    }
-                    h->jit_grid[u] = prop.multiProcessorCount * per_sm;
                 }
             }
             if (err.empty()) h->jit = true;

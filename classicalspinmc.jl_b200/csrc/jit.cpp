@@ -159,19 +159,19 @@ struct Gen {
             int mx = 1;
             for (int s = s0; s < s1; ++s) mx = std::max(mx, hm.segs[s].count);
             const int tiles_per_seg = (mx + 255) / 256;
-            // Work item w -> (replica, tile); tile -> (segment, tile within segment) with the segments of
-            // the colour interleaved, so classes that gather from the same neighbour classes sweep the
-            // same region of the lattice at the same time (one DRAM read of the other colours per pass).
-            // The grid is persistent: gridDim.x CTAs stride over the work items (no partial last wave).
+            // grid = (tiles_per_seg * nseg, 1, replicas).  The segments (classes) of the colour are
+            // interleaved along blockIdx.x, so classes that gather from the same neighbour classes sweep
+            // the same region of the lattice at the same time: the other colours are read from DRAM once
+            // per pass instead of once per class (measured at L=4096: 604 MB -> 402 MB read per pass).
+            (void)tiles_per_seg;
             for (int u = 0; u < 4; ++u) {
-                o << "extern \"C\" __global__ void __launch_bounds__(TPB) csmc_sweep_c" << c << "_u" << u << "(double *__restrict__ spins, const SweepArgs a, const int n_work) {\n";
-                o << "    pdl_launch_dependents();\n    pdl_wait();\n";
-                o << "    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {\n";
-                o << "        const int rep = w / " << (tiles_per_seg * nseg) << ", tile = w % " << (tiles_per_seg * nseg) << ";\n";
-                o << "        const int idx = (tile / " << nseg << ") * TPB + threadIdx.x;\n";
-                o << "        switch (tile % " << nseg << ") {\n";
-                for (int s = s0; s < s1; ++s) o << "        case " << (s - s0) << ": sweep_site<" << u << ", Seg" << s << ">(spins, a, idx, rep); break;\n";
-                o << "        default: break;\n        }\n    }\n}\n";
+                o << "extern \"C\" __global__ void __launch_bounds__(TPB) csmc_sweep_c" << c << "_u" << u << "(double *__restrict__ spins, const SweepArgs a) {\n";
+                o << "#ifdef CSMC_PDL\n    pdl_launch_dependents();\n    pdl_wait();\n#endif\n";
+                o << "    const int rep = blockIdx.z, tile = blockIdx.x;\n";
+                o << "    const int idx = (tile / " << nseg << ") * TPB + threadIdx.x;\n";
+                o << "    switch (tile % " << nseg << ") {\n";
+                for (int s = s0; s < s1; ++s) o << "    case " << (s - s0) << ": sweep_site<" << u << ", Seg" << s << ">(spins, a, idx, rep); break;\n";
+                o << "    default: break;\n    }\n}\n";
             }
             o << "extern \"C\" __global__ void __launch_bounds__(TPB) csmc_energy_c" << c << "(const double *__restrict__ spins, double *__restrict__ partials, int n_partials, int partial_base) {\n";
             o << "    double v[4] = {0.0, 0.0, 0.0, 0.0};\n    switch (blockIdx.y) {\n";
@@ -221,9 +221,10 @@ bool load_nvrtc() {
 
 }  // namespace
 
-std::string jit_generate_source(const HostModel &hm) {
+std::string jit_generate_source(const HostModel &hm, bool pdl) {
     Gen g(hm);
-    return g.run();
+    std::string src = g.run();
+    return pdl ? "#define CSMC_PDL 1\n" + src : src;
 }
 
 // returns "" on success

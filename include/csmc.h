@@ -90,8 +90,9 @@ typedef struct csmc_opts {
 #define CSMC_FLAG_JIT 4           /* require the runtime-specialised (NVRTC) kernels: fail     \
                                      csmc_create if they cannot be built                      */
 #define CSMC_FLAG_NO_JIT 8        /* never specialise at run time (ahead-of-time kernels only) */
-#define CSMC_FLAG_NO_PDL 16       /* launch passes fully serialised (no programmatic dependent  \
-                                     launch); for A/B measurements                             */
+#define CSMC_FLAG_PDL 16          /* launch the specialised passes with programmatic dependent  \
+                                     launch (griddepcontrol); measured slower on B200 for the   \
+                                     BASELINE sizes, kept for A/B measurements                  */
 /* Default: models whose colouring is a periodic pattern get kernels specialised for that model
  * (unrolled terms, literal coefficients, constant geometry; compiled for sm_100a with NVRTC at
  * csmc_create) when n_sites * n_replicas >= 32768; smaller problems are launch-latency bound and
