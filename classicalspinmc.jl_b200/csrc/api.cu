@@ -94,6 +94,7 @@ struct csmc_handle {
     bool jit = false;
     cudaLibrary_t jit_lib = nullptr;
     std::vector<cudaKernel_t> jit_sweep[4], jit_energy;
+    JitPlan jit_plan;
     std::string jit_note;
 
     // CUDA graph of one bench cycle
@@ -131,10 +132,10 @@ void launch_sweep_pass(csmc_handle *h, int colour, const SweepArgs &a) {
     const int nseg = h->hm.colour_seg_begin[colour + 1] - h->hm.colour_seg_begin[colour];
     dim3 grid(h->pass_blocks[colour], nseg, h->R), block(TPB);
     if (h->jit) {
-        // segments of the colour are interleaved along blockIdx.x (see jit.cpp)
+        // multi-dimensional CTA tiles over supercell coordinates, classes fused per thread (jit.cpp)
         void *args[] = {(void *)&h->d_spins, (void *)&a};
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(h->pass_blocks[colour] * nseg, 1, h->R);
+        cfg.gridDim = dim3(h->jit_plan.tiles[colour], h->jit_plan.groups[colour], h->R);
         cfg.blockDim = block;
         cfg.stream = h->stream;
         cudaLaunchAttribute attr[1];
@@ -363,7 +364,7 @@ int32_t csmc_create(const csmc_model *model, const csmc_opts *opts, csmc_handle 
     }
     // runtime specialisation
     {
-        const bool want = !(h->flags & CSMC_FLAG_NO_JIT) && hm.structured &&
+        const bool want = !(h->flags & CSMC_FLAG_NO_JIT) && hm.structured && !hm.self_loop &&
                           ((h->flags & CSMC_FLAG_JIT) || (int64_t)hm.N * h->R >= 32768);
         if ((h->flags & CSMC_FLAG_JIT) && !hm.structured)
             return bail(CSMC_ERR_UNSUPPORTED, "CSMC_FLAG_JIT: the model has no periodic colouring pattern (explicit-table kernels only)");
@@ -371,7 +372,7 @@ int32_t csmc_create(const csmc_model *model, const csmc_opts *opts, csmc_handle 
             std::string err, log;
             std::vector<char> cubin;
             try {
-                const std::string src = jit_generate_source(hm, (h->flags & CSMC_FLAG_PDL) != 0);
+                const std::string src = jit_generate_source(hm, (h->flags & CSMC_FLAG_PDL) != 0, &h->jit_plan);
                 err = jit_compile(src, cubin, log);
             } catch (const std::exception &ex) {
                 err = std::string("code generation failed: ") + ex.what();

@@ -4,6 +4,8 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <cmath>
+#include <stdexcept>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -27,6 +29,10 @@ std::string lit(double v) {
     return buf;
 }
 
+int pow2_floor(int v) { int p = 1; while (2 * p <= v) p *= 2; return p; }
+int pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
+int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
 struct Gen {
     const HostModel &hm;
     std::ostringstream o;
@@ -36,9 +42,9 @@ struct Gen {
             seg_of_class[std::make_tuple(hm.segs[s].basis, hm.segs[s].r[0], hm.segs[s].r[1], hm.segs[s].r[2])] = (int)s;
     }
 
-    // emits code computing `int j<tag>` (storage position of neighbour k of term t) and, for open
-    // boundaries, updates `ok`.  Returns false when the neighbour class does not exist at all.
-    bool neighbour(const HostSeg &hs, const HostTerm &t, int k, const std::string &tag) {
+    // emits code computing `int j` (storage position of neighbour k of term t) and, for open
+    // boundaries, clears `okt`.  Returns false when the neighbour class does not exist at all.
+    bool neighbour(const HostSeg &hs, const HostTerm &t, int k) {
         int r2[MAXD] = {0, 0, 0}, delta[MAXD] = {0, 0, 0};
         for (int d = 0; d < hm.D; ++d) {
             r2[d] = posmod(hs.r[d] + t.off[k][d], hm.P[d]);
@@ -47,7 +53,7 @@ struct Gen {
         auto it = seg_of_class.find(std::make_tuple(t.nb_basis[k], r2[0], r2[1], r2[2]));
         if (it == seg_of_class.end()) return false;
         const HostSeg &ns = hm.segs[it->second];
-        o << "        int j" << tag << ";\n        {\n";
+        o << "          int j" << k << ";\n          {\n";
         for (int d = 0; d < MAXD; ++d) {
             if (d >= hm.D) { o << "            const int n" << d << " = 0;\n"; continue; }
             o << "            int n" << d << " = m" << d << " + (" << delta[d] << ");\n";
@@ -55,55 +61,89 @@ struct Gen {
                 if (delta[d] > 0) o << "            n" << d << " = (n" << d << " >= " << ns.M[d] << ") ? n" << d << " - " << ns.M[d] << " : n" << d << ";\n";
                 if (delta[d] < 0) o << "            n" << d << " = (n" << d << " < 0) ? n" << d << " + " << ns.M[d] << " : n" << d << ";\n";
             } else {
-                if (delta[d] < 0) o << "            ok = ok && (n" << d << " >= 0);\n";
-                if (hs.M[d] - 1 + delta[d] >= ns.M[d]) o << "            ok = ok && (n" << d << " < " << ns.M[d] << ");\n";
+                if (delta[d] < 0) o << "            okt = okt && (n" << d << " >= 0);\n";
+                if (hs.M[d] - 1 + delta[d] >= ns.M[d]) o << "            okt = okt && (n" << d << " < " << ns.M[d] << ");\n";
             }
         }
-        o << "            j" << tag << " = " << ns.start << " + (n0 * " << ns.M[1] << " + n1) * " << ns.M[2] << " + n2;\n        }\n";
+        o << "            j" << k << " = " << ns.start << " + (n0 * " << ns.M[1] << " + n1) * " << ns.M[2] << " + n2;\n          }\n";
         return true;
     }
 
     void segment(int s) {
         const HostSeg &hs = hm.segs[s];
         const int b = hs.basis;
+        // which terms are live (some non-zero coefficient, every neighbour class exists)
+        struct Live { const HostTerm *t; int slot; int bit; };
+        std::vector<Live> live;
+        int nnb = 0;
+        for (const auto &t : hm.basis_terms[b]) {
+            const double *C = hm.coefs.data() + t.coef;
+            const int ncoef = t.kind == 2 ? 9 : t.kind == 3 ? 27 : 81;
+            bool any = false;
+            for (int k = 0; k < ncoef; ++k) any |= (C[k] != 0.0);
+            bool exists = true;
+            for (int k = 0; k < t.kind - 1; ++k) {
+                int r2[MAXD] = {0, 0, 0};
+                for (int d = 0; d < hm.D; ++d) r2[d] = posmod(hs.r[d] + t.off[k][d], hm.P[d]);
+                exists &= seg_of_class.count(std::make_tuple(t.nb_basis[k], r2[0], r2[1], r2[2])) > 0;
+            }
+            if (!any || !exists) continue;
+            live.push_back({&t, nnb, (int)live.size()});
+            nnb += t.kind - 1;
+        }
+        if (live.size() > 32) throw std::runtime_error("more than 32 live interaction slots per site");
+
         o << "struct Seg" << s << " {\n";
-        o << "    static constexpr int START = " << hs.start << ", COUNT = " << hs.count << ";\n";
+        o << "    static constexpr int START = " << hs.start << ", COUNT = " << hs.count << ", NNB = " << nnb << ";\n";
         o << "    static constexpr double H0 = " << lit(hm.field[3 * b]) << ", H1 = " << lit(hm.field[3 * b + 1]) << ", H2 = " << lit(hm.field[3 * b + 2]) << ";\n";
         const bool ons = hm.onsite_coef[b] >= 0;
         o << "    static constexpr bool ONSITE = " << (ons ? "true" : "false") << ";\n";
         for (int k = 0; k < 9; ++k) o << "    static constexpr double O" << k << " = " << lit(hm.onsite[9 * b + k]) << ";\n";
-        // idx -> supercell coordinates
+        o << "    static __device__ __forceinline__ bool valid(int m0, int m1, int m2) { return m0 < " << hs.M[0] << " && m1 < " << hs.M[1] << " && m2 < " << hs.M[2] << "; }\n";
+        o << "    static __device__ __forceinline__ int pos(int m0, int m1, int m2) { return " << hs.start << " + (m0 * " << hs.M[1] << " + m1) * " << hs.M[2] << " + m2; }\n";
+        // linear index -> supercell coordinates (energy kernel)
         o << "    static __device__ __forceinline__ void locate(int idx, int &m0, int &m1, int &m2) {\n";
         o << "        m2 = idx % " << hs.M[2] << "; const int t = idx / " << hs.M[2] << "; m1 = t % " << hs.M[1] << "; m0 = t / " << hs.M[1] << ";\n    }\n";
         // reference site index (Philox counter)
         o << "    static __device__ __forceinline__ unsigned site(int m0, int m1, int m2) {\n";
         o << "        return (unsigned)(((" << b << " * " << hm.L[0] << " + (m0 * " << hs.P[0] << " + " << hs.r[0] << ")) * " << hm.L[1]
           << " + (m1 * " << hs.P[1] << " + " << hs.r[1] << ")) * " << hm.L[2] << " + (m2 * " << hs.P[2] << " + " << hs.r[2] << "));\n    }\n";
-        // unrolled neighbour field: a* bilinear, b* cubic, c* quartic accumulators
-        o << "    static __device__ __forceinline__ void field(const double *__restrict__ sx, const double *__restrict__ sy, const double *__restrict__ sz,\n"
-             "            int m0, int m1, int m2, double &a0, double &a1, double &a2, double &b0, double &b1, double &b2, double &c0, double &c1, double &c2) {\n";
-        int tn = 0;
-        for (const auto &t : hm.basis_terms[b]) {
+        // phase 1: all neighbour loads (read-only for the duration of the pass: other colours) via ld.global.nc
+        o << "    static __device__ __forceinline__ void load(const double *__restrict__ sx, const double *__restrict__ sy, const double *__restrict__ sz,\n"
+             "            int m0, int m1, int m2, double (&nb)[3 * NNB + 1], unsigned &ok) {\n";
+        for (const auto &lv : live) {
+            const HostTerm &t = *lv.t;
+            o << "        { // slot " << lv.bit << " kind " << t.kind << "\n";
+            if (!hm.periodic) o << "          bool okt = true;\n";
+            for (int k = 0; k < t.kind - 1; ++k) neighbour(hs, t, k);
+            if (!hm.periodic) o << "          if (okt) {\n";
+            for (int k = 0; k < t.kind - 1; ++k) {
+                const int base = 3 * (lv.slot + k);
+                o << "          nb[" << base << "] = __ldg(sx + j" << k << "); nb[" << base + 1 << "] = __ldg(sy + j" << k << "); nb[" << base + 2 << "] = __ldg(sz + j" << k << ");\n";
+            }
+            if (!hm.periodic) {
+                o << "          } else {\n            ok &= ~(1u << " << lv.bit << ");\n";
+                for (int k = 0; k < t.kind - 1; ++k) {
+                    const int base = 3 * (lv.slot + k);
+                    o << "            nb[" << base << "] = 0.0; nb[" << base + 1 << "] = 0.0; nb[" << base + 2 << "] = 0.0;\n";
+                }
+                o << "          }\n";
+            }
+            o << "        }\n";
+        }
+        o << "    }\n";
+        // phase 2: unrolled neighbour field from registers: a* bilinear, b* cubic, c* quartic accumulators
+        o << "    static __device__ __forceinline__ void field(const double (&nb)[3 * NNB + 1], unsigned ok,\n"
+             "            double &a0, double &a1, double &a2, double &b0, double &b1, double &b2, double &c0, double &c1, double &c2) {\n";
+        for (const auto &lv : live) {
+            const HostTerm &t = *lv.t;
             const double *C = hm.coefs.data() + t.coef;
-            const int nn = t.kind - 1;
-            const int ncoef = t.kind == 2 ? 9 : t.kind == 3 ? 27 : 81;
-            bool any = false;
-            for (int k = 0; k < ncoef; ++k) any |= (C[k] != 0.0);
-            if (!any) { ++tn; continue; }
-            o << "      { // term " << tn << " kind " << t.kind << "\n";
-            if (!hm.periodic) o << "        bool ok = true;\n";
-            bool exists = true;
-            std::ostringstream saved;
-            saved.swap(o);
-            for (int k = 0; k < nn && exists; ++k) exists = neighbour(hs, t, k, std::to_string(k));
-            std::string body = o.str();
-            o.swap(saved);
-            if (!exists) { o << "      }\n"; ++tn; continue; }
-            o << body;
-            if (!hm.periodic) o << "        if (ok) {\n";
+            o << "      " << (hm.periodic ? "" : "if (ok & (1u << " + std::to_string(lv.bit) + ")) ") << "{ // slot " << lv.bit << "\n";
             const char *nm[3] = {"p", "q", "w"};
-            for (int k = 0; k < nn; ++k)
-                o << "        const double " << nm[k] << "0 = sx[j" << k << "], " << nm[k] << "1 = sy[j" << k << "], " << nm[k] << "2 = sz[j" << k << "];\n";
+            for (int k = 0; k < t.kind - 1; ++k) {
+                const int base = 3 * (lv.slot + k);
+                o << "        const double " << nm[k] << "0 = nb[" << base << "], " << nm[k] << "1 = nb[" << base + 1 << "], " << nm[k] << "2 = nb[" << base + 2 << "];\n";
+            }
             if (t.kind == 2) {
                 for (int a = 0; a < 3; ++a) {
                     std::string e;
@@ -141,39 +181,62 @@ struct Gen {
                         o << "        }\n";
                     }
             }
-            if (!hm.periodic) o << "        }\n";
             o << "      }\n";
-            ++tn;
         }
         o << "    }\n};\n\n";
     }
 
-    std::string run() {
+    std::string run(JitPlan &plan) {
         o << "#define NPAD " << hm.npad << "\n";
         o << "#define SPIN_S " << lit(hm.S) << "\n";
         o << kJitPrelude << "\n";
         for (size_t s = 0; s < hm.segs.size(); ++s) segment((int)s);
+        plan.tiles.assign(hm.n_colours, 1);
+        plan.groups.assign(hm.n_colours, 1);
         for (int c = 0; c < hm.n_colours; ++c) {
             const int s0 = hm.colour_seg_begin[c], s1 = hm.colour_seg_begin[c + 1];
             const int nseg = s1 - s0;
-            int mx = 1;
-            for (int s = s0; s < s1; ++s) mx = std::max(mx, hm.segs[s].count);
-            const int tiles_per_seg = (mx + 255) / 256;
-            // grid = (tiles_per_seg * nseg, 1, replicas).  The segments (classes) of the colour are
-            // interleaved along blockIdx.x, so classes that gather from the same neighbour classes sweep
-            // the same region of the lattice at the same time: the other colours are read from DRAM once
-            // per pass instead of once per class (measured at L=4096: 604 MB -> 402 MB read per pass).
-            (void)tiles_per_seg;
+            // CTA tile over supercell coordinates (multi-dimensional, for L1 reuse of shifted neighbour
+            // runs): 256 threads, the fastest lattice dimension gets up to 32, the rest goes to the slower
+            // dimensions.  Tiling is laid over the largest class extent of the colour; classes guard.
+            int M[MAXD] = {1, 1, 1}, T[MAXD] = {1, 1, 1}, NT[MAXD] = {1, 1, 1};
+            for (int s = s0; s < s1; ++s) for (int d = 0; d < MAXD; ++d) M[d] = std::max(M[d], hm.segs[s].M[d]);
+            int left = 256;
+            const int last = hm.D - 1;
+            T[last] = std::min(std::min(32, pow2_ceil(M[last])), left);
+            if (hm.D == 3) T[last] = std::min(T[last], 16);
+            left /= T[last];
+            for (int d = last - 1; d >= 0; --d) {
+                int want = (d == 0) ? left : std::min(left, std::max(1, (int)pow2_floor((int)std::max(1.0, std::sqrt((double)left)))));
+                T[d] = std::min(want, pow2_ceil(M[d]));
+                if (d == 0) T[d] = left;   // always 256 threads; out-of-range threads idle
+                left /= T[d];
+            }
+            if (hm.D == 1) T[0] = 256;
+            for (int d = 0; d < MAXD; ++d) NT[d] = (M[d] + T[d] - 1) / T[d];
+            plan.tiles[c] = NT[0] * NT[1] * NT[2];
+            // classes of the colour are fused in pairs into one thread (shared neighbour loads, ILP)
+            const int G = std::min(nseg, 2);
+            const int ngroups = (nseg + G - 1) / G;
+            plan.groups[c] = ngroups;
             for (int u = 0; u < 4; ++u) {
-                o << "extern \"C\" __global__ void __launch_bounds__(TPB) csmc_sweep_c" << c << "_u" << u << "(double *__restrict__ spins, const SweepArgs a) {\n";
+                o << "extern \"C\" __global__ void __launch_bounds__(TPB) csmc_sweep_c" << c << "_u" << u << "(double *spins, const SweepArgs a) {\n";
                 o << "#ifdef CSMC_PDL\n    pdl_launch_dependents();\n    pdl_wait();\n#endif\n";
-                o << "    const int rep = blockIdx.z, tile = blockIdx.x;\n";
-                o << "    const int idx = (tile / " << nseg << ") * TPB + threadIdx.x;\n";
-                o << "    switch (tile % " << nseg << ") {\n";
-                for (int s = s0; s < s1; ++s) o << "    case " << (s - s0) << ": sweep_site<" << u << ", Seg" << s << ">(spins, a, idx, rep); break;\n";
+                o << "    const int rep = blockIdx.z;\n    int t = blockIdx.x;\n";
+                o << "    const int t2 = t % " << NT[2] << "; t /= " << NT[2] << "; const int t1 = t % " << NT[1] << "; const int t0 = t / " << NT[1] << ";\n";
+                o << "    const int l2 = threadIdx.x & " << (T[2] - 1) << ", l1 = (threadIdx.x >> " << ilog2(T[2]) << ") & " << (T[1] - 1)
+                  << ", l0 = threadIdx.x >> " << (ilog2(T[2]) + ilog2(T[1])) << ";\n";
+                o << "    const int m0 = t0 * " << T[0] << " + l0, m1 = t1 * " << T[1] << " + l1, m2 = t2 * " << T[2] << " + l2;\n";
+                o << "    switch (blockIdx.y) {\n";
+                for (int g = 0; g < ngroups; ++g) {
+                    o << "    case " << g << ": {\n";
+                    for (int s = s0 + g * G; s < std::min(s1, s0 + (g + 1) * G); ++s) o << "        Site<Seg" << s << "> d" << s << "; site_load(d" << s << ", spins, rep, m0, m1, m2);\n";
+                    for (int s = s0 + g * G; s < std::min(s1, s0 + (g + 1) * G); ++s) o << "        site_finish<" << u << ">(d" << s << ", spins, rep, a);\n";
+                    o << "    } break;\n";
+                }
                 o << "    default: break;\n    }\n}\n";
             }
-            o << "extern \"C\" __global__ void __launch_bounds__(TPB) csmc_energy_c" << c << "(const double *__restrict__ spins, double *__restrict__ partials, int n_partials, int partial_base) {\n";
+            o << "extern \"C\" __global__ void __launch_bounds__(TPB) csmc_energy_c" << c << "(const double *spins, double *__restrict__ partials, int n_partials, int partial_base) {\n";
             o << "    double v[4] = {0.0, 0.0, 0.0, 0.0};\n    switch (blockIdx.y) {\n";
             for (int s = s0; s < s1; ++s) o << "    case " << (s - s0) << ": energy_site<Seg" << s << ">(spins, v); break;\n";
             o << "    default: break;\n    }\n    energy_block_reduce(v, partials, n_partials, partial_base);\n}\n";
@@ -221,9 +284,10 @@ bool load_nvrtc() {
 
 }  // namespace
 
-std::string jit_generate_source(const HostModel &hm, bool pdl) {
+std::string jit_generate_source(const HostModel &hm, bool pdl, JitPlan *plan) {
     Gen g(hm);
-    std::string src = g.run();
+    JitPlan local;
+    std::string src = g.run(plan ? *plan : local);
     return pdl ? "#define CSMC_PDL 1\n" + src : src;
 }
 

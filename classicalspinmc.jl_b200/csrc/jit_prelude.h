@@ -63,17 +63,56 @@ __device__ __forceinline__ double warp_sum(double v) {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-// one site of one colour pass; SEG supplies the constant geometry, Zeeman / on-site constants and
-// the unrolled neighbour-field accumulation
+// Per-site working set.  A pass first *loads* everything a thread needs (own spin and all neighbour
+// spins, for every class the thread handles), then computes, then stores: with all loads issued up
+// front the Metropolis RNG / proposal arithmetic overlaps the memory latency, and the sites of
+// different classes handled by one thread are independent instruction streams (ILP).
+template <class SEG>
+struct Site {
+    bool valid;
+    int pos, m0, m1, m2;
+    unsigned ok;                      // open boundaries: bit t set <=> term t has all its neighbours
+    double s0, s1, s2;
+    double nb[3 * SEG::NNB + 1];      // neighbour spins, compile-time indexed (registers)
+};
+
+template <class SEG>
+__device__ __forceinline__ void site_load(Site<SEG> &d, const double *spins, int rep, int m0, int m1, int m2) {
+    const double *sx = spins + (size_t)rep * (3ull * NPAD), *sy = sx + NPAD, *sz = sy + NPAD;
+    d.valid = SEG::valid(m0, m1, m2);
+    d.m0 = m0; d.m1 = m1; d.m2 = m2;
+    d.ok = 0xffffffffu;
+    if (d.valid) {
+        d.pos = SEG::pos(m0, m1, m2);
+        d.s0 = sx[d.pos]; d.s1 = sy[d.pos]; d.s2 = sz[d.pos];
+        SEG::load(sx, sy, sz, m0, m1, m2, d.nb, d.ok);
+    }
+}
+
 template <int UPD, class SEG>
-__device__ __forceinline__ void sweep_site(double *__restrict__ spins, const SweepArgs &a, const int idx, const int rep) {
+__device__ __forceinline__ void site_finish(Site<SEG> &d, double *spins, int rep, const SweepArgs &a) {
     double *sx = spins + (size_t)rep * (3ull * NPAD), *sy = sx + NPAD, *sz = sy + NPAD;
     bool accepted = false;
-    if (idx < SEG::COUNT) {
-        int m0, m1, m2;
-        SEG::locate(idx, m0, m1, m2);
-        const int pos = SEG::START + idx;
-        const double s0 = sx[pos], s1 = sy[pos], s2 = sz[pos];
+    if (d.valid) {
+        const int pos = d.pos;
+        const double s0 = d.s0, s1 = d.s1, s2 = d.s2;
+        double n0 = 0.0, n1 = 0.0, n2 = 0.0;
+        u4 q; q.x = q.y = q.z = q.w = 0u;
+        if (UPD == UPD_METRO || UPD == UPD_CONE) {
+            // both Philox calls and the proposal are independent of the loads issued in site_load
+            const unsigned long long ctr = (a.ctr_base ? *a.ctr_base : 0ULL) + a.ctr_off;
+            const uint32_t site = SEG::site(d.m0, d.m1, d.m2);
+            const uint32_t grep = (uint32_t)(a.replica_base + rep);
+            const u4 r = philox_stream(a.seed, site, grep, ctr, TAG_PROPOSE);
+            q = philox_stream(a.seed, site, grep, ctr, TAG_ACCEPT);
+            random_orientation(SPIN_S, u53(r.x, r.y), u53(r.z, r.w), n0, n1, n2);
+            if (UPD == UPD_CONE) {
+                const double sg = a.sigma[rep];
+                n0 = s0 + sg * n0; n1 = s1 + sg * n1; n2 = s2 + sg * n2;
+                const double nrm = sqrt(n0 * n0 + n1 * n1 + n2 * n2);
+                n0 = n0 / nrm * SPIN_S; n1 = n1 / nrm * SPIN_S; n2 = n2 / nrm * SPIN_S;
+            }
+        }
         double g0 = 0.0, g1 = 0.0, g2 = 0.0;
         if (UPD == UPD_OR || UPD == UPD_DET) {
             if (SEG::ONSITE) {
@@ -82,7 +121,7 @@ __device__ __forceinline__ void sweep_site(double *__restrict__ spins, const Swe
                 g2 = 2 * (SEG::O6 * s0 + SEG::O7 * s1 + SEG::O8 * s2);
             }
         }
-        SEG::field(sx, sy, sz, m0, m1, m2, g0, g1, g2, g0, g1, g2, g0, g1, g2);
+        SEG::field(d.nb, d.ok, g0, g1, g2, g0, g1, g2, g0, g1, g2);
         const double F0 = g0 - SEG::H0, F1 = g1 - SEG::H1, F2 = g2 - SEG::H2;
         if (UPD == UPD_OR) {
             if (!(F0 == 0.0 && F1 == 0.0 && F2 == 0.0)) {
@@ -95,18 +134,6 @@ __device__ __forceinline__ void sweep_site(double *__restrict__ spins, const Swe
                 sx[pos] = -F0 / nrm * SPIN_S; sy[pos] = -F1 / nrm * SPIN_S; sz[pos] = -F2 / nrm * SPIN_S;
             }
         } else {
-            const unsigned long long ctr = (a.ctr_base ? *a.ctr_base : 0ULL) + a.ctr_off;
-            const uint32_t site = SEG::site(m0, m1, m2);
-            const uint32_t grep = (uint32_t)(a.replica_base + rep);
-            const u4 r = philox_stream(a.seed, site, grep, ctr, TAG_PROPOSE);
-            double n0, n1, n2;
-            random_orientation(SPIN_S, u53(r.x, r.y), u53(r.z, r.w), n0, n1, n2);
-            if (UPD == UPD_CONE) {
-                const double sg = a.sigma[rep];
-                n0 = s0 + sg * n0; n1 = s1 + sg * n1; n2 = s2 + sg * n2;
-                const double nrm = sqrt(n0 * n0 + n1 * n1 + n2 * n2);
-                n0 = n0 / nrm * SPIN_S; n1 = n1 / nrm * SPIN_S; n2 = n2 / nrm * SPIN_S;
-            }
             double dE = (n0 - s0) * F0 + (n1 - s1) * F1 + (n2 - s2) * F2;
             if (SEG::ONSITE) {
                 const double en = n0 * (SEG::O0 * n0 + SEG::O1 * n1 + SEG::O2 * n2) + n1 * (SEG::O3 * n0 + SEG::O4 * n1 + SEG::O5 * n2) +
@@ -116,10 +143,7 @@ __device__ __forceinline__ void sweep_site(double *__restrict__ spins, const Swe
                 dE += en - eo;
             }
             accepted = dE < 0.0;
-            if (!accepted) {
-                const u4 q = philox_stream(a.seed, site, grep, ctr, TAG_ACCEPT);
-                accepted = u53(q.x, q.y) < exp(-dE / a.T[rep]);
-            }
+            if (!accepted) accepted = u53(q.x, q.y) < exp(-dE / a.T[rep]);
             if (accepted) { sx[pos] = n0; sy[pos] = n1; sz[pos] = n2; }
         }
     }
@@ -130,17 +154,17 @@ __device__ __forceinline__ void sweep_site(double *__restrict__ spins, const Swe
 }
 
 template <class SEG>
-__device__ __forceinline__ void energy_site(const double *__restrict__ spins, double (&v)[4]) {
+__device__ __forceinline__ void energy_site(const double *spins, double (&v)[4]) {
     const int idx = blockIdx.x * TPB + threadIdx.x;
     const int rep = blockIdx.z;
-    const double *sx = spins + (size_t)rep * (3ull * NPAD), *sy = sx + NPAD, *sz = sy + NPAD;
     if (idx < SEG::COUNT) {
         int m0, m1, m2;
         SEG::locate(idx, m0, m1, m2);
-        const int pos = SEG::START + idx;
-        const double s0 = sx[pos], s1 = sy[pos], s2 = sz[pos];
+        Site<SEG> d;
+        site_load(d, spins, rep, m0, m1, m2);
+        const double s0 = d.s0, s1 = d.s1, s2 = d.s2;
         double a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0, c0 = 0, c1 = 0, c2 = 0;
-        SEG::field(sx, sy, sz, m0, m1, m2, a0, a1, a2, b0, b1, b2, c0, c1, c2);
+        SEG::field(d.nb, d.ok, a0, a1, a2, b0, b1, b2, c0, c1, c2);
         double e = (s0 * a0 + s1 * a1 + s2 * a2) / 2 + (s0 * b0 + s1 * b1 + s2 * b2) / 3 +
                    (s0 * c0 + s1 * c1 + s2 * c2) / 4 - (s0 * SEG::H0 + s1 * SEG::H1 + s2 * SEG::H2);
         if (SEG::ONSITE)

@@ -235,11 +235,17 @@ function parallel_tempering!(mc::MonteCarlo, saveIC::Vector{Int64}=Int64[]; alg:
     for r in 1:R, k in 1:size(E, 2)
         update_observables!(mc.observables_all[r], E[base+r, k], M[base+r, k])
     end
-    download!(mc)          # configurations stay with their replicas; slots = pt_slots(e, n_slots)
+    download!(mc)          # configurations stay with their replicas; replica r sits in slot slots[base+r]
     if out
         slots = pt_slots(e, n_slots)
         for r in 1:R
-            write_final_observables(slotfile(slots[base+r]), mc.replica_spins[r], mc.observables_all[findfirst(==(slots[base+r]), base:base+R-1) === nothing ? r : slots[base+r]-base+1], T_all[slots[base+r]+1], mc.lattice.size)
+            # spins: written by the process that holds the slot's replica
+            write_spins(slotfile(slots[base+r]), mc.replica_spins[r])
+        end
+        barrier()
+        for r in 1:R
+            # observables: accumulated per temperature slot; slot base+r-1 was measured on this process
+            write_observables(slotfile(base + r - 1), mc.observables_all[r], T_all[base+r], mc.lattice.size)
         end
     end
     rank == 0 && @printf("Simulation finished on %s.\n", Dates.format(Dates.now(), "dd u yyyy HH:MM:SS"))

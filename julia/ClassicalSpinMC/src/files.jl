@@ -61,11 +61,10 @@ function write_initial_configuration(filename::String, T, configfile::String, sp
     end
 end
 
-function write_final_observables(path::String, spins, obs::Observables, T, N)
+function write_observables(path::String, obs::Observables, T, N)
     heat, dheat = specific_heat(obs, T, N)
     chi, dchi = susceptibility(obs, T, N)
     h5open(path, "r+") do f
-        f["spins"][:, :] = spins
         haskey(f, "observables") && delete_object(f, "observables")
         g = create_group(f, "observables")
         g["specific_heat"] = heat;  g["specific_heat_err"] = abs(dheat / heat)
