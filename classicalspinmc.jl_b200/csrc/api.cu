@@ -69,7 +69,7 @@ struct csmc_handle {
 
     double *d_spins = nullptr, *d_stage = nullptr, *d_out = nullptr;
     int32_t *d_nbr = nullptr, *d_ref_of_pos = nullptr;
-    double *d_T = nullptr, *d_sigma = nullptr;
+    double *d_beta = nullptr, *d_sigma = nullptr;
     unsigned long long *d_acc = nullptr, *d_acc_prev = nullptr, *d_ctr = nullptr;
     double *d_partials = nullptr;
     int n_partials = 0;
@@ -156,7 +156,7 @@ void launch_sweep_pass(csmc_handle *h, int colour, const SweepArgs &a) {
 
 SweepArgs sweep_args(csmc_handle *h, unsigned long long ctr_off, bool device_ctr) {
     SweepArgs a{};
-    a.T = h->d_T; a.sigma = h->d_sigma; a.accepted = h->d_acc;
+    a.beta = h->d_beta; a.sigma = h->d_sigma; a.accepted = h->d_acc;
     a.ctr_base = device_ctr ? h->d_ctr : nullptr;
     a.ctr_off = ctr_off; a.seed = h->seed; a.replica_base = h->replica_base;
     return a;
@@ -227,8 +227,10 @@ int check_metropolis(csmc_handle *h) {
 int upload_T(csmc_handle *h, const double *T) {
     for (int r = 0; r < h->R; ++r)
         if (!(T[r] > 0.0)) return fail(h, CSMC_ERR_INVALID, "temperatures must be > 0");
-    CK(cudaMemcpyAsync(h->d_T, T, sizeof(double) * h->R, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));  // T is caller memory: do not retain the pointer
+    std::vector<double> beta(h->R);
+    for (int r = 0; r < h->R; ++r) beta[r] = 1.0 / T[r];
+    CK(cudaMemcpyAsync(h->d_beta, beta.data(), sizeof(double) * h->R, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));  // host buffers are not retained
     return CSMC_OK;
 }
 
@@ -237,7 +239,7 @@ PtState pt_state(csmc_handle *h) {
     st.n_slots = h->n_slots; st.n_local = h->R; st.replica_base = h->replica_base;
     st.T_slot = h->d_T_slot; st.slot_of_rep = h->d_slot_of_rep; st.rep_of_slot = h->d_rep_of_slot;
     st.meas_all = h->d_meas_all; st.E_last = h->d_E_last; st.acc_prev = h->d_acc_prev_pt;
-    st.acc_slot = h->d_acc_slot; st.exch_slot = h->d_exch_slot; st.T_local = h->d_T;
+    st.acc_slot = h->d_acc_slot; st.exch_slot = h->d_exch_slot; st.beta_local = h->d_beta;
     st.accepted_pairs = h->d_accepted_pairs;
     return st;
 }
@@ -325,14 +327,14 @@ int32_t csmc_create(const csmc_model *model, const csmc_opts *opts, csmc_handle 
     CKC(cudaMemcpyAsync(h->d_nbr, hm.nbr.data(), sizeof(int32_t) * hm.nbr.size(), cudaMemcpyHostToDevice, h->stream));
     CKC(dalloc(&h->d_ref_of_pos, npad));
     CKC(cudaMemcpyAsync(h->d_ref_of_pos, hm.ref_of_pos.data(), sizeof(int32_t) * npad, cudaMemcpyHostToDevice, h->stream));
-    CKC(dalloc(&h->d_T, h->R)); CKC(dalloc(&h->d_sigma, h->R));
+    CKC(dalloc(&h->d_beta, h->R)); CKC(dalloc(&h->d_sigma, h->R));
     CKC(dalloc(&h->d_acc, h->R)); CKC(dalloc(&h->d_acc_prev, h->R)); CKC(dalloc(&h->d_ctr, 1));
     CKC(cudaMemsetAsync(h->d_acc, 0, sizeof(unsigned long long) * h->R, h->stream));
     CKC(cudaMemsetAsync(h->d_acc_prev, 0, sizeof(unsigned long long) * h->R, h->stream));
     CKC(cudaMemsetAsync(h->d_ctr, 0, sizeof(unsigned long long), h->stream));
     {
         std::vector<double> ones(h->R, 1.0), sig(h->R, 60.0);
-        CKC(cudaMemcpyAsync(h->d_T, ones.data(), sizeof(double) * h->R, cudaMemcpyHostToDevice, h->stream));
+        CKC(cudaMemcpyAsync(h->d_beta, ones.data(), sizeof(double) * h->R, cudaMemcpyHostToDevice, h->stream));
         CKC(cudaMemcpyAsync(h->d_sigma, sig.data(), sizeof(double) * h->R, cudaMemcpyHostToDevice, h->stream));
         CKC(cudaStreamSynchronize(h->stream));
     }
@@ -449,7 +451,7 @@ int32_t csmc_destroy(csmc_handle *h) {
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     free_pt(h);
     cudaFree(h->d_spins); cudaFree(h->d_stage); cudaFree(h->d_out); cudaFree(h->d_nbr); cudaFree(h->d_ref_of_pos);
-    cudaFree(h->d_T); cudaFree(h->d_sigma); cudaFree(h->d_acc); cudaFree(h->d_acc_prev); cudaFree(h->d_ctr);
+    cudaFree(h->d_beta); cudaFree(h->d_sigma); cudaFree(h->d_acc); cudaFree(h->d_acc_prev); cudaFree(h->d_ctr);
     cudaFree(h->d_partials);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -761,8 +763,12 @@ int32_t csmc_pt_init(csmc_handle *h, int32_t n_slots, const double *T_all) {
     CK(cudaMemsetAsync(h->d_acc_slot, 0, sizeof(double) * n_slots, h->stream));
     CK(cudaMemsetAsync(h->d_exch_slot, 0, sizeof(double) * n_slots, h->stream));
     CK(cudaMemsetAsync(h->d_accepted_pairs, 0, sizeof(int) * n_slots, h->stream));
-    CK(cudaMemcpyAsync(h->d_T, T_all + h->replica_base, sizeof(double) * h->R, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    {
+        std::vector<double> beta(h->R);
+        for (int r = 0; r < h->R; ++r) beta[r] = 1.0 / T_all[h->replica_base + r];
+        CK(cudaMemcpyAsync(h->d_beta, beta.data(), sizeof(double) * h->R, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
     // E = total_energy(mc.lattice) before the loop (src/monte_carlo.jl:265); acc_prev = current counters
     int rc = enqueue_measure_all(h, true); if (rc) return rc;
     PtState st = pt_state(h);

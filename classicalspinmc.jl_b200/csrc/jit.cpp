@@ -7,6 +7,8 @@
 #include <cmath>
 #include <stdexcept>
 #include <cstdio>
+#include <cstdlib>
+#include <functional>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -296,7 +298,17 @@ std::string jit_compile(const std::string &src, std::vector<char> &cubin, std::s
     std::lock_guard<std::mutex> lk(g_rtc_mu);
     if (!load_nvrtc()) return g_rtc.err;
     nvrtcProgram prog = nullptr;
-    int rc = g_rtc.CreateProgram(&prog, src.c_str(), "csmc_jit.cu", 0, nullptr, nullptr);
+    // CSMC_JIT_DUMP=<dir>: keep the generated source on disk under the name the cubin's line table
+    // refers to, so `ncu --import-source on` / cuobjdump can map SASS back to it
+    std::string name = "csmc_jit.cu";
+    if (const char *dir = std::getenv("CSMC_JIT_DUMP")) {
+        size_t hsh = std::hash<std::string>{}(src);
+        char buf[64];
+        std::snprintf(buf, sizeof buf, "/csmc_jit_%016zx.cu", hsh);
+        name = std::string(dir) + buf;
+        if (FILE *f = std::fopen(name.c_str(), "w")) { std::fwrite(src.data(), 1, src.size(), f); std::fclose(f); }
+    }
+    int rc = g_rtc.CreateProgram(&prog, src.c_str(), name.c_str(), 0, nullptr, nullptr);
     if (rc != 0) return "nvrtcCreateProgram failed";
     const char *opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--fmad=true"};
     rc = g_rtc.CompileProgram(prog, 4, opts);

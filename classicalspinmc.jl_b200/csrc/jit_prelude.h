@@ -17,7 +17,7 @@ enum { TAG_PROPOSE = 0, TAG_ACCEPT = 1, TAG_INIT = 2, TAG_EXCHANGE = 3 };
 #define TPB 256
 
 struct SweepArgs {
-    const double *T;
+    const double *beta;
     const double *sigma;
     unsigned long long *accepted;
     const unsigned long long *ctr_base;
@@ -44,6 +44,11 @@ __device__ __forceinline__ u4 philox_stream(unsigned long long seed, uint32_t c0
 }
 __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
     return (double)((((unsigned long long)hi << 32) | lo) >> 11) * 0x1.0p-53;
+}
+__device__ __forceinline__ void philox_to_3_uniforms(const u4 &r, double &u1, double &u2, double &u3) {
+    u1 = (double)(((unsigned long long)r.x << 11) | (r.y >> 21)) * 0x1.0p-43;
+    u2 = (double)(((unsigned long long)(r.y & 0x1FFFFFu) << 22) | (r.z >> 10)) * 0x1.0p-43;
+    u3 = (double)(((unsigned long long)(r.z & 0x3FFu) << 32) | r.w) * 0x1.0p-42;
 }
 __device__ __forceinline__ void random_orientation(double S, double u1, double u2, double &x, double &y, double &z) {
     double sn, cs;
@@ -96,16 +101,16 @@ __device__ __forceinline__ void site_finish(Site<SEG> &d, double *spins, int rep
     if (d.valid) {
         const int pos = d.pos;
         const double s0 = d.s0, s1 = d.s1, s2 = d.s2;
-        double n0 = 0.0, n1 = 0.0, n2 = 0.0;
-        u4 q; q.x = q.y = q.z = q.w = 0u;
+        double n0 = 0.0, n1 = 0.0, n2 = 0.0, u3 = 0.0;
         if (UPD == UPD_METRO || UPD == UPD_CONE) {
-            // both Philox calls and the proposal are independent of the loads issued in site_load
+            // the Philox call and the proposal are independent of the loads issued in site_load
             const unsigned long long ctr = (a.ctr_base ? *a.ctr_base : 0ULL) + a.ctr_off;
             const uint32_t site = SEG::site(d.m0, d.m1, d.m2);
             const uint32_t grep = (uint32_t)(a.replica_base + rep);
             const u4 r = philox_stream(a.seed, site, grep, ctr, TAG_PROPOSE);
-            q = philox_stream(a.seed, site, grep, ctr, TAG_ACCEPT);
-            random_orientation(SPIN_S, u53(r.x, r.y), u53(r.z, r.w), n0, n1, n2);
+            double u1, u2;
+            philox_to_3_uniforms(r, u1, u2, u3);
+            random_orientation(SPIN_S, u1, u2, n0, n1, n2);
             if (UPD == UPD_CONE) {
                 const double sg = a.sigma[rep];
                 n0 = s0 + sg * n0; n1 = s1 + sg * n1; n2 = s2 + sg * n2;
@@ -142,8 +147,7 @@ __device__ __forceinline__ void site_finish(Site<SEG> &d, double *spins, int rep
                                   s2 * (SEG::O6 * s0 + SEG::O7 * s1 + SEG::O8 * s2);
                 dE += en - eo;
             }
-            accepted = dE < 0.0;
-            if (!accepted) accepted = u53(q.x, q.y) < exp(-dE / a.T[rep]);
+            accepted = dE < 0.0 || u3 < exp(-dE * a.beta[rep]);
             if (accepted) { sx[pos] = n0; sy[pos] = n1; sz[pos] = n2; }
         }
     }

@@ -19,7 +19,7 @@ enum { UPD_OR = 0, UPD_DET = 1, UPD_METRO = 2, UPD_CONE = 3 };
 enum { TAG_PROPOSE = 0, TAG_ACCEPT = 1, TAG_INIT = 2, TAG_EXCHANGE = 3 };
 
 struct SweepArgs {
-    const double *T;                     // [R] per-replica temperature          (Metropolis)
+    const double *beta;                  // [R] per-replica inverse temperature   (Metropolis)
     const double *sigma;                 // [R] per-replica cone width            (cone moves)
     unsigned long long *accepted;        // [R] accepted-proposal counters        (Metropolis)
     const unsigned long long *ctr_base;  // optional device-resident sweep counter (graph replay)
@@ -46,6 +46,13 @@ __device__ __forceinline__ u4 philox_stream(unsigned long long seed, uint32_t c0
 }
 __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
     return (double)((((unsigned long long)hi << 32) | lo) >> 11) * 0x1.0p-53;
+}
+// One Philox call per Metropolis proposal: its 128 bits are split into three uniforms in [0,1):
+// u1 (43 bits: azimuth), u2 (43 bits: z), u3 (42 bits: acceptance).
+__device__ __forceinline__ void philox_to_3_uniforms(const u4 &r, double &u1, double &u2, double &u3) {
+    u1 = (double)(((unsigned long long)r.x << 11) | (r.y >> 21)) * 0x1.0p-43;
+    u2 = (double)(((unsigned long long)(r.y & 0x1FFFFFu) << 22) | (r.z >> 10)) * 0x1.0p-43;
+    u3 = (double)(((unsigned long long)(r.z & 0x3FFu) << 32) | r.w) * 0x1.0p-42;
 }
 
 // random_spin_orientation (src/lattice.jl:306-311): phi = 2 pi u1, z = 2 u2 - 1
@@ -207,8 +214,9 @@ __global__ void __launch_bounds__(TPB) k_sweep(const __grid_constant__ P p, cons
             const uint32_t site = ref_index<P, STRUCT>(p, seg, pos, m);
             const uint32_t grep = (uint32_t)(a.replica_base + rep);
             const u4 r = philox_stream(a.seed, site, grep, ctr, TAG_PROPOSE);
-            double n0, n1, n2;
-            random_orientation(p.S, u53(r.x, r.y), u53(r.z, r.w), n0, n1, n2);
+            double n0, n1, n2, u1, u2, u3;
+            philox_to_3_uniforms(r, u1, u2, u3);
+            random_orientation(p.S, u1, u2, n0, n1, n2);
             if (UPD == UPD_CONE) {
                 // gaussian_move, src/metropolis.jl:84-87
                 const double sg = a.sigma[rep];
@@ -225,11 +233,7 @@ __global__ void __launch_bounds__(TPB) k_sweep(const __grid_constant__ P p, cons
                                   s2 * (O[6] * s0 + O[7] * s1 + O[8] * s2);
                 dE += en - eo;
             }
-            accepted = dE < 0.0;
-            if (!accepted) {
-                const u4 q = philox_stream(a.seed, site, grep, ctr, TAG_ACCEPT);
-                accepted = u53(q.x, q.y) < exp(-dE / a.T[rep]);  // src/metropolis.jl:73
-            }
+            accepted = dE < 0.0 || u3 < exp(-dE * a.beta[rep]);  // src/metropolis.jl:73
             if (accepted) { sx[pos] = n0; sy[pos] = n1; sz[pos] = n2; }
         }
     }
@@ -399,7 +403,7 @@ struct PtState {
     double *E_last;                // [n_slots] energy after the replica's last Metropolis sweep
     double *acc_prev;              // [n_slots] accepted counter at the last flush
     double *acc_slot, *exch_slot;  // [n_slots] statistics attributed to temperature slots
-    double *T_local;               // [n_local] temperatures of the local replicas (kernel input)
+    double *beta_local;            // [n_local] inverse temperatures of the local replicas (kernel input)
     int *accepted_pairs;           // [n_slots] decisions of the last exchange step
 };
 
@@ -436,7 +440,7 @@ __global__ void k_pt_exchange(PtState st, int first, unsigned long long exch_ctr
         }
     }
     __syncthreads();
-    for (int r = threadIdx.x; r < st.n_local; r += blockDim.x) st.T_local[r] = st.T_slot[st.slot_of_rep[st.replica_base + r]];
+    for (int r = threadIdx.x; r < st.n_local; r += blockDim.x) st.beta_local[r] = 1.0 / st.T_slot[st.slot_of_rep[st.replica_base + r]];
 }
 
 // probe, src/monte_carlo.jl:368-370: (E, |M|) of every slot appended to the series

@@ -554,16 +554,15 @@ double orc_metropolis_philox(const orc_lattice *L, double *spins, const int64_t 
         double old[3] = {s[0], s[1], s[2]}, prop[3];
         uint32_t r[4];
         orc_philox_raw(seed, (uint32_t)(point - 1), replica, sweep_ctr, TAG_PROPOSE, r);
-        double u1 = u53(r[0], r[1]), u2 = u53(r[2], r[3]);
+        /* one Philox call per proposal, 128 bits -> u1 (43 bits), u2 (43 bits), u3 (42 bits) */
+        double u1 = (double)(((uint64_t)r[0] << 11) | (r[1] >> 21)) * 0x1.0p-43;
+        double u2 = (double)(((uint64_t)(r[1] & 0x1FFFFFu) << 22) | (r[2] >> 10)) * 0x1.0p-43;
+        double u3 = (double)(((uint64_t)(r[2] & 0x3FFu) << 32) | r[3]) * 0x1.0p-42;
         double E_old = orc_site_energy(L, spins, point);
         if (sigma < 0) rso(L->S, u1, u2, prop); else cone_move(L->S, old, sigma, u1, u2, prop);
         s[0] = prop[0]; s[1] = prop[1]; s[2] = prop[2];
         double dE = orc_site_energy(L, spins, point) - E_old;
-        int accept = 1;
-        if (!(dE < 0)) {
-            orc_philox_raw(seed, (uint32_t)(point - 1), replica, sweep_ctr, TAG_ACCEPT, r);
-            accept = u53(r[0], r[1]) < exp(-dE / T);
-        }
+        int accept = dE < 0 ? 1 : (u3 < exp(-dE / T));
         if (!accept) { s[0] = old[0]; s[1] = old[1]; s[2] = old[2]; } else accepted += 1;
     }
     return accepted;
