@@ -328,8 +328,8 @@ int32_t csmc_create(const csmc_model *model, const csmc_opts *opts, csmc_handle 
     CKC(dalloc(&h->d_ref_of_pos, npad));
     CKC(cudaMemcpyAsync(h->d_ref_of_pos, hm.ref_of_pos.data(), sizeof(int32_t) * npad, cudaMemcpyHostToDevice, h->stream));
     CKC(dalloc(&h->d_beta, h->R)); CKC(dalloc(&h->d_sigma, h->R));
-    CKC(dalloc(&h->d_acc, h->R)); CKC(dalloc(&h->d_acc_prev, h->R)); CKC(dalloc(&h->d_ctr, 1));
-    CKC(cudaMemsetAsync(h->d_acc, 0, sizeof(unsigned long long) * h->R, h->stream));
+    CKC(dalloc(&h->d_acc, (size_t)h->R * ACC_STRIPE)); CKC(dalloc(&h->d_acc_prev, h->R)); CKC(dalloc(&h->d_ctr, 1));
+    CKC(cudaMemsetAsync(h->d_acc, 0, sizeof(unsigned long long) * h->R * ACC_STRIPE, h->stream));
     CKC(cudaMemsetAsync(h->d_acc_prev, 0, sizeof(unsigned long long) * h->R, h->stream));
     CKC(cudaMemsetAsync(h->d_ctr, 0, sizeof(unsigned long long), h->stream));
     {
@@ -622,9 +622,10 @@ int32_t csmc_set_temperatures(csmc_handle *h, const double *T) {
 int32_t csmc_get_accepted(csmc_handle *h, double *accepted, int32_t reset) {
     NEED(h); NEEDARG(h, accepted);
     CK(cudaSetDevice(h->device));
-    std::vector<unsigned long long> now(h->R);
-    CK(cudaMemcpyAsync(now.data(), h->d_acc, sizeof(unsigned long long) * h->R, cudaMemcpyDeviceToHost, h->stream));
+    std::vector<unsigned long long> stripes((size_t)h->R * ACC_STRIPE), now(h->R, 0ULL);
+    CK(cudaMemcpyAsync(stripes.data(), h->d_acc, sizeof(unsigned long long) * stripes.size(), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    for (int r = 0; r < h->R; ++r) for (int k = 0; k < ACC_STRIPE; ++k) now[r] += stripes[(size_t)r * ACC_STRIPE + k];
     for (int r = 0; r < h->R; ++r) { accepted[r] = (double)(now[r] - h->acc_base[r]); if (reset) h->acc_base[r] = now[r]; }
     return CSMC_OK;
 }
@@ -651,9 +652,15 @@ int32_t csmc_metropolis_cone(csmc_handle *h, const double *T, double *sigma, int
     CK(cudaSetDevice(h->device));
     rc = upload_T(h, T); if (rc) return rc;
     CK(cudaMemcpyAsync(h->d_sigma, sigma, sizeof(double) * h->R, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d_acc_prev, h->d_acc, sizeof(unsigned long long) * h->R, cudaMemcpyDeviceToDevice, h->stream));
     std::vector<double> before(h->R), after(h->R);
-    if (accepted) { rc = csmc_get_accepted(h, before.data(), 0); if (rc) return rc; }
+    rc = csmc_get_accepted(h, before.data(), 0); if (rc) return rc;
+    {
+        // running totals as of now, for the per-sweep acceptance of the adaptive rule
+        std::vector<unsigned long long> prev(h->R);
+        for (int r = 0; r < h->R; ++r) prev[r] = (unsigned long long)before[r] + h->acc_base[r];
+        CK(cudaMemcpyAsync(h->d_acc_prev, prev.data(), sizeof(unsigned long long) * h->R, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
     for (int s = 0; s < n_sweeps; ++s) {
         enqueue_metropolis(h, true);
         if (adapt) { k_adapt_sigma<<<(h->R + 127) / 128, 128, 0, h->stream>>>(h->d_sigma, h->d_acc, h->d_acc_prev, (double)h->hm.N, h->R); h->launches++; }

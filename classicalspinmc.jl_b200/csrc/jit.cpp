@@ -233,7 +233,9 @@ struct Gen {
                 for (int g = 0; g < ngroups; ++g) {
                     o << "    case " << g << ": {\n";
                     for (int s = s0 + g * G; s < std::min(s1, s0 + (g + 1) * G); ++s) o << "        Site<Seg" << s << "> d" << s << "; site_load(d" << s << ", spins, rep, m0, m1, m2);\n";
-                    for (int s = s0 + g * G; s < std::min(s1, s0 + (g + 1) * G); ++s) o << "        site_finish<" << u << ">(d" << s << ", spins, rep, a);\n";
+                    o << "        int n_acc = 0;\n";
+                    for (int s = s0 + g * G; s < std::min(s1, s0 + (g + 1) * G); ++s) o << "        n_acc += site_finish<" << u << ">(d" << s << ", spins, rep, a) ? 1 : 0;\n";
+                    if (u >= 2) o << "        count_accepted(n_acc, rep, a);\n";
                     o << "    } break;\n";
                 }
                 o << "    default: break;\n    }\n}\n";

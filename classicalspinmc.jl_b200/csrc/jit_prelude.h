@@ -15,6 +15,7 @@ typedef unsigned long long uint64_t;
 enum { UPD_OR = 0, UPD_DET = 1, UPD_METRO = 2, UPD_CONE = 3 };
 enum { TAG_PROPOSE = 0, TAG_ACCEPT = 1, TAG_INIT = 2, TAG_EXCHANGE = 3 };
 #define TPB 256
+#define ACC_STRIPE 32
 
 struct SweepArgs {
     const double *beta;
@@ -95,7 +96,7 @@ __device__ __forceinline__ void site_load(Site<SEG> &d, const double *spins, int
 }
 
 template <int UPD, class SEG>
-__device__ __forceinline__ void site_finish(Site<SEG> &d, double *spins, int rep, const SweepArgs &a) {
+__device__ __forceinline__ bool site_finish(Site<SEG> &d, double *spins, int rep, const SweepArgs &a) {
     double *sx = spins + (size_t)rep * (3ull * NPAD), *sy = sx + NPAD, *sz = sy + NPAD;
     bool accepted = false;
     if (d.valid) {
@@ -151,10 +152,19 @@ __device__ __forceinline__ void site_finish(Site<SEG> &d, double *spins, int rep
             if (accepted) { sx[pos] = n0; sy[pos] = n1; sz[pos] = n2; }
         }
     }
-    if (UPD == UPD_METRO || UPD == UPD_CONE) {
-        const unsigned ballot = __ballot_sync(0xffffffffu, accepted);
-        if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(a.accepted + rep, (unsigned long long)__popc(ballot));
-    }
+    return accepted;
+}
+
+// one atomic per CTA, striped over ACC_STRIPE addresses per replica (same-address L2 atomics serialise)
+__device__ __forceinline__ void count_accepted(int n_mine, int rep, const SweepArgs &a) {
+    __shared__ int sh_acc;
+    if (threadIdx.x == 0) sh_acc = 0;
+    __syncthreads();
+    const int w = __reduce_add_sync(0xffffffffu, n_mine);
+    if ((threadIdx.x & 31) == 0 && w) atomicAdd(&sh_acc, w);
+    __syncthreads();
+    if (threadIdx.x == 0 && sh_acc)
+        atomicAdd(a.accepted + (size_t)rep * ACC_STRIPE + (blockIdx.x & (ACC_STRIPE - 1)), (unsigned long long)sh_acc);
 }
 
 template <class SEG>

@@ -14,6 +14,9 @@
 namespace csmc {
 
 constexpr int TPB = 256;  // threads per block of the pass kernels
+// accepted-proposal counters are striped: [replica][ACC_STRIPE]; one atomic per CTA lands on stripe
+// blockIdx.x % ACC_STRIPE (same-address L2 atomics serialise: one per warp cost ~10 us per pass at C2)
+constexpr int ACC_STRIPE = 32;
 
 enum { UPD_OR = 0, UPD_DET = 1, UPD_METRO = 2, UPD_CONE = 3 };
 enum { TAG_PROPOSE = 0, TAG_ACCEPT = 1, TAG_INIT = 2, TAG_EXCHANGE = 3 };
@@ -238,8 +241,9 @@ __global__ void __launch_bounds__(TPB) k_sweep(const __grid_constant__ P p, cons
         }
     }
     if (UPD == UPD_METRO || UPD == UPD_CONE) {
-        const unsigned ballot = __ballot_sync(0xffffffffu, accepted);
-        if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(a.accepted + rep, (unsigned long long)__popc(ballot));
+        const int n_acc = __syncthreads_count(accepted);
+        if (threadIdx.x == 0 && n_acc)
+            atomicAdd(a.accepted + (size_t)rep * ACC_STRIPE + (blockIdx.x & (ACC_STRIPE - 1)), (unsigned long long)n_acc);
     }
 }
 
@@ -314,7 +318,11 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const double *__restric
         for (int w = 0; w < 8; ++w) t += sh[threadIdx.x][w];
         if (threadIdx.x > 0 || write_energy) meas[(size_t)rep * 8 + threadIdx.x] = t;
     }
-    if (threadIdx.x == 4) meas[(size_t)rep * 8 + 4] = (double)accepted[rep];
+    if (threadIdx.x == 4) {
+        unsigned long long acc = 0;
+        for (int k = 0; k < ACC_STRIPE; ++k) acc += accepted[(size_t)rep * ACC_STRIPE + k];
+        meas[(size_t)rep * 8 + 4] = (double)acc;
+    }
 }
 
 // ---- evaluation kernels (API / parity tests): outputs in reference site order -------------------------
@@ -388,8 +396,10 @@ __global__ void k_add_u64(unsigned long long *ctr, unsigned long long v) { *ctr 
 __global__ void k_adapt_sigma(double *sigma, const unsigned long long *accepted, unsigned long long *prev, double n_sites, int R) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
-    const double acc = (double)(accepted[r] - prev[r]);
-    prev[r] = accepted[r];
+    unsigned long long now = 0;
+    for (int k = 0; k < ACC_STRIPE; ++k) now += accepted[(size_t)r * ACC_STRIPE + k];
+    const double acc = (double)(now - prev[r]);
+    prev[r] = now;
     const double a = acc / n_sites, f = 0.5 / fmax(1.0 - a, 0.05);
     sigma[r] = fmin(fmax(sigma[r] * f, 0.0), 100.0);
 }
