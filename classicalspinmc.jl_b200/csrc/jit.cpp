@@ -38,6 +38,22 @@ int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 struct Gen {
     const HostModel &hm;
     std::ostringstream o;
+    std::vector<double> ktab;                 // coefficients placed in the constant bank
+    std::map<uint64_t, int> kslot;
+    // interaction coefficient as an operand: simple values stay literals (the compiler folds +-1 into
+    // adds), everything else is read from a __constant__ table with a compile-time index, so it is a
+    // direct c[bank][offset] operand of the DFMA instead of an immediate built with two UMOVs
+    std::string coef(double v) {
+        static const bool use_table = std::getenv("CSMC_JIT_KTAB") != nullptr;   // A/B switch, default: literals
+        if (!use_table || v == 1.0 || v == -1.0 || v == 2.0 || v == -2.0 || v == 0.5 || v == -0.5) return lit(v);
+        uint64_t bits;
+        std::memcpy(&bits, &v, 8);
+        auto it = kslot.find(bits);
+        int idx;
+        if (it == kslot.end()) { idx = (int)ktab.size(); ktab.push_back(v); kslot[bits] = idx; }
+        else idx = it->second;
+        return "CSMC_K[" + std::to_string(idx) + "]";
+    }
     std::map<std::tuple<int, int, int, int>, int> seg_of_class;
     explicit Gen(const HostModel &h) : hm(h) {
         for (size_t s = 0; s < hm.segs.size(); ++s)
@@ -110,47 +126,16 @@ struct Gen {
         o << "    static __device__ __forceinline__ unsigned site(int m0, int m1, int m2) {\n";
         o << "        return (unsigned)(((" << b << " * " << hm.L[0] << " + (m0 * " << hs.P[0] << " + " << hs.r[0] << ")) * " << hm.L[1]
           << " + (m1 * " << hs.P[1] << " + " << hs.r[1] << ")) * " << hm.L[2] << " + (m2 * " << hs.P[2] << " + " << hs.r[2] << "));\n    }\n";
-        // phase 1: all neighbour loads (read-only for the duration of the pass: other colours) via ld.global.nc
-        o << "    static __device__ __forceinline__ void load(const double *__restrict__ sx, const double *__restrict__ sy, const double *__restrict__ sz,\n"
-             "            int m0, int m1, int m2, double (&nb)[3 * NNB + 1], unsigned &ok) {\n";
-        for (const auto &lv : live) {
-            const HostTerm &t = *lv.t;
-            o << "        { // slot " << lv.bit << " kind " << t.kind << "\n";
-            if (!hm.periodic) o << "          bool okt = true;\n";
-            for (int k = 0; k < t.kind - 1; ++k) neighbour(hs, t, k);
-            if (!hm.periodic) o << "          if (okt) {\n";
-            for (int k = 0; k < t.kind - 1; ++k) {
-                const int base = 3 * (lv.slot + k);
-                o << "          nb[" << base << "] = __ldg(sx + j" << k << "); nb[" << base + 1 << "] = __ldg(sy + j" << k << "); nb[" << base + 2 << "] = __ldg(sz + j" << k << ");\n";
-            }
-            if (!hm.periodic) {
-                o << "          } else {\n            ok &= ~(1u << " << lv.bit << ");\n";
-                for (int k = 0; k < t.kind - 1; ++k) {
-                    const int base = 3 * (lv.slot + k);
-                    o << "            nb[" << base << "] = 0.0; nb[" << base + 1 << "] = 0.0; nb[" << base + 2 << "] = 0.0;\n";
-                }
-                o << "          }\n";
-            }
-            o << "        }\n";
-        }
-        o << "    }\n";
-        // phase 2: unrolled neighbour field from registers: a* bilinear, b* cubic, c* quartic accumulators
-        o << "    static __device__ __forceinline__ void field(const double (&nb)[3 * NNB + 1], unsigned ok,\n"
-             "            double &a0, double &a1, double &a2, double &b0, double &b1, double &b2, double &c0, double &c1, double &c2) {\n";
-        for (const auto &lv : live) {
-            const HostTerm &t = *lv.t;
+        static const int preload_max = std::getenv("CSMC_JIT_PRELOAD_MAX") ? std::atoi(std::getenv("CSMC_JIT_PRELOAD_MAX")) : 64;
+        const bool preload = nnb <= preload_max;
+        o << "    static constexpr bool PRELOAD = " << (preload ? "true" : "false") << ";\n";
+        auto emit_accumulate = [&](const HostTerm &t) {
             const double *C = hm.coefs.data() + t.coef;
-            o << "      " << (hm.periodic ? "" : "if (ok & (1u << " + std::to_string(lv.bit) + ")) ") << "{ // slot " << lv.bit << "\n";
-            const char *nm[3] = {"p", "q", "w"};
-            for (int k = 0; k < t.kind - 1; ++k) {
-                const int base = 3 * (lv.slot + k);
-                o << "        const double " << nm[k] << "0 = nb[" << base << "], " << nm[k] << "1 = nb[" << base + 1 << "], " << nm[k] << "2 = nb[" << base + 2 << "];\n";
-            }
             if (t.kind == 2) {
                 for (int a = 0; a < 3; ++a) {
                     std::string e;
                     for (int c = 0; c < 3; ++c)
-                        if (C[3 * a + c] != 0.0) e += (e.empty() ? "" : " + ") + lit(C[3 * a + c]) + " * p" + std::to_string(c);
+                        if (C[3 * a + c] != 0.0) e += (e.empty() ? "" : " + ") + coef(C[3 * a + c]) + " * p" + std::to_string(c);
                     if (!e.empty()) o << "        a" << a << " += " << e << ";\n";
                 }
             } else if (t.kind == 3) {
@@ -161,7 +146,7 @@ struct Gen {
                         if (!used) continue;
                         o << "        { const double v = p" << bb << " * q" << c << ";";
                         for (int a = 0; a < 3; ++a)
-                            if (C[a * 9 + bb * 3 + c] != 0.0) o << " b" << a << " += " << lit(C[a * 9 + bb * 3 + c]) << " * v;";
+                            if (C[a * 9 + bb * 3 + c] != 0.0) o << " b" << a << " += " << coef(C[a * 9 + bb * 3 + c]) << " * v;";
                         o << " }\n";
                     }
             } else {
@@ -177,22 +162,89 @@ struct Gen {
                             if (!used) continue;
                             o << "          { const double v = vbc * w" << d << ";";
                             for (int a = 0; a < 3; ++a)
-                                if (C[a * 27 + bb * 9 + c * 3 + d] != 0.0) o << " c" << a << " += " << lit(C[a * 27 + bb * 9 + c * 3 + d]) << " * v;";
+                                if (C[a * 27 + bb * 9 + c * 3 + d] != 0.0) o << " c" << a << " += " << coef(C[a * 27 + bb * 9 + c * 3 + d]) << " * v;";
                             o << " }\n";
                         }
                         o << "        }\n";
                     }
             }
-            o << "      }\n";
-        }
+        };
+        const char *nm[3] = {"p", "q", "w"};
+        // phase 1 (PRELOAD): all neighbour loads up front (read-only during the pass: other colours) via ld.global.nc
+        o << "    static __device__ __forceinline__ void load(const double *__restrict__ sx, const double *__restrict__ sy, const double *__restrict__ sz,\n"
+             "            int m0, int m1, int m2, double (&nb)[PRELOAD ? 3 * NNB + 1 : 1], unsigned &ok) {\n";
+        if (preload)
+            for (const auto &lv : live) {
+                const HostTerm &t = *lv.t;
+                o << "        { // slot " << lv.bit << " kind " << t.kind << "\n";
+                if (!hm.periodic) o << "          bool okt = true;\n";
+                for (int k = 0; k < t.kind - 1; ++k) neighbour(hs, t, k);
+                if (!hm.periodic) o << "          if (okt) {\n";
+                for (int k = 0; k < t.kind - 1; ++k) {
+                    const int base = 3 * (lv.slot + k);
+                    o << "          nb[" << base << "] = __ldg(sx + j" << k << "); nb[" << base + 1 << "] = __ldg(sy + j" << k << "); nb[" << base + 2 << "] = __ldg(sz + j" << k << ");\n";
+                }
+                if (!hm.periodic) {
+                    o << "          } else {\n            ok &= ~(1u << " << lv.bit << ");\n";
+                    for (int k = 0; k < t.kind - 1; ++k) {
+                        const int base = 3 * (lv.slot + k);
+                        o << "            nb[" << base << "] = 0.0; nb[" << base + 1 << "] = 0.0; nb[" << base + 2 << "] = 0.0;\n";
+                    }
+                    o << "          }\n";
+                }
+                o << "        }\n";
+            }
+        o << "    }\n";
+        // phase 2 (PRELOAD): unrolled neighbour field from registers: a* bilinear, b* cubic, c* quartic accumulators
+        o << "    static __device__ __forceinline__ void field(const double (&nb)[PRELOAD ? 3 * NNB + 1 : 1], unsigned ok,\n"
+             "            double &a0, double &a1, double &a2, double &b0, double &b1, double &b2, double &c0, double &c1, double &c2) {\n";
+        if (preload)
+            for (const auto &lv : live) {
+                const HostTerm &t = *lv.t;
+                o << "      " << (hm.periodic ? "" : "if (ok & (1u << " + std::to_string(lv.bit) + ")) ") << "{ // slot " << lv.bit << "\n";
+                for (int k = 0; k < t.kind - 1; ++k) {
+                    const int base = 3 * (lv.slot + k);
+                    o << "        const double " << nm[k] << "0 = nb[" << base << "], " << nm[k] << "1 = nb[" << base + 1 << "], " << nm[k] << "2 = nb[" << base + 2 << "];\n";
+                }
+                emit_accumulate(t);
+                o << "      }\n";
+            }
+        o << "    }\n";
+        // streaming variant (many neighbours: keeping them all live would cost occupancy): gather and
+        // accumulate slot by slot
+        o << "    static __device__ __forceinline__ void field_stream(const double *__restrict__ sx, const double *__restrict__ sy, const double *__restrict__ sz,\n"
+             "            int m0, int m1, int m2, double &a0, double &a1, double &a2, double &b0, double &b1, double &b2, double &c0, double &c1, double &c2) {\n";
+        if (!preload)
+            for (const auto &lv : live) {
+                const HostTerm &t = *lv.t;
+                o << "      { // slot " << lv.bit << " kind " << t.kind << "\n";
+                if (!hm.periodic) o << "          bool okt = true;\n";
+                for (int k = 0; k < t.kind - 1; ++k) neighbour(hs, t, k);
+                if (!hm.periodic) o << "        if (okt) {\n";
+                for (int k = 0; k < t.kind - 1; ++k)
+                    o << "        const double " << nm[k] << "0 = __ldg(sx + j" << k << "), " << nm[k] << "1 = __ldg(sy + j" << k << "), " << nm[k] << "2 = __ldg(sz + j" << k << ");\n";
+                emit_accumulate(t);
+                if (!hm.periodic) o << "        }\n";
+                o << "      }\n";
+            }
         o << "    }\n};\n\n";
     }
 
     std::string run(JitPlan &plan) {
-        o << "#define NPAD " << hm.npad << "\n";
-        o << "#define SPIN_S " << lit(hm.S) << "\n";
-        o << kJitPrelude << "\n";
-        for (size_t s = 0; s < hm.segs.size(); ++s) segment((int)s);
+        {
+            std::ostringstream head;
+            head.swap(o);
+            for (size_t s = 0; s < hm.segs.size(); ++s) segment((int)s);   // fills ktab
+            std::string segs = o.str();
+            o.swap(head);
+            o << "#define NPAD " << hm.npad << "\n";
+            o << "#define SPIN_S " << lit(hm.S) << "\n";
+            o << kJitPrelude << "\n";
+            o << "__constant__ double CSMC_K[" << std::max<size_t>(ktab.size(), 1) << "] = {";
+            for (size_t k = 0; k < ktab.size(); ++k) o << (k ? ", " : "") << lit(ktab[k]);
+            if (ktab.empty()) o << "0.0";
+            o << "};\n\n" << segs;
+        }
         plan.tiles.assign(hm.n_colours, 1);
         plan.groups.assign(hm.n_colours, 1);
         for (int c = 0; c < hm.n_colours; ++c) {

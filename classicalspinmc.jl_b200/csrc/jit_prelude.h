@@ -79,7 +79,7 @@ struct Site {
     int pos, m0, m1, m2;
     unsigned ok;                      // open boundaries: bit t set <=> term t has all its neighbours
     double s0, s1, s2;
-    double nb[3 * SEG::NNB + 1];      // neighbour spins, compile-time indexed (registers)
+    double nb[SEG::PRELOAD ? 3 * SEG::NNB + 1 : 1];   // neighbour spins, compile-time indexed (registers)
 };
 
 template <class SEG>
@@ -91,7 +91,7 @@ __device__ __forceinline__ void site_load(Site<SEG> &d, const double *spins, int
     if (d.valid) {
         d.pos = SEG::pos(m0, m1, m2);
         d.s0 = sx[d.pos]; d.s1 = sy[d.pos]; d.s2 = sz[d.pos];
-        SEG::load(sx, sy, sz, m0, m1, m2, d.nb, d.ok);
+        if (SEG::PRELOAD) SEG::load(sx, sy, sz, m0, m1, m2, d.nb, d.ok);
     }
 }
 
@@ -127,7 +127,8 @@ __device__ __forceinline__ bool site_finish(Site<SEG> &d, double *spins, int rep
                 g2 = 2 * (SEG::O6 * s0 + SEG::O7 * s1 + SEG::O8 * s2);
             }
         }
-        SEG::field(d.nb, d.ok, g0, g1, g2, g0, g1, g2, g0, g1, g2);
+        if (SEG::PRELOAD) SEG::field(d.nb, d.ok, g0, g1, g2, g0, g1, g2, g0, g1, g2);
+        else SEG::field_stream(sx, sy, sz, d.m0, d.m1, d.m2, g0, g1, g2, g0, g1, g2, g0, g1, g2);
         const double F0 = g0 - SEG::H0, F1 = g1 - SEG::H1, F2 = g2 - SEG::H2;
         if (UPD == UPD_OR) {
             if (!(F0 == 0.0 && F1 == 0.0 && F2 == 0.0)) {
@@ -178,7 +179,11 @@ __device__ __forceinline__ void energy_site(const double *spins, double (&v)[4])
         site_load(d, spins, rep, m0, m1, m2);
         const double s0 = d.s0, s1 = d.s1, s2 = d.s2;
         double a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0, c0 = 0, c1 = 0, c2 = 0;
-        SEG::field(d.nb, d.ok, a0, a1, a2, b0, b1, b2, c0, c1, c2);
+        if (SEG::PRELOAD) SEG::field(d.nb, d.ok, a0, a1, a2, b0, b1, b2, c0, c1, c2);
+        else {
+            const double *sx = spins + (size_t)rep * (3ull * NPAD), *sy = sx + NPAD, *sz = sy + NPAD;
+            SEG::field_stream(sx, sy, sz, m0, m1, m2, a0, a1, a2, b0, b1, b2, c0, c1, c2);
+        }
         double e = (s0 * a0 + s1 * a1 + s2 * a2) / 2 + (s0 * b0 + s1 * b1 + s2 * b2) / 3 +
                    (s0 * c0 + s1 * c1 + s2 * c2) / 4 - (s0 * SEG::H0 + s1 * SEG::H1 + s2 * SEG::H2);
         if (SEG::ONSITE)
