@@ -114,12 +114,13 @@ def measured_peak_gbs():
     return 6650.0, "fallback"
 
 
-def ncu_traffic(workload):
+def ncu_traffic(workload, L=None):
     """dram bytes per launch of the dominant kernel from the committed ncu --set full capture."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(workload)
+            d = json.load(open(p))
+            return d.get(f"{workload}:{L}") if (L and f"{workload}:{L}" in d) else (d.get(workload) if not L or L == 1024 else None)
         except Exception:
             return None
     return None
@@ -312,10 +313,10 @@ def run_ours(args):
     bytes_per_launch = B_ALG.get(n_col, 24.0 * (n_col + 1)) * N / n_col
     peak, peak_kind = measured_peak_gbs()
     achieved = bytes_per_launch / (pass_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_sweep<OR> colour pass", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "csmc_sweep_c<colour>_u0 (overrelaxation colour pass)", "achieved": achieved, "peak": peak,
                 "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
                 "us_per_launch": pass_ms * 1e3, "algorithmic_bytes_per_launch": bytes_per_launch,
-                "traffic": ncu_traffic(cfg["workload"])}
+                "traffic": ncu_traffic(cfg["workload"], cfg.get("L"))}
 
     # ---- end to end through the C-ABI with HOST buffers ---------------------------------------------------
     host_in = torch.empty((N, 3), dtype=torch.float64).pin_memory()
