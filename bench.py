@@ -14,7 +14,6 @@ parallel-tempering exchange path over NCCL is measured separately with --workloa
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time

@@ -78,7 +78,6 @@ struct csmc_handle {
     std::vector<PassLarge> pl;
     bool large = false;
     unsigned long long metro_ctr = 0;  // Metropolis sweeps enqueued so far (Philox counter)
-    unsigned long long acc_reset[1] = {0};
     std::vector<unsigned long long> acc_base;  // per-replica counter value at last reset
 
     // parallel tempering
@@ -135,7 +134,7 @@ void launch_sweep_pass(csmc_handle *h, int colour, const SweepArgs &a) {
         // multi-dimensional CTA tiles over supercell coordinates, classes fused per thread (jit.cpp)
         void *args[] = {(void *)&h->d_spins, (void *)&a};
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(h->jit_plan.tiles[colour], h->jit_plan.groups[colour], h->R);
+        cfg.gridDim = dim3(h->jit_plan.tiles[colour], (UPD >= UPD_METRO ? h->jit_plan.groups_metro : h->jit_plan.groups)[colour], h->R);
         cfg.blockDim = block;
         cfg.stream = h->stream;
         cudaLaunchAttribute attr[1];

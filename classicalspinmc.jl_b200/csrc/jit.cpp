@@ -269,12 +269,19 @@ struct Gen {
             if (hm.D == 1) T[0] = 256;
             for (int d = 0; d < MAXD; ++d) NT[d] = (M[d] + T[d] - 1) / T[d];
             plan.tiles[c] = NT[0] * NT[1] * NT[2];
-            // classes of the colour are fused in pairs into one thread (shared neighbour loads, ILP)
-            const int G = std::min(nseg, 2);
-            const int ngroups = (nseg + G - 1) / G;
-            plan.groups[c] = ngroups;
+            // classes of the colour are fused in pairs into one thread (shared neighbour loads, ILP);
+            // tuning knobs (environment, for A/B runs): CSMC_JIT_FUSE / CSMC_JIT_FUSE_METRO (classes per
+            // thread), CSMC_JIT_MB / CSMC_JIT_MB_METRO (min resident CTAs per SM in __launch_bounds__)
+            auto env_int = [](const char *n, int dflt) { const char *v = std::getenv(n); return v ? std::atoi(v) : dflt; };
+            const int fuse_or = std::max(1, env_int("CSMC_JIT_FUSE", 2)), fuse_mc = std::max(1, env_int("CSMC_JIT_FUSE_METRO", 1));
+            const int mb_or = std::max(1, env_int("CSMC_JIT_MB", 1)), mb_mc = std::max(1, env_int("CSMC_JIT_MB_METRO", mb_or));
+            plan.groups[c] = 0;
             for (int u = 0; u < 4; ++u) {
-                o << "extern \"C\" __global__ void __launch_bounds__(TPB) csmc_sweep_c" << c << "_u" << u << "(double *spins, const SweepArgs a) {\n";
+                const int G = std::min(nseg, u >= 2 ? fuse_mc : fuse_or);
+                const int ngroups = (nseg + G - 1) / G;
+                if (u == 0) plan.groups[c] = ngroups;
+                if (u == 2) plan.groups_metro.resize(hm.n_colours), plan.groups_metro[c] = ngroups;
+                o << "extern \"C\" __global__ void __launch_bounds__(TPB, " << (u >= 2 ? mb_mc : mb_or) << ") csmc_sweep_c" << c << "_u" << u << "(double *spins, const SweepArgs a) {\n";
                 o << "#ifdef CSMC_PDL\n    pdl_launch_dependents();\n    pdl_wait();\n#endif\n";
                 o << "    const int rep = blockIdx.z;\n    int t = blockIdx.x;\n";
                 o << "    const int t2 = t % " << NT[2] << "; t /= " << NT[2] << "; const int t1 = t % " << NT[1] << "; const int t0 = t / " << NT[1] << ";\n";

@@ -93,10 +93,24 @@ def test_plan_rejects_bad_models():
         _lib.plan(md)
 
 
-def test_library_tables_match_oracle_tables():
-    """csmc_get_tables is host-only: reference-layout neighbour tables vs the oracle's."""
-    # (the handle-based getter needs a GPU; the same closed form is exercised through csmc_plan's
-    # colouring above and through tests/test_gpu_parity.py::test_tables on the GPU box)
-    md = ModelData(models.mixed_basis_multispin(), (3, 4), 1.0)
-    colour, n_colours, st, pos = _lib.plan(md)
-    assert n_colours >= 2
+@pytest.mark.parametrize("name,builder,shape,bc,ncol,structured", PLAN_CASES, ids=[c[0] for c in PLAN_CASES])
+def test_library_tables_match_oracle_tables(name, builder, shape, bc, ncol, structured):
+    """csmc_reference_tables (host-only closed form, what Lattice.bilinear_sites etc. expose) against the
+    oracle's literal restatement of the reference constructor's findfirst scan."""
+    md = ModelData(builder(), shape, 1.0, bc)
+    lat = orc.OracleLattice(md, literal=True)
+    for a, b in zip(_lib.reference_tables(md), lat.tables()):
+        assert np.array_equal(a, b)
+
+
+def test_jit_source_generation_and_nvrtc_compile():
+    """The per-model kernel source is generated and compiled for sm_100a without a GPU (csmc_jit_check)."""
+    md = ModelData(models.kitaev_honeycomb(), (8, 8), 1.0)
+    src, log = _lib.jit_check(md, compile=True)
+    assert 'extern "C" __global__' in src and "csmc_sweep_c0_u0" in src and "csmc_energy_c1" in src
+    assert "struct Seg0" in src and "struct Seg1" in src
+    # literal coefficients: K + J = -1 appears as an exact hexadecimal literal
+    assert "(-0x1p+0)" in src
+    md2 = ModelData(models.square_heisenberg(), (11, 13), 1.0)     # no periodic pattern -> no specialisation
+    with pytest.raises(_lib.CsmcError, match="explicit-table"):
+        _lib.jit_check(md2, compile=False)
