@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <new>
 #include <string>
@@ -99,6 +100,8 @@ struct csmc_handle {
     // CUDA graph of one bench cycle
     cudaGraphExec_t cycle_graph = nullptr;
     int cycle_or = -1, cycle_metro = -1;
+    // CUDA graphs of n consecutive overrelaxation sweeps (parallel-tempering loop)
+    std::map<int, cudaGraphExec_t> or_graphs;
 
     std::string err;
     long long launches = 0;
@@ -446,6 +449,7 @@ int32_t csmc_destroy(csmc_handle *h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->cycle_graph) cudaGraphExecDestroy(h->cycle_graph);
+    for (auto &kv : h->or_graphs) cudaGraphExecDestroy(kv.second);
     if (h->jit_lib) cudaLibraryUnload(h->jit_lib);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     free_pt(h);
@@ -719,6 +723,33 @@ int32_t csmc_cycles_async(csmc_handle *h, int64_t n_cycles, int32_t orc, int32_t
     return CSMC_OK;
 }
 
+// n consecutive overrelaxation sweeps: one graph replay instead of 2*n*colours launches
+static int enqueue_or_block(csmc_handle *h, int n) {
+    if (n <= 0) return CSMC_OK;
+    if ((h->flags & CSMC_FLAG_NO_GRAPH) || n < 2) {
+        for (int s = 0; s < n; ++s) enqueue_sweep<UPD_OR>(h);
+        return CSMC_OK;
+    }
+    auto it = h->or_graphs.find(n);
+    if (it == h->or_graphs.end()) {
+        cudaGraph_t graph = nullptr;
+        const long long before = h->launches;
+        CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        for (int s = 0; s < n; ++s) enqueue_sweep<UPD_OR>(h);
+        CK(cudaStreamEndCapture(h->stream, &graph));
+        h->launches = before;
+        cudaGraphExec_t exec = nullptr;
+        cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return fail(h, CSMC_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+        if (h->or_graphs.size() > 64) { for (auto &kv : h->or_graphs) cudaGraphExecDestroy(kv.second); h->or_graphs.clear(); }
+        it = h->or_graphs.emplace(n, exec).first;
+    }
+    CK(cudaGraphLaunch(it->second, h->stream));
+    h->launches += (long long)n * h->hm.n_colours;
+    return CSMC_OK;
+}
+
 int32_t csmc_sync(csmc_handle *h) { NEED(h); CK(cudaSetDevice(h->device)); return finish(h); }
 
 int32_t csmc_anneal_temperature(csmc_handle *h, const double *T, int64_t t_thermalization, int32_t rate, double *accepted) {
@@ -834,9 +865,12 @@ int32_t csmc_pt_run(csmc_handle *h, const csmc_pt_params *p, int64_t sweep_begin
     rc = ensure_series(h, h->n_probes + probes); if (rc) return rc;
     PtState st = pt_state(h);
     const int nb = (h->n_slots + 127) / 128;
+    int pending_or = 0;   // overrelaxation sweeps not yet enqueued (flushed as one graph replay)
     for (int64_t sweep = sweep_begin; sweep < sweep_end; ++sweep) {
-        if (rate != 0) enqueue_sweep<UPD_OR>(h);                                // :298-300
+        if (rate != 0) ++pending_or;                                            // :298-300
         const bool metro = (sweep % dosweep == 0);
+        const bool probe = (sweep >= p->t_thermalization && sweep % p->probe_rate == 0);
+        if (metro || probe || sweep + 1 == sweep_end) { rc = enqueue_or_block(h, pending_or); if (rc) return rc; pending_or = 0; }
         if (metro) {                                                            // :302-305
             enqueue_metropolis(h, false);
             rc = enqueue_measure_all(h, true); if (rc) return rc;
@@ -846,7 +880,7 @@ int32_t csmc_pt_run(csmc_handle *h, const csmc_pt_params *p, int64_t sweep_begin
                 k_pt_exchange<<<1, 128, 0, h->stream>>>(st, (int)(k % 2), (unsigned long long)k, h->seed); h->launches++;
             }
         }
-        if (sweep >= p->t_thermalization && sweep % p->probe_rate == 0) {       // :353,368-370
+        if (probe) {                                                            // :353,368-370
             if (!metro) { rc = enqueue_measure_all(h, false); if (rc) return rc; }
             k_pt_probe<<<nb, 128, 0, h->stream>>>(st, h->d_series_E, h->d_series_M, h->n_probes); h->launches++;
             h->n_probes++;
