@@ -1,0 +1,137 @@
+"""The reference's own tests restated against the host mirror (Python stand-in for the Julia layer),
+running on the GPU through libcsmc, plus driver-level behaviour: output files, parallel tempering
+through `parallel_tempering`, error reporting across the C-ABI."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import classicalspinmc.jl_b200 as csm
+from classicalspinmc.jl_b200 import _lib
+from classicalspinmc.jl_b200 import hdf5 as h5
+from classicalspinmc.jl_b200._abi import FLAG_FORCE_GENERIC, ModelData
+from tests import models
+
+pytestmark = pytest.mark.gpu
+
+
+def test_lattice_tests_jl():
+    # test/latticetests.jl:3-31, line by line
+    U = csm.Square()
+    lat = csm.Lattice((2, 2), U, 1.0)
+    assert np.all(np.round(np.linalg.norm(lat.spins, axis=0), 9) == 1.0)
+
+    U = csm.Square()
+    h = np.array([1.0, 0.0, 0.0])
+    csm.addZeemanCoupling(U, 1, h)
+    lat = csm.Lattice((1, 1), U, 1.0)
+    lat.spins[:] = np.array([1.0, 0.0, 0.0])[:, None]
+    assert -1.0 == csm.total_energy(lat)
+    assert tuple(-h) == csm.get_local_field(lat, 1)
+
+    U = csm.Square()
+    J = -1.0 * np.eye(3)
+    csm.addBilinear(U, 1, 1, J, (1, 0))
+    csm.addBilinear(U, 1, 1, J, (-1, 0))
+    csm.addBilinear(U, 1, 1, J, (0, 1))
+    csm.addBilinear(U, 1, 1, J, (0, -1))
+    lat = csm.Lattice((2, 2), U, 1.0)
+    lat.spins[:] = np.array([1.0, 0.0, 0.0])[:, None]
+    assert -2.0 == csm.total_energy(lat) / lat.size
+    # the host array is the state of a bare Lattice: mutate and re-evaluate
+    lat.spins[:, 0] = (0.0, 0.0, 1.0)
+    assert abs(csm.total_energy(lat) - (-4.0)) < 1e-14
+    assert abs(csm.get_magnetization(lat) - np.linalg.norm([3.0, 0.0, 1.0])) < 1e-14
+
+
+def test_adaptive_annealing_mctests_jl():
+    # test/mctests.jl:52-58: MetropolisAdaptive, no deterministic step
+    lat = csm.Lattice((4, 4), models.kitaev_honeycomb(), 1, rng=np.random.default_rng(8))
+    params = {"t_thermalization": 2000, "overrelaxation_rate": 10, "t_deterministic": int(1e6)}
+    mc = csm.MonteCarlo(1e-7, lat, params, seed=4)
+    csm.simulated_annealing(mc, lambda x: 1.0 * 0.9 ** x, 1.0, alg=csm.MetropolisAdaptive())
+    assert round(csm.energy_density(mc.lattice), 3) == -0.644
+    assert 0.0 <= mc.sigma <= 100.0
+
+
+def test_drivers_write_reference_file_layout(tmp_path):
+    out = str(tmp_path) + "/"
+    lat = csm.Lattice((4, 4), models.kitaev_honeycomb(), 1.0, rng=np.random.default_rng(2))
+    params = {"t_thermalization": 50, "overrelaxation_rate": 5}
+    mc = csm.MonteCarlo(0.5, lat, params, outpath=out, seed=9)
+    csm.simulated_annealing(mc, lambda x: 1.0 * 0.5 ** x, 1.0)      # checkpoint after every temperature
+    lat2 = csm.Lattice((4, 4), models.kitaev_honeycomb(), 1.0)
+    csm.read_spin_configuration(lat2, out + "configuration_0.h5")
+    assert np.array_equal(lat2.spins, mc.lattice.spins)
+
+
+def test_parallel_tempering_driver_single_process(tmp_path):
+    """parallel_tempering! with four temperature slots in one process (one GPU): observables per slot,
+    files per slot, configurations attributed to temperatures."""
+    out = str(tmp_path) + "/"
+    lat = csm.Lattice((4, 4), models.kitaev_honeycomb(), 1.0, rng=np.random.default_rng(3))
+    Ts = np.geomspace(0.2, 1.0, 4)
+    params = {"t_thermalization": 400, "t_measurement": 1600, "probe_rate": 10, "swap_rate": 10,
+              "overrelaxation_rate": 5, "report_interval": 1000, "checkpoint_rate": 800}
+    mc = csm.MonteCarlo(Ts, lat, params, outpath=out, seed=12)
+    csm.parallel_tempering(mc, saveIC=[0])
+    st = mc.statistics
+    assert st["energy_series"].shape == (160, 4)
+    assert sorted(st["slot_of_replica"].tolist()) == [0, 1, 2, 3]
+    assert st["exchanges"].sum() > 0
+    E_mean = [o.energy.mean(1) for o in mc.observables_all]
+    assert E_mean[0] < E_mean[-1]                       # colder slot, lower energy
+    for s in range(4):
+        path = out + f"configuration_{s}.h5"
+        assert os.path.isfile(path)
+        obs = h5.read_observables(path)
+        assert set(obs) == {"specific_heat", "specific_heat_err", "susceptibility", "susceptibility_err",
+                            "magnetization", "magnetization_err", "energy", "energy_err"}
+        assert abs(obs["energy"] - E_mean[s]) < 1e-9
+        f = h5._open(path, "r")
+        assert abs(h5._get_attr(f, "T") - Ts[s]) < 1e-15
+        f.close()
+    assert os.path.isfile(out + "IC_0/IC_0.h5") and os.path.isfile(out + "IC_0/IC_1.h5")
+    # mc.lattice.spins is the configuration sitting at temperature slot 0 at the end; its energy is the
+    # last recorded energy of slot 0 up to the sweeps after the last probe -> just check consistency
+    e0 = csm.total_energy(mc.lattice)
+    assert np.isfinite(e0) and np.allclose(np.linalg.norm(mc.lattice.spins, axis=0), 1.0, atol=1e-9)
+
+
+def test_errors_cross_the_abi_as_status_codes():
+    L = _lib.lib()
+    md = ModelData(models.square_heisenberg(), (4, 4), 1.0)
+    eng = _lib.Engine(md)
+    out = np.zeros(3)
+    assert L.csmc_local_field(eng._h, 0, 0, out.ctypes.data_as(ctypes.c_void_p)) == 1          # site is 1-based
+    assert b"site out of range" in L.csmc_last_error(eng._h)
+    assert L.csmc_local_field(eng._h, 5, 1, out.ctypes.data_as(ctypes.c_void_p)) == 1          # replica
+    assert L.csmc_set_spins(eng._h, 0, None) == 1                                              # NULL buffer
+    assert L.csmc_total_energy(None, out.ctypes.data_as(ctypes.c_void_p)) == 1                 # NULL handle
+    with pytest.raises(_lib.CsmcError, match="temperatures must be > 0"):
+        eng.metropolis(0.0, 1)
+    with pytest.raises(_lib.CsmcError, match="csmc_pt_init has not been called"):
+        eng.pt_run(dict(t_thermalization=1, t_measurement=1, probe_rate=1, swap_rate=1, overrelaxation_rate=1), 0, 1)
+    md_bad = ModelData(models.square_heisenberg(), (4, 4), 1.0)
+    md_bad.struct.dim = 7
+    with pytest.raises(_lib.CsmcError, match="dim must be 1..3"):
+        _lib.Engine(md_bad)
+    # a handle stays usable after an error
+    eng.randomize(1)
+    assert np.isfinite(eng.total_energy()[0])
+
+
+def test_open_boundary_parallel_tempering_generic_kernels():
+    """Open boundaries + lattice without a periodic colouring pattern: the explicit-table kernels run the
+    whole PT loop; energies stay consistent with a fresh evaluation."""
+    md = ModelData(models.square_heisenberg(), (7, 5), 1.0, "open")
+    eng = _lib.Engine(md, n_replicas=3, seed=3, flags=FLAG_FORCE_GENERIC)
+    assert eng.kernel_mode == 0
+    eng.randomize(5)
+    eng.pt_init([0.3, 0.6, 1.2])
+    p = dict(t_thermalization=100, t_measurement=200, probe_rate=10, swap_rate=5, overrelaxation_rate=4)
+    eng.pt_run(p, 0, 300)
+    E, M = eng.pt_series()
+    assert E.shape == (20, 3) and np.all(np.isfinite(E)) and np.all(M >= 0)
+    assert E[:, 0].mean() < E[:, 2].mean()
