@@ -63,6 +63,7 @@ FLAG_NO_GRAPH = 2
 FLAG_JIT = 4
 FLAG_NO_JIT = 8
 FLAG_PDL = 16
+FLAG_NO_RESIDENT = 32
 
 
 def resolve_field_onsite(uc):

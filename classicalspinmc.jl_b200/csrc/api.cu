@@ -95,6 +95,8 @@ struct csmc_handle {
     cudaLibrary_t jit_lib = nullptr;
     std::vector<cudaKernel_t> jit_sweep[4], jit_energy;
     JitPlan jit_plan;
+    cudaKernel_t jit_resident = nullptr;
+    bool jit_tried = false;
     std::string jit_note;
 
     // CUDA graph of one bench cycle
@@ -210,6 +212,101 @@ void enqueue_eval(csmc_handle *h, int rep, int what, double *out) {
         }
         h->launches++;
     }
+}
+
+
+// Builds (once) the kernels specialised for this handle's model; "" on success.  On failure the
+// ahead-of-time kernels stay in use and csmc_kernel_mode reports the reason.
+std::map<size_t, std::vector<char>> g_cubin_cache;   // generated source hash -> cubin (same model, many handles)
+std::mutex g_cubin_mu;
+
+std::string build_jit(csmc_handle *h) {
+    if (h->jit) return "";
+    if (h->jit_tried) return h->jit_note;
+    h->jit_tried = true;
+    const HostModel &hm = h->hm;
+    std::string err;
+    if ((h->flags & CSMC_FLAG_NO_JIT) || !hm.structured || hm.self_loop) {
+        h->jit_note = "not applicable (no periodic colouring pattern, self-interaction, or CSMC_FLAG_NO_JIT)";
+        return h->jit_note;
+    }
+    std::string log;
+    std::vector<char> cubin;
+    try {
+        const std::string src = jit_generate_source(hm, (h->flags & CSMC_FLAG_PDL) != 0, &h->jit_plan);
+        const size_t key = std::hash<std::string>{}(src);
+        {
+            std::lock_guard<std::mutex> lk(g_cubin_mu);
+            auto it = g_cubin_cache.find(key);
+            if (it != g_cubin_cache.end()) cubin = it->second;
+        }
+        if (cubin.empty()) {
+            err = jit_compile(src, cubin, log);
+            if (err.empty()) {
+                std::lock_guard<std::mutex> lk(g_cubin_mu);
+                if (g_cubin_cache.size() > 64) g_cubin_cache.clear();
+                g_cubin_cache[key] = cubin;
+            }
+        }
+    } catch (const std::exception &ex) {
+        err = std::string("code generation failed: ") + ex.what();
+    }
+    if (err.empty()) {
+        cudaError_t ce = cudaLibraryLoadData(&h->jit_lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+        if (ce != cudaSuccess) err = std::string("cudaLibraryLoadData: ") + cudaGetErrorString(ce);
+    }
+    if (err.empty()) {
+        for (int u = 0; u < 4 && err.empty(); ++u) {
+            h->jit_sweep[u].resize(hm.n_colours);
+            for (int c = 0; c < hm.n_colours; ++c) {
+                const std::string nm = "csmc_sweep_c" + std::to_string(c) + "_u" + std::to_string(u);
+                if (cudaLibraryGetKernel(&h->jit_sweep[u][c], h->jit_lib, nm.c_str()) != cudaSuccess) { err = "kernel not found: " + nm; break; }
+            }
+        }
+        h->jit_energy.resize(hm.n_colours);
+        for (int c = 0; c < hm.n_colours && err.empty(); ++c) {
+            const std::string nm = "csmc_energy_c" + std::to_string(c);
+            if (cudaLibraryGetKernel(&h->jit_energy[c], h->jit_lib, nm.c_str()) != cudaSuccess) err = "kernel not found: " + nm;
+        }
+        if (err.empty() && h->jit_plan.resident) {
+            if (cudaLibraryGetKernel(&h->jit_resident, h->jit_lib, "csmc_resident") != cudaSuccess) err = "kernel not found: csmc_resident";
+            else {
+                const int smem = 3 * hm.npad * (int)sizeof(double);
+                if (cudaFuncSetAttribute((const void *)h->jit_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+                    cudaGetLastError();
+                    h->jit_resident = nullptr;     // pass kernels still work
+                }
+            }
+        }
+    }
+    if (err.empty()) {
+        // graphs captured with the ahead-of-time kernels must not be replayed any more
+        if (h->cycle_graph) { cudaGraphExecDestroy(h->cycle_graph); h->cycle_graph = nullptr; h->cycle_or = h->cycle_metro = -1; }
+        for (auto &kv : h->or_graphs) cudaGraphExecDestroy(kv.second);
+        h->or_graphs.clear();
+        h->jit = true;
+    } else {
+        cudaGetLastError();
+        h->jit_note = err;
+    }
+    return err;
+}
+
+// small lattices: one CTA per replica, lattice resident in shared memory (see jit.cpp)
+bool use_resident(csmc_handle *h, long long sweeps_requested) {
+    if ((h->flags & (CSMC_FLAG_NO_RESIDENT | CSMC_FLAG_NO_JIT)) || h->hm.N > 4096) return false;
+    if (!h->jit && !h->jit_tried && (sweeps_requested >= 32 || (h->flags & CSMC_FLAG_JIT))) build_jit(h);
+    return h->jit && h->jit_resident != nullptr;
+}
+
+// n_cycles x (orc OR + mc Metropolis sweeps) then det deterministic sweeps, optional measurement record
+void enqueue_resident(csmc_handle *h, int n_cycles, int orc, int mc, int cone, int det, double *meas, int write_energy) {
+    SweepArgs a = sweep_args(h, h->metro_ctr, false);
+    void *args[] = {(void *)&h->d_spins, (void *)&a, (void *)&n_cycles, (void *)&orc, (void *)&mc, (void *)&cone, (void *)&det, (void *)&meas, (void *)&write_energy};
+    const size_t smem = (size_t)3 * h->hm.npad * sizeof(double);
+    cudaLaunchKernel((const void *)h->jit_resident, dim3(h->R), dim3(256), args, smem, h->stream);
+    h->metro_ctr += (unsigned long long)n_cycles * mc;
+    h->launches++;
 }
 
 int finish(csmc_handle *h) {
@@ -366,46 +463,13 @@ int32_t csmc_create(const csmc_model *model, const csmc_opts *opts, csmc_handle 
         }
         if (!pe.empty()) return bail(CSMC_ERR_UNSUPPORTED, pe);
     }
-    // runtime specialisation
-    {
-        const bool want = !(h->flags & CSMC_FLAG_NO_JIT) && hm.structured && !hm.self_loop &&
-                          ((h->flags & CSMC_FLAG_JIT) || (int64_t)hm.N * h->R >= 32768);
-        if ((h->flags & CSMC_FLAG_JIT) && !hm.structured)
-            return bail(CSMC_ERR_UNSUPPORTED, "CSMC_FLAG_JIT: the model has no periodic colouring pattern (explicit-table kernels only)");
-        if (want) {
-            std::string err, log;
-            std::vector<char> cubin;
-            try {
-                const std::string src = jit_generate_source(hm, (h->flags & CSMC_FLAG_PDL) != 0, &h->jit_plan);
-                err = jit_compile(src, cubin, log);
-            } catch (const std::exception &ex) {
-                err = std::string("code generation failed: ") + ex.what();
-            }
-            if (err.empty()) {
-                cudaError_t ce = cudaLibraryLoadData(&h->jit_lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
-                if (ce != cudaSuccess) err = std::string("cudaLibraryLoadData: ") + cudaGetErrorString(ce);
-            }
-            if (err.empty()) {
-                for (int u = 0; u < 4 && err.empty(); ++u) {
-                    h->jit_sweep[u].resize(hm.n_colours);
-                    for (int c = 0; c < hm.n_colours; ++c) {
-                        const std::string nm = "csmc_sweep_c" + std::to_string(c) + "_u" + std::to_string(u);
-                        if (cudaLibraryGetKernel(&h->jit_sweep[u][c], h->jit_lib, nm.c_str()) != cudaSuccess) { err = "kernel not found: " + nm; break; }
-                    }
-                }
-                h->jit_energy.resize(hm.n_colours);
-                for (int c = 0; c < hm.n_colours && err.empty(); ++c) {
-                    const std::string nm = "csmc_energy_c" + std::to_string(c);
-                    if (cudaLibraryGetKernel(&h->jit_energy[c], h->jit_lib, nm.c_str()) != cudaSuccess) err = "kernel not found: " + nm;
-                }
-            }
-            if (err.empty()) h->jit = true;
-            else {
-                cudaGetLastError();
-                if (h->flags & CSMC_FLAG_JIT) return bail(CSMC_ERR_UNSUPPORTED, "runtime specialisation failed: " + err);
-                h->jit_note = err;   // ahead-of-time kernels stay in use; csmc_kernel_mode reports it
-            }
-        }
+    // runtime specialisation: eager for problems large enough to be bandwidth-bound (or on request),
+    // lazy (first long sweep request) for small lattices, which then run on the resident kernel
+    if ((h->flags & CSMC_FLAG_JIT) && !hm.structured)
+        return bail(CSMC_ERR_UNSUPPORTED, "CSMC_FLAG_JIT: the model has no periodic colouring pattern (explicit-table kernels only)");
+    if ((h->flags & CSMC_FLAG_JIT) || (int64_t)hm.N * h->R >= 32768) {
+        std::string jerr = build_jit(h);
+        if (!jerr.empty() && (h->flags & CSMC_FLAG_JIT)) return bail(CSMC_ERR_UNSUPPORTED, "runtime specialisation failed: " + jerr);
     }
 #undef CKC
     *out = h;
@@ -470,7 +534,7 @@ int32_t csmc_n_colours(const csmc_handle *h, int32_t *c) { NEED(h); NEEDARG(h, c
 int32_t csmc_is_structured(const csmc_handle *h, int32_t *f) { NEED(h); NEEDARG(h, f); *f = h->hm.structured ? 1 : 0; return CSMC_OK; }
 int32_t csmc_kernel_mode(const csmc_handle *h, int32_t *mode) {
     NEED(h); NEEDARG(h, mode);
-    *mode = h->jit ? 2 : (h->hm.structured ? 1 : 0);
+    *mode = h->jit ? (h->jit_resident && h->hm.N <= 4096 && !(h->flags & CSMC_FLAG_NO_RESIDENT) ? 3 : 2) : (h->hm.structured ? 1 : 0);
     if (!h->jit && !h->jit_note.empty()) const_cast<csmc_handle *>(h)->err = "runtime specialisation unavailable: " + h->jit_note;
     return CSMC_OK;
 }
@@ -605,14 +669,16 @@ int32_t csmc_magnetization(csmc_handle *h, double *M3) {
 int32_t csmc_overrelax(csmc_handle *h, int32_t n_sweeps) {
     NEED(h);
     CK(cudaSetDevice(h->device));
-    for (int s = 0; s < n_sweeps; ++s) enqueue_sweep<UPD_OR>(h);
+    if (n_sweeps > 0 && use_resident(h, n_sweeps)) enqueue_resident(h, 1, n_sweeps, 0, 0, 0, nullptr, 0);
+    else for (int s = 0; s < n_sweeps; ++s) enqueue_sweep<UPD_OR>(h);
     return finish(h);
 }
 
 int32_t csmc_deterministic(csmc_handle *h, int32_t n_sweeps) {
     NEED(h);
     CK(cudaSetDevice(h->device));
-    for (int s = 0; s < n_sweeps; ++s) enqueue_sweep<UPD_DET>(h);
+    if (n_sweeps > 0 && use_resident(h, n_sweeps)) enqueue_resident(h, 0, 0, 0, 0, n_sweeps, nullptr, 0);
+    else for (int s = 0; s < n_sweeps; ++s) enqueue_sweep<UPD_DET>(h);
     return finish(h);
 }
 
@@ -640,7 +706,8 @@ int32_t csmc_metropolis(csmc_handle *h, const double *T, int32_t n_sweeps, doubl
     rc = upload_T(h, T); if (rc) return rc;
     std::vector<double> before(h->R), after(h->R);
     if (accepted) { rc = csmc_get_accepted(h, before.data(), 0); if (rc) return rc; }
-    for (int s = 0; s < n_sweeps; ++s) enqueue_metropolis(h, false);
+    if (n_sweeps > 0 && use_resident(h, n_sweeps)) enqueue_resident(h, 1, 0, n_sweeps, 0, 0, nullptr, 0);
+    else for (int s = 0; s < n_sweeps; ++s) enqueue_metropolis(h, false);
     rc = finish(h); if (rc) return rc;
     if (accepted) {
         rc = csmc_get_accepted(h, after.data(), 0); if (rc) return rc;
@@ -664,7 +731,8 @@ int32_t csmc_metropolis_cone(csmc_handle *h, const double *T, double *sigma, int
         CK(cudaMemcpyAsync(h->d_acc_prev, prev.data(), sizeof(unsigned long long) * h->R, cudaMemcpyHostToDevice, h->stream));
         CK(cudaStreamSynchronize(h->stream));
     }
-    for (int s = 0; s < n_sweeps; ++s) {
+    if (!adapt && n_sweeps > 0 && use_resident(h, n_sweeps)) enqueue_resident(h, 1, 0, n_sweeps, 1, 0, nullptr, 0);
+    else for (int s = 0; s < n_sweeps; ++s) {
         enqueue_metropolis(h, true);
         if (adapt) { k_adapt_sigma<<<(h->R + 127) / 128, 128, 0, h->stream>>>(h->d_sigma, h->d_acc, h->d_acc_prev, (double)h->hm.N, h->R); h->launches++; }
     }
@@ -705,6 +773,15 @@ int32_t csmc_cycles_async(csmc_handle *h, int64_t n_cycles, int32_t orc, int32_t
     if (n_cycles < 0 || orc < 0 || mc < 0) return fail(h, CSMC_ERR_INVALID, "negative cycle counts");
     if (mc > 0) { int rc = check_metropolis(h); if (rc) return rc; }
     CK(cudaSetDevice(h->device));
+    if (n_cycles > 0 && orc + mc > 0 && use_resident(h, n_cycles * (orc + mc))) {
+        for (int64_t done = 0; done < n_cycles;) {
+            const int chunk = (int)std::min<int64_t>(n_cycles - done, 1 << 20);
+            enqueue_resident(h, chunk, orc, mc, 0, 0, nullptr, 0);
+            done += chunk;
+        }
+        CK(cudaGetLastError());
+        return CSMC_OK;
+    }
     if (h->flags & CSMC_FLAG_NO_GRAPH) {
         for (int64_t c = 0; c < n_cycles; ++c) {
             for (int s = 0; s < orc; ++s) enqueue_sweep<UPD_OR>(h);
@@ -865,15 +942,32 @@ int32_t csmc_pt_run(csmc_handle *h, const csmc_pt_params *p, int64_t sweep_begin
     rc = ensure_series(h, h->n_probes + probes); if (rc) return rc;
     PtState st = pt_state(h);
     const int nb = (h->n_slots + 127) / 128;
+    const bool resident = use_resident(h, sweep_end - sweep_begin);
+    double *mine = h->d_meas_all + (size_t)h->replica_base * 8;
+    auto gather = [&]() -> int {
+        if (h->comm) CKN(g_nccl.AllGather(mine, h->d_meas_all, (size_t)h->R * 8, ncclFloat64, h->comm, h->stream));
+        return CSMC_OK;
+    };
     int pending_or = 0;   // overrelaxation sweeps not yet enqueued (flushed as one graph replay)
     for (int64_t sweep = sweep_begin; sweep < sweep_end; ++sweep) {
         if (rate != 0) ++pending_or;                                            // :298-300
         const bool metro = (sweep % dosweep == 0);
         const bool probe = (sweep >= p->t_thermalization && sweep % p->probe_rate == 0);
-        if (metro || probe || sweep + 1 == sweep_end) { rc = enqueue_or_block(h, pending_or); if (rc) return rc; pending_or = 0; }
+        if (resident && metro) {
+            // one launch: the pending OR sweeps, the Metropolis sweep and E/M of every local replica
+            enqueue_resident(h, 1, pending_or, 1, 0, 0, mine, 1);
+            pending_or = 0;
+            rc = gather(); if (rc) return rc;
+        } else if (metro || probe || sweep + 1 == sweep_end) {
+            if (resident) { if (pending_or) enqueue_resident(h, 1, pending_or, 0, 0, 0, nullptr, 0); }
+            else { rc = enqueue_or_block(h, pending_or); if (rc) return rc; }
+            pending_or = 0;
+        }
         if (metro) {                                                            // :302-305
-            enqueue_metropolis(h, false);
-            rc = enqueue_measure_all(h, true); if (rc) return rc;
+            if (!resident) {
+                enqueue_metropolis(h, false);
+                rc = enqueue_measure_all(h, true); if (rc) return rc;
+            }
             k_pt_update<<<nb, 128, 0, h->stream>>>(st); h->launches++;
             if (h->n_slots > 1 && sweep % p->swap_rate == 0) {                  // :308-349
                 const long long k = sweep / p->swap_rate;
@@ -881,7 +975,10 @@ int32_t csmc_pt_run(csmc_handle *h, const csmc_pt_params *p, int64_t sweep_begin
             }
         }
         if (probe) {                                                            // :353,368-370
-            if (!metro) { rc = enqueue_measure_all(h, false); if (rc) return rc; }
+            if (!metro) {
+                if (resident) { enqueue_resident(h, 0, 0, 0, 0, 0, mine, 0); rc = gather(); if (rc) return rc; }
+                else { rc = enqueue_measure_all(h, false); if (rc) return rc; }
+            }
             k_pt_probe<<<nb, 128, 0, h->stream>>>(st, h->d_series_E, h->d_series_M, h->n_probes); h->launches++;
             h->n_probes++;
         }

@@ -171,7 +171,7 @@ struct Gen {
         };
         const char *nm[3] = {"p", "q", "w"};
         // phase 1 (PRELOAD): all neighbour loads up front (read-only during the pass: other colours) via ld.global.nc
-        o << "    static __device__ __forceinline__ void load(const double *__restrict__ sx, const double *__restrict__ sy, const double *__restrict__ sz,\n"
+        o << "    template <bool NC> static __device__ __forceinline__ void load(const double *__restrict__ sx, const double *__restrict__ sy, const double *__restrict__ sz,\n"
              "            int m0, int m1, int m2, double (&nb)[PRELOAD ? 3 * NNB + 1 : 1], unsigned &ok) {\n";
         if (preload)
             for (const auto &lv : live) {
@@ -182,7 +182,7 @@ struct Gen {
                 if (!hm.periodic) o << "          if (okt) {\n";
                 for (int k = 0; k < t.kind - 1; ++k) {
                     const int base = 3 * (lv.slot + k);
-                    o << "          nb[" << base << "] = __ldg(sx + j" << k << "); nb[" << base + 1 << "] = __ldg(sy + j" << k << "); nb[" << base + 2 << "] = __ldg(sz + j" << k << ");\n";
+                    o << "          nb[" << base << "] = ld<NC>(sx + j" << k << "); nb[" << base + 1 << "] = ld<NC>(sy + j" << k << "); nb[" << base + 2 << "] = ld<NC>(sz + j" << k << ");\n";
                 }
                 if (!hm.periodic) {
                     o << "          } else {\n            ok &= ~(1u << " << lv.bit << ");\n";
@@ -212,7 +212,7 @@ struct Gen {
         o << "    }\n";
         // streaming variant (many neighbours: keeping them all live would cost occupancy): gather and
         // accumulate slot by slot
-        o << "    static __device__ __forceinline__ void field_stream(const double *__restrict__ sx, const double *__restrict__ sy, const double *__restrict__ sz,\n"
+        o << "    template <bool NC> static __device__ __forceinline__ void field_stream(const double *__restrict__ sx, const double *__restrict__ sy, const double *__restrict__ sz,\n"
              "            int m0, int m1, int m2, double &a0, double &a1, double &a2, double &b0, double &b1, double &b2, double &c0, double &c1, double &c2) {\n";
         if (!preload)
             for (const auto &lv : live) {
@@ -222,7 +222,7 @@ struct Gen {
                 for (int k = 0; k < t.kind - 1; ++k) neighbour(hs, t, k);
                 if (!hm.periodic) o << "        if (okt) {\n";
                 for (int k = 0; k < t.kind - 1; ++k)
-                    o << "        const double " << nm[k] << "0 = __ldg(sx + j" << k << "), " << nm[k] << "1 = __ldg(sy + j" << k << "), " << nm[k] << "2 = __ldg(sz + j" << k << ");\n";
+                    o << "        const double " << nm[k] << "0 = ld<NC>(sx + j" << k << "), " << nm[k] << "1 = ld<NC>(sy + j" << k << "), " << nm[k] << "2 = ld<NC>(sz + j" << k << ");\n";
                 emit_accumulate(t);
                 if (!hm.periodic) o << "        }\n";
                 o << "      }\n";
@@ -303,6 +303,55 @@ struct Gen {
             o << "    double v[4] = {0.0, 0.0, 0.0, 0.0};\n    switch (blockIdx.y) {\n";
             for (int s = s0; s < s1; ++s) o << "    case " << (s - s0) << ": energy_site<Seg" << s << ">(spins, v); break;\n";
             o << "    default: break;\n    }\n    energy_block_reduce(v, partials, n_partials, partial_base);\n}\n";
+        }
+        // ---- resident kernel: one CTA per replica keeps the whole lattice in shared memory and runs
+        // whole sweep schedules (n_cycles x (or_per_cycle OR + metro_per_cycle Metropolis), then det_sweeps
+        // deterministic sweeps) with __syncthreads() between colour passes: one launch instead of
+        // 2 * colours * sweeps launches for lattices that are launch-latency bound.
+        plan.resident = (size_t)hm.npad * 24 <= 200 * 1024;
+        if (plan.resident) {
+            auto sweep_code = [&](int u, const char *ctr_extra) {
+                for (int c = 0; c < hm.n_colours; ++c) {
+                    for (int s = hm.colour_seg_begin[c]; s < hm.colour_seg_begin[c + 1]; ++s)
+                        o << "            for (int idx = threadIdx.x; idx < Seg" << s << "::COUNT; idx += blockDim.x) n_acc += resident_site<" << u << ", Seg" << s
+                          << ">(sh, idx, rep, a, " << ctr_extra << ");\n";
+                    o << "            __syncthreads();\n";
+                }
+            };
+            o << "extern \"C\" __global__ void __launch_bounds__(RES_TPB) csmc_resident(double *spins, const SweepArgs a, int n_cycles, int or_per_cycle,\n"
+                 "        int metro_per_cycle, int cone, int det_sweeps, double *meas, int write_energy) {\n";
+            o << "    extern __shared__ double sh[];\n    const int rep = blockIdx.x;\n";
+            o << "    double *g = spins + (size_t)rep * (3ull * NPAD);\n";
+            o << "    for (int i = threadIdx.x; i < 3 * NPAD; i += blockDim.x) sh[i] = g[i];\n    __syncthreads();\n";
+            o << "    int n_acc = 0;\n";
+            o << "    for (int cyc = 0; cyc < n_cycles; ++cyc) {\n";
+            o << "        for (int k = 0; k < or_per_cycle; ++k) {\n";
+            sweep_code(0, "0ULL");
+            o << "        }\n        for (int k = 0; k < metro_per_cycle; ++k) {\n";
+            o << "            const unsigned long long ce = (unsigned long long)cyc * metro_per_cycle + k;\n";
+            o << "            if (cone) {\n";
+            sweep_code(3, "ce");
+            o << "            } else {\n";
+            sweep_code(2, "ce");
+            o << "            }\n        }\n    }\n";
+            o << "    for (int k = 0; k < det_sweeps; ++k) {\n";
+            sweep_code(1, "0ULL");
+            o << "    }\n";
+            o << "    for (int i = threadIdx.x; i < 3 * NPAD; i += blockDim.x) g[i] = sh[i];\n";
+            o << "    __shared__ int sh_acc;\n    __shared__ double red[4][RES_TPB / 32];\n";
+            o << "    if (threadIdx.x == 0) sh_acc = 0;\n    __syncthreads();\n";
+            o << "    { const int w = __reduce_add_sync(0xffffffffu, n_acc); if ((threadIdx.x & 31) == 0 && w) atomicAdd(&sh_acc, w); }\n";
+            o << "    __syncthreads();\n";
+            o << "    if (threadIdx.x == 0 && sh_acc) a.accepted[(size_t)rep * ACC_STRIPE] += (unsigned long long)sh_acc;   // this CTA owns the replica\n";
+            o << "    if (meas) {\n        double v[4] = {0.0, 0.0, 0.0, 0.0};\n";
+            for (size_t s = 0; s < hm.segs.size(); ++s)
+                o << "        for (int idx = threadIdx.x; idx < Seg" << s << "::COUNT; idx += blockDim.x) energy_site_at<Seg" << s << ">(sh, idx, v);\n";
+            o << "        for (int k = 0; k < 4; ++k) { const double w = warp_sum(v[k]); if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = w; }\n";
+            o << "        __syncthreads();\n";
+            o << "        if (threadIdx.x < 4) { double t = 0.0; for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[threadIdx.x][w];\n";
+            o << "            if (threadIdx.x > 0 || write_energy) meas[(size_t)rep * 8 + threadIdx.x] = t; }\n";
+            o << "        if (threadIdx.x == 4) { unsigned long long acc = 0; for (int k = 0; k < ACC_STRIPE; ++k) acc += a.accepted[(size_t)rep * ACC_STRIPE + k];\n";
+            o << "            meas[(size_t)rep * 8 + 4] = (double)acc; }\n    }\n}\n";
         }
         return o.str();
     }

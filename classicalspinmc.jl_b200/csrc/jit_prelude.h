@@ -16,6 +16,9 @@ enum { UPD_OR = 0, UPD_DET = 1, UPD_METRO = 2, UPD_CONE = 3 };
 enum { TAG_PROPOSE = 0, TAG_ACCEPT = 1, TAG_INIT = 2, TAG_EXCHANGE = 3 };
 #define TPB 256
 #define ACC_STRIPE 32
+#define RES_TPB 256
+
+template <bool NC> __device__ __forceinline__ double ld(const double *p) { return NC ? __ldg(p) : *p; }
 
 struct SweepArgs {
     const double *beta;
@@ -82,7 +85,7 @@ struct Site {
     double nb[SEG::PRELOAD ? 3 * SEG::NNB + 1 : 1];   // neighbour spins, compile-time indexed (registers)
 };
 
-template <class SEG>
+template <class SEG, bool NC = true>
 __device__ __forceinline__ void site_load(Site<SEG> &d, const double *spins, int rep, int m0, int m1, int m2) {
     const double *sx = spins + (size_t)rep * (3ull * NPAD), *sy = sx + NPAD, *sz = sy + NPAD;
     d.valid = SEG::valid(m0, m1, m2);
@@ -91,12 +94,13 @@ __device__ __forceinline__ void site_load(Site<SEG> &d, const double *spins, int
     if (d.valid) {
         d.pos = SEG::pos(m0, m1, m2);
         d.s0 = sx[d.pos]; d.s1 = sy[d.pos]; d.s2 = sz[d.pos];
-        if (SEG::PRELOAD) SEG::load(sx, sy, sz, m0, m1, m2, d.nb, d.ok);
+        if (SEG::PRELOAD) SEG::template load<NC>(sx, sy, sz, m0, m1, m2, d.nb, d.ok);
     }
 }
 
-template <int UPD, class SEG>
-__device__ __forceinline__ bool site_finish(Site<SEG> &d, double *spins, int rep, const SweepArgs &a) {
+template <int UPD, class SEG, bool NC = true>
+__device__ __forceinline__ bool site_finish(Site<SEG> &d, double *spins, int rep, const SweepArgs &a, int grep_override = -1,
+                                            unsigned long long ctr_extra = 0ULL) {
     double *sx = spins + (size_t)rep * (3ull * NPAD), *sy = sx + NPAD, *sz = sy + NPAD;
     bool accepted = false;
     if (d.valid) {
@@ -105,15 +109,16 @@ __device__ __forceinline__ bool site_finish(Site<SEG> &d, double *spins, int rep
         double n0 = 0.0, n1 = 0.0, n2 = 0.0, u3 = 0.0;
         if (UPD == UPD_METRO || UPD == UPD_CONE) {
             // the Philox call and the proposal are independent of the loads issued in site_load
-            const unsigned long long ctr = (a.ctr_base ? *a.ctr_base : 0ULL) + a.ctr_off;
+            const unsigned long long ctr = (a.ctr_base ? *a.ctr_base : 0ULL) + a.ctr_off + ctr_extra;
             const uint32_t site = SEG::site(d.m0, d.m1, d.m2);
-            const uint32_t grep = (uint32_t)(a.replica_base + rep);
+            const int rr = grep_override >= 0 ? grep_override : rep;   // resident kernels index shared memory with rep == 0
+            const uint32_t grep = (uint32_t)(a.replica_base + rr);
             const u4 r = philox_stream(a.seed, site, grep, ctr, TAG_PROPOSE);
             double u1, u2;
             philox_to_3_uniforms(r, u1, u2, u3);
             random_orientation(SPIN_S, u1, u2, n0, n1, n2);
             if (UPD == UPD_CONE) {
-                const double sg = a.sigma[rep];
+                const double sg = a.sigma[grep_override >= 0 ? grep_override : rep];
                 n0 = s0 + sg * n0; n1 = s1 + sg * n1; n2 = s2 + sg * n2;
                 const double nrm = sqrt(n0 * n0 + n1 * n1 + n2 * n2);
                 n0 = n0 / nrm * SPIN_S; n1 = n1 / nrm * SPIN_S; n2 = n2 / nrm * SPIN_S;
@@ -128,7 +133,7 @@ __device__ __forceinline__ bool site_finish(Site<SEG> &d, double *spins, int rep
             }
         }
         if (SEG::PRELOAD) SEG::field(d.nb, d.ok, g0, g1, g2, g0, g1, g2, g0, g1, g2);
-        else SEG::field_stream(sx, sy, sz, d.m0, d.m1, d.m2, g0, g1, g2, g0, g1, g2, g0, g1, g2);
+        else SEG::template field_stream<NC>(sx, sy, sz, d.m0, d.m1, d.m2, g0, g1, g2, g0, g1, g2, g0, g1, g2);
         const double F0 = g0 - SEG::H0, F1 = g1 - SEG::H1, F2 = g2 - SEG::H2;
         if (UPD == UPD_OR) {
             if (!(F0 == 0.0 && F1 == 0.0 && F2 == 0.0)) {
@@ -149,7 +154,7 @@ __device__ __forceinline__ bool site_finish(Site<SEG> &d, double *spins, int rep
                                   s2 * (SEG::O6 * s0 + SEG::O7 * s1 + SEG::O8 * s2);
                 dE += en - eo;
             }
-            accepted = dE < 0.0 || u3 < exp(-dE * a.beta[rep]);
+            accepted = dE < 0.0 || u3 < exp(-dE * a.beta[grep_override >= 0 ? grep_override : rep]);
             if (accepted) { sx[pos] = n0; sy[pos] = n1; sz[pos] = n2; }
         }
     }
@@ -182,7 +187,7 @@ __device__ __forceinline__ void energy_site(const double *spins, double (&v)[4])
         if (SEG::PRELOAD) SEG::field(d.nb, d.ok, a0, a1, a2, b0, b1, b2, c0, c1, c2);
         else {
             const double *sx = spins + (size_t)rep * (3ull * NPAD), *sy = sx + NPAD, *sz = sy + NPAD;
-            SEG::field_stream(sx, sy, sz, m0, m1, m2, a0, a1, a2, b0, b1, b2, c0, c1, c2);
+            SEG::template field_stream<true>(sx, sy, sz, m0, m1, m2, a0, a1, a2, b0, b1, b2, c0, c1, c2);
         }
         double e = (s0 * a0 + s1 * a1 + s2 * a2) / 2 + (s0 * b0 + s1 * b1 + s2 * b2) / 3 +
                    (s0 * c0 + s1 * c1 + s2 * c2) / 4 - (s0 * SEG::H0 + s1 * SEG::H1 + s2 * SEG::H2);
@@ -191,6 +196,38 @@ __device__ __forceinline__ void energy_site(const double *spins, double (&v)[4])
                  s2 * (SEG::O6 * s0 + SEG::O7 * s1 + SEG::O8 * s2);
         v[0] = e; v[1] = s0; v[2] = s1; v[3] = s2;
     }
+}
+
+// weighted site energy (total_energy convention) from shared-memory spins, resident kernel
+template <class SEG>
+__device__ __forceinline__ void energy_site_at(const double *spins, int idx, double (&v)[4]) {
+    if (idx < SEG::COUNT) {
+        int m0, m1, m2;
+        SEG::locate(idx, m0, m1, m2);
+        Site<SEG> d;
+        site_load<SEG, false>(d, spins, 0, m0, m1, m2);
+        const double s0 = d.s0, s1 = d.s1, s2 = d.s2;
+        double a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0, c0 = 0, c1 = 0, c2 = 0;
+        if (SEG::PRELOAD) SEG::field(d.nb, d.ok, a0, a1, a2, b0, b1, b2, c0, c1, c2);
+        else SEG::template field_stream<false>(spins, spins + NPAD, spins + 2 * NPAD, m0, m1, m2, a0, a1, a2, b0, b1, b2, c0, c1, c2);
+        double e = (s0 * a0 + s1 * a1 + s2 * a2) / 2 + (s0 * b0 + s1 * b1 + s2 * b2) / 3 +
+                   (s0 * c0 + s1 * c1 + s2 * c2) / 4 - (s0 * SEG::H0 + s1 * SEG::H1 + s2 * SEG::H2);
+        if (SEG::ONSITE)
+            e += s0 * (SEG::O0 * s0 + SEG::O1 * s1 + SEG::O2 * s2) + s1 * (SEG::O3 * s0 + SEG::O4 * s1 + SEG::O5 * s2) +
+                 s2 * (SEG::O6 * s0 + SEG::O7 * s1 + SEG::O8 * s2);
+        v[0] += e; v[1] += s0; v[2] += s1; v[3] += s2;
+    }
+}
+
+// one site of a resident sweep: spins live in shared memory (plain loads), rep indexes beta/sigma/RNG
+template <int UPD, class SEG>
+__device__ __forceinline__ int resident_site(double *sh, int idx, int rep, const SweepArgs &a, unsigned long long ctr_extra) {
+    if (idx >= SEG::COUNT) return 0;
+    int m0, m1, m2;
+    SEG::locate(idx, m0, m1, m2);
+    Site<SEG> d;
+    site_load<SEG, false>(d, sh, 0, m0, m1, m2);
+    return site_finish<UPD, SEG, false>(d, sh, 0, a, rep, ctr_extra) ? 1 : 0;
 }
 
 __device__ __forceinline__ void energy_block_reduce(const double (&v)[4], double *__restrict__ partials, int n_partials, int partial_base) {

@@ -93,10 +93,14 @@ typedef struct csmc_opts {
 #define CSMC_FLAG_PDL 16          /* launch the specialised passes with programmatic dependent  \
                                      launch (griddepcontrol); measured slower on B200 for the   \
                                      BASELINE sizes, kept for A/B measurements                  */
+#define CSMC_FLAG_NO_RESIDENT 32  /* never use the resident (one CTA per replica) kernel           */
 /* Default: models whose colouring is a periodic pattern get kernels specialised for that model
  * (unrolled terms, literal coefficients, constant geometry; compiled for sm_100a with NVRTC at
  * csmc_create) when n_sites * n_replicas >= 32768; smaller problems are launch-latency bound and
- * use the ahead-of-time kernels. */
+ * use the ahead-of-time kernels for short requests; the first request of >= 32 sweeps on a lattice
+ * of <= 4096 sites builds the specialised kernels lazily and from then on runs whole sweep schedules
+ * in ONE launch on the "resident" kernel: one CTA per replica, the lattice held in shared memory,
+ * __syncthreads() between colour passes (csmc_kernel_mode == 3). */
 
 typedef struct csmc_handle csmc_handle;
 
@@ -130,7 +134,8 @@ int32_t csmc_get_colouring(const csmc_handle *h, int32_t *colour);
 /* 1 if the arithmetic-neighbour kernels are in use, 0 if the explicit-table kernels are. */
 int32_t csmc_is_structured(const csmc_handle *h, int32_t *flag);
 /* which pass kernels this handle launches: 0 explicit-table, 1 arithmetic-neighbour (both ahead of
- * time), 2 runtime-specialised for this model (NVRTC, sm_100a). */
+ * time), 2 runtime-specialised for this model (NVRTC, sm_100a), 3 runtime-specialised with the
+ * resident small-lattice kernel for sweep schedules. */
 int32_t csmc_kernel_mode(const csmc_handle *h, int32_t *mode);
 /* Host-only (no GPU needed): generate the specialised kernel source for `model` and, if
  * compile != 0, compile it with NVRTC for sm_100a.  source/log may be NULL; *_cap are buffer sizes;
