@@ -886,7 +886,7 @@ int32_t csmc_pt_init(csmc_handle *h, int32_t n_slots, const double *T_all) {
     // E = total_energy(mc.lattice) before the loop (src/monte_carlo.jl:265); acc_prev = current counters
     int rc = enqueue_measure_all(h, true); if (rc) return rc;
     PtState st = pt_state(h);
-    k_pt_update<<<(n_slots + 127) / 128, 128, 0, h->stream>>>(st); h->launches++;
+    k_pt_update<<<(n_slots + 127) / 128, 128, 0, h->stream>>>(st, 1); h->launches++;
     CK(cudaMemsetAsync(h->d_acc_slot, 0, sizeof(double) * n_slots, h->stream));
     return finish(h);
 }
@@ -943,21 +943,32 @@ int32_t csmc_pt_run(csmc_handle *h, const csmc_pt_params *p, int64_t sweep_begin
     PtState st = pt_state(h);
     const int nb = (h->n_slots + 127) / 128;
     const bool resident = use_resident(h, sweep_end - sweep_begin);
+    if (h->comm && (h->n_slots != h->R * h->n_ranks || h->replica_base != h->rank * h->R))
+        return fail(h, CSMC_ERR_INVALID, "NCCL gather needs equal replica counts per rank and replica_base == rank * n_replicas");
     double *mine = h->d_meas_all + (size_t)h->replica_base * 8;
     auto gather = [&]() -> int {
         if (h->comm) CKN(g_nccl.AllGather(mine, h->d_meas_all, (size_t)h->R * 8, ncclFloat64, h->comm, h->stream));
         return CSMC_OK;
     };
     int pending_or = 0;   // overrelaxation sweeps not yet enqueued (flushed as one graph replay)
+    // The energies are consumed only by an exchange (same sweep) or by probes before the next Metropolis
+    // sweep, so total_energy (src/monte_carlo.jl:305) is evaluated -- and gathered across GPUs -- only at
+    // Metropolis sweeps where one of the two follows; the values that are consumed are unchanged.
+    auto probe_at = [&](int64_t s) { return s >= p->t_thermalization && s % p->probe_rate == 0; };
+    auto energy_needed = [&](int64_t s) {
+        if (h->n_slots > 1 && s % p->swap_rate == 0) return true;
+        for (int64_t q = s; q < s + dosweep; ++q) if (probe_at(q)) return true;
+        return false;
+    };
     for (int64_t sweep = sweep_begin; sweep < sweep_end; ++sweep) {
         if (rate != 0) ++pending_or;                                            // :298-300
         const bool metro = (sweep % dosweep == 0);
-        const bool probe = (sweep >= p->t_thermalization && sweep % p->probe_rate == 0);
+        const bool probe = probe_at(sweep);
+        const bool meas = metro && energy_needed(sweep);
         if (resident && metro) {
-            // one launch: the pending OR sweeps, the Metropolis sweep and E/M of every local replica
-            enqueue_resident(h, 1, pending_or, 1, 0, 0, mine, 1);
+            // one launch: the pending OR sweeps, the Metropolis sweep and (if consumed) E/M of every local replica
+            enqueue_resident(h, 1, pending_or, 1, 0, 0, meas ? mine : nullptr, 1);
             pending_or = 0;
-            rc = gather(); if (rc) return rc;
         } else if (metro || probe || sweep + 1 == sweep_end) {
             if (resident) { if (pending_or) enqueue_resident(h, 1, pending_or, 0, 0, 0, nullptr, 0); }
             else { rc = enqueue_or_block(h, pending_or); if (rc) return rc; }
@@ -966,24 +977,33 @@ int32_t csmc_pt_run(csmc_handle *h, const csmc_pt_params *p, int64_t sweep_begin
         if (metro) {                                                            // :302-305
             if (!resident) {
                 enqueue_metropolis(h, false);
-                rc = enqueue_measure_all(h, true); if (rc) return rc;
+                if (meas) enqueue_measure(h, mine, true);
             }
-            k_pt_update<<<nb, 128, 0, h->stream>>>(st); h->launches++;
+            if (meas) {
+                rc = gather(); if (rc) return rc;
+                k_pt_update<<<nb, 128, 0, h->stream>>>(st, 1); h->launches++;
+            }
             if (h->n_slots > 1 && sweep % p->swap_rate == 0) {                  // :308-349
                 const long long k = sweep / p->swap_rate;
                 k_pt_exchange<<<1, 128, 0, h->stream>>>(st, (int)(k % 2), (unsigned long long)k, h->seed); h->launches++;
             }
         }
         if (probe) {                                                            // :353,368-370
-            if (!metro) {
-                if (resident) { enqueue_resident(h, 0, 0, 0, 0, 0, mine, 0); rc = gather(); if (rc) return rc; }
-                else { rc = enqueue_measure_all(h, false); if (rc) return rc; }
+            if (!metro) {   // fresh magnetisation, energy of the last Metropolis sweep
+                if (resident) enqueue_resident(h, 0, 0, 0, 0, 0, mine, 0);
+                else enqueue_measure(h, mine, false);
+                rc = gather(); if (rc) return rc;
             }
             k_pt_probe<<<nb, 128, 0, h->stream>>>(st, h->d_series_E, h->d_series_M, h->n_probes); h->launches++;
             h->n_probes++;
         }
         if ((sweep & 63) == 63) CK(cudaGetLastError());
     }
+    // attribute the Metropolis acceptance counts since the last exchange to the current slots
+    if (resident) enqueue_resident(h, 0, 0, 0, 0, 0, mine, 0);
+    else enqueue_measure(h, mine, false);
+    rc = gather(); if (rc) return rc;
+    k_pt_update<<<nb, 128, 0, h->stream>>>(st, 0); h->launches++;
     return finish(h);
 }
 
@@ -993,7 +1013,7 @@ int32_t csmc_pt_exchange(csmc_handle *h, int32_t parity, int32_t *accepted_pairs
     CK(cudaSetDevice(h->device));
     int rc = enqueue_measure_all(h, true); if (rc) return rc;
     PtState st = pt_state(h);
-    k_pt_update<<<(h->n_slots + 127) / 128, 128, 0, h->stream>>>(st); h->launches++;
+    k_pt_update<<<(h->n_slots + 127) / 128, 128, 0, h->stream>>>(st, 1); h->launches++;
     k_pt_exchange<<<1, 128, 0, h->stream>>>(st, parity & 1, (unsigned long long)(parity), h->seed); h->launches++;
     if (accepted_pairs) CK(cudaMemcpyAsync(accepted_pairs, h->d_accepted_pairs, sizeof(int) * h->n_slots, cudaMemcpyDeviceToHost, h->stream));
     return finish(h);

@@ -419,11 +419,11 @@ struct PtState {
 
 // after a Metropolis sweep + energy gather: E = total_energy (src/monte_carlo.jl:305) and
 // accepted_local += ... (:304), attributed to the slot the replica currently occupies
-__global__ void k_pt_update(PtState st) {
+__global__ void k_pt_update(PtState st, int update_energy) {
     const int rep = blockIdx.x * blockDim.x + threadIdx.x;
     if (rep >= st.n_slots) return;
     const double *mrec = st.meas_all + (size_t)rep * 8;
-    st.E_last[rep] = mrec[0];
+    if (update_energy) st.E_last[rep] = mrec[0];
     const double acc = mrec[4];
     st.acc_slot[st.slot_of_rep[rep]] += acc - st.acc_prev[rep];
     st.acc_prev[rep] = acc;
