@@ -72,7 +72,7 @@ struct csmc_handle {
     int32_t *d_nbr = nullptr, *d_ref_of_pos = nullptr;
     double *d_beta = nullptr, *d_sigma = nullptr;
     unsigned long long *d_acc = nullptr, *d_acc_prev = nullptr, *d_ctr = nullptr;
-    double *d_partials = nullptr;
+    double *d_partials = nullptr, *d_meas = nullptr;
     int n_partials = 0;
     std::vector<int> pass_blocks, partial_base;
     std::vector<PassSmall> ps;
@@ -140,7 +140,7 @@ void launch_sweep_pass(csmc_handle *h, int colour, const SweepArgs &a) {
         void *args[] = {(void *)&h->d_spins, (void *)&a};
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(h->jit_plan.tiles[colour], (UPD >= UPD_METRO ? h->jit_plan.groups_metro : h->jit_plan.groups)[colour], h->R);
-        cfg.blockDim = block;
+        cfg.blockDim = dim3(h->jit_plan.sweep_tpb);
         cfg.stream = h->stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -451,6 +451,7 @@ int32_t csmc_create(const csmc_model *model, const csmc_opts *opts, csmc_handle 
         h->n_partials += h->pass_blocks[c] * (hm.colour_seg_begin[c + 1] - hm.colour_seg_begin[c]);
     }
     CKC(dalloc(&h->d_partials, (size_t)h->R * h->n_partials * 4));
+    CKC(dalloc(&h->d_meas, (size_t)h->R * 8));
     if (h->large) h->pl.resize(hm.n_colours); else h->ps.resize(hm.n_colours);
     for (int c = 0; c < hm.n_colours; ++c) {
         std::string pe;
@@ -519,7 +520,7 @@ int32_t csmc_destroy(csmc_handle *h) {
     free_pt(h);
     cudaFree(h->d_spins); cudaFree(h->d_stage); cudaFree(h->d_out); cudaFree(h->d_nbr); cudaFree(h->d_ref_of_pos);
     cudaFree(h->d_beta); cudaFree(h->d_sigma); cudaFree(h->d_acc); cudaFree(h->d_acc_prev); cudaFree(h->d_ctr);
-    cudaFree(h->d_partials);
+    cudaFree(h->d_partials); cudaFree(h->d_meas);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return CSMC_OK;
@@ -638,14 +639,10 @@ int32_t csmc_site_energy_all(csmc_handle *h, int32_t replica, double *out) {
 
 static int measure_to_host(csmc_handle *h, std::vector<double> &rec) {
     CK(cudaSetDevice(h->device));
-    double *d_meas = nullptr;
-    CK(dalloc(&d_meas, (size_t)h->R * 8));
-    enqueue_measure(h, d_meas, true);
+    enqueue_measure(h, h->d_meas, true);
     rec.resize((size_t)h->R * 8);
-    cudaError_t e = cudaMemcpyAsync(rec.data(), d_meas, sizeof(double) * h->R * 8, cudaMemcpyDeviceToHost, h->stream);
-    int rc = e == cudaSuccess ? finish(h) : fail(h, CSMC_ERR_CUDA, cudaGetErrorString(e));
-    cudaFree(d_meas);
-    return rc;
+    CK(cudaMemcpyAsync(rec.data(), h->d_meas, sizeof(double) * h->R * 8, cudaMemcpyDeviceToHost, h->stream));
+    return finish(h);
 }
 
 int32_t csmc_total_energy(csmc_handle *h, double *E) {

@@ -129,6 +129,7 @@ struct Gen {
         static const int preload_max = std::getenv("CSMC_JIT_PRELOAD_MAX") ? std::atoi(std::getenv("CSMC_JIT_PRELOAD_MAX")) : 64;
         const bool preload = nnb <= preload_max;
         o << "    static constexpr bool PRELOAD = " << (preload ? "true" : "false") << ";\n";
+        static const bool staged = !(std::getenv("CSMC_JIT_CONTRACT") && std::string(std::getenv("CSMC_JIT_CONTRACT")) == "outer");
         auto emit_accumulate = [&](const HostTerm &t) {
             const double *C = hm.coefs.data() + t.coef;
             if (t.kind == 2) {
@@ -137,6 +138,42 @@ struct Gen {
                     for (int c = 0; c < 3; ++c)
                         if (C[3 * a + c] != 0.0) e += (e.empty() ? "" : " + ") + coef(C[3 * a + c]) + " * p" + std::to_string(c);
                     if (!e.empty()) o << "        a" << a << " += " << e << ";\n";
+                }
+            } else if (staged && t.kind == 3) {
+                // b_a += sum_b (sum_c C[a,b,c] q_c) p_b : innermost index first, few live temporaries
+                for (int a = 0; a < 3; ++a) {
+                    std::string outer;
+                    for (int bb = 0; bb < 3; ++bb) {
+                        std::string inner;
+                        for (int c = 0; c < 3; ++c)
+                            if (C[a * 9 + bb * 3 + c] != 0.0) inner += (inner.empty() ? "" : " + ") + coef(C[a * 9 + bb * 3 + c]) + " * q" + std::to_string(c);
+                        if (!inner.empty()) outer += (outer.empty() ? "" : " + ") + std::string("(") + inner + ") * p" + std::to_string(bb);
+                    }
+                    if (!outer.empty()) o << "        b" << a << " += " << outer << ";\n";
+                }
+            } else if (staged && t.kind == 4) {
+                // c_a += sum_b (sum_c (sum_d R[a,b,c,d] w_d) q_c) p_b
+                for (int a = 0; a < 3; ++a) {
+                    std::string sum_b;
+                    for (int bb = 0; bb < 3; ++bb) {
+                        std::string sum_c;
+                        for (int c = 0; c < 3; ++c) {
+                            std::string sum_d;
+                            for (int d = 0; d < 3; ++d)
+                                if (C[a * 27 + bb * 9 + c * 3 + d] != 0.0)
+                                    sum_d += (sum_d.empty() ? "" : " + ") + coef(C[a * 27 + bb * 9 + c * 3 + d]) + " * w" + std::to_string(d);
+                            if (!sum_d.empty()) sum_c += (sum_c.empty() ? "" : " + ") + std::string("(") + sum_d + ") * q" + std::to_string(c);
+                        }
+                        if (!sum_c.empty()) {
+                            o << "        { const double t" << bb << " = " << sum_c << ";";
+                            sum_b += (sum_b.empty() ? "" : " + ") + std::string("t") + std::to_string(bb) + " * p" + std::to_string(bb);
+                        } else {
+                            o << "        {";
+                        }
+                        o << "\n";
+                    }
+                    if (!sum_b.empty()) o << "        c" << a << " += " << sum_b << ";\n";
+                    o << "        }}}\n";
                 }
             } else if (t.kind == 3) {
                 for (int bb = 0; bb < 3; ++bb)
@@ -255,7 +292,10 @@ struct Gen {
             // dimensions.  Tiling is laid over the largest class extent of the colour; classes guard.
             int M[MAXD] = {1, 1, 1}, T[MAXD] = {1, 1, 1}, NT[MAXD] = {1, 1, 1};
             for (int s = s0; s < s1; ++s) for (int d = 0; d < MAXD; ++d) M[d] = std::max(M[d], hm.segs[s].M[d]);
-            int left = 256;
+            static const int sw_tpb_env = std::getenv("CSMC_JIT_TPB") ? std::atoi(std::getenv("CSMC_JIT_TPB")) : 128;
+            const int sw_tpb = (sw_tpb_env == 64 || sw_tpb_env == 128 || sw_tpb_env == 256 || sw_tpb_env == 512) ? sw_tpb_env : 128;
+            plan.sweep_tpb = sw_tpb;
+            int left = sw_tpb;
             const int last = hm.D - 1;
             T[last] = std::min(std::min(32, pow2_ceil(M[last])), left);
             if (hm.D == 3) T[last] = std::min(T[last], 16);
@@ -266,7 +306,7 @@ struct Gen {
                 if (d == 0) T[d] = left;   // always 256 threads; out-of-range threads idle
                 left /= T[d];
             }
-            if (hm.D == 1) T[0] = 256;
+            if (hm.D == 1) T[0] = sw_tpb;
             for (int d = 0; d < MAXD; ++d) NT[d] = (M[d] + T[d] - 1) / T[d];
             plan.tiles[c] = NT[0] * NT[1] * NT[2];
             // classes of the colour are fused in pairs into one thread (shared neighbour loads, ILP);
@@ -281,7 +321,7 @@ struct Gen {
                 const int ngroups = (nseg + G - 1) / G;
                 if (u == 0) plan.groups[c] = ngroups;
                 if (u == 2) plan.groups_metro.resize(hm.n_colours), plan.groups_metro[c] = ngroups;
-                o << "extern \"C\" __global__ void __launch_bounds__(TPB, " << (u >= 2 ? mb_mc : mb_or) << ") csmc_sweep_c" << c << "_u" << u << "(double *spins, const SweepArgs a) {\n";
+                o << "extern \"C\" __global__ void __launch_bounds__(" << sw_tpb << ", " << (u >= 2 ? mb_mc : mb_or) << ") csmc_sweep_c" << c << "_u" << u << "(double *spins, const SweepArgs a) {\n";
                 o << "#ifdef CSMC_PDL\n    pdl_launch_dependents();\n    pdl_wait();\n#endif\n";
                 o << "    const int rep = blockIdx.z;\n    int t = blockIdx.x;\n";
                 o << "    const int t2 = t % " << NT[2] << "; t /= " << NT[2] << "; const int t1 = t % " << NT[1] << "; const int t0 = t / " << NT[1] << ";\n";
