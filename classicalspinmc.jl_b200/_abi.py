@@ -54,7 +54,7 @@ class CsmcPtParams(C.Structure):
         ("probe_rate", C.c_int32),
         ("swap_rate", C.c_int32),
         ("overrelaxation_rate", C.c_int32),
-        ("reserved", C.c_int32),
+        ("algorithm", C.c_int32),
     ]
 
 

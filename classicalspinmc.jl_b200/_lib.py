@@ -26,6 +26,7 @@ EXPORTS = [
     "csmc_randomize_spins", "csmc_local_field", "csmc_local_field_all", "csmc_site_energy_all",
     "csmc_total_energy", "csmc_magnetization", "csmc_overrelax", "csmc_deterministic",
     "csmc_metropolis", "csmc_metropolis_cone", "csmc_anneal_temperature", "csmc_set_temperatures",
+    "csmc_set_sigma", "csmc_get_sigma",
     "csmc_cycles_async", "csmc_sync", "csmc_get_accepted", "csmc_pt_init", "csmc_comm_unique_id",
     "csmc_comm_init", "csmc_pt_run", "csmc_pt_exchange", "csmc_pt_get_slots", "csmc_pt_get_series",
     "csmc_pt_get_stats",
@@ -87,6 +88,8 @@ def lib():
     L.csmc_metropolis_cone.argtypes = [vp, vp, vp, i32, i32, vp]
     L.csmc_anneal_temperature.argtypes = [vp, vp, i64, i32, vp]
     L.csmc_set_temperatures.argtypes = [vp, vp]
+    L.csmc_set_sigma.argtypes = [vp, vp]
+    L.csmc_get_sigma.argtypes = [vp, vp]
     L.csmc_cycles_async.argtypes = [vp, i64, i32, i32]
     L.csmc_sync.argtypes = [vp]
     L.csmc_get_accepted.argtypes = [vp, vp, i32]
@@ -316,6 +319,14 @@ class Engine:
     def set_temperatures(self, T):
         self._ck(self._L.csmc_set_temperatures(self._h, _p(self._T(T))))
 
+    def set_sigma(self, sigma):
+        self._ck(self._L.csmc_set_sigma(self._h, _p(self._T(sigma))))
+
+    def get_sigma(self):
+        s = np.zeros(self.n_replicas)
+        self._ck(self._L.csmc_get_sigma(self._h, _p(s)))
+        return s
+
     def cycles_async(self, n_cycles, or_per_cycle, metro_per_cycle):
         self._ck(self._L.csmc_cycles_async(self._h, n_cycles, or_per_cycle, metro_per_cycle))
 
@@ -339,7 +350,7 @@ class Engine:
 
     def pt_run(self, params: dict, sweep_begin, sweep_end):
         p = CsmcPtParams(params["t_thermalization"], params["t_measurement"], params["probe_rate"],
-                         params["swap_rate"], params["overrelaxation_rate"], 0)
+                         params["swap_rate"], params["overrelaxation_rate"], int(params.get("algorithm", 0)))
         self._ck(self._L.csmc_pt_run(self._h, C.byref(p), sweep_begin, sweep_end))
 
     def pt_exchange(self, parity):

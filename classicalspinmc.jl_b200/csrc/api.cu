@@ -85,7 +85,7 @@ struct csmc_handle {
     int n_slots = 0;
     double *d_T_slot = nullptr, *d_meas_all = nullptr, *d_E_last = nullptr, *d_acc_prev_pt = nullptr;
     double *d_acc_slot = nullptr, *d_exch_slot = nullptr, *d_series_E = nullptr, *d_series_M = nullptr;
-    int *d_slot_of_rep = nullptr, *d_rep_of_slot = nullptr, *d_accepted_pairs = nullptr;
+    int *d_slot_of_rep = nullptr, *d_rep_of_slot = nullptr, *d_accepted_pairs = nullptr, *d_prev_rep_of_slot = nullptr;
     long long series_cap = 0, n_probes = 0;
     ncclComm_t comm = nullptr;
     int n_ranks = 1, rank = 0;
@@ -195,7 +195,7 @@ void enqueue_measure(csmc_handle *h, double *meas, bool write_energy) {
         }
         h->launches++;
     }
-    k_reduce_partials<<<h->R, 256, 0, h->stream>>>(h->d_partials, h->n_partials, h->d_acc, meas, write_energy ? 1 : 0);
+    k_reduce_partials<<<h->R, 256, 0, h->stream>>>(h->d_partials, h->n_partials, h->d_acc, h->d_sigma, meas, write_energy ? 1 : 0);
     h->launches++;
 }
 
@@ -300,9 +300,9 @@ bool use_resident(csmc_handle *h, long long sweeps_requested) {
 }
 
 // n_cycles x (orc OR + mc Metropolis sweeps) then det deterministic sweeps, optional measurement record
-void enqueue_resident(csmc_handle *h, int n_cycles, int orc, int mc, int cone, int det, double *meas, int write_energy) {
+void enqueue_resident(csmc_handle *h, int n_cycles, int orc, int mc, int cone, int det, double *meas, int write_energy, int adapt = 0) {
     SweepArgs a = sweep_args(h, h->metro_ctr, false);
-    void *args[] = {(void *)&h->d_spins, (void *)&a, (void *)&n_cycles, (void *)&orc, (void *)&mc, (void *)&cone, (void *)&det, (void *)&meas, (void *)&write_energy};
+    void *args[] = {(void *)&h->d_spins, (void *)&a, (void *)&n_cycles, (void *)&orc, (void *)&mc, (void *)&cone, (void *)&adapt, (void *)&det, (void *)&meas, (void *)&write_energy};
     const size_t smem = (size_t)3 * h->hm.npad * sizeof(double);
     cudaLaunchKernel((const void *)h->jit_resident, dim3(h->R), dim3(256), args, smem, h->stream);
     h->metro_ctr += (unsigned long long)n_cycles * mc;
@@ -338,7 +338,7 @@ PtState pt_state(csmc_handle *h) {
     st.n_slots = h->n_slots; st.n_local = h->R; st.replica_base = h->replica_base;
     st.T_slot = h->d_T_slot; st.slot_of_rep = h->d_slot_of_rep; st.rep_of_slot = h->d_rep_of_slot;
     st.meas_all = h->d_meas_all; st.E_last = h->d_E_last; st.acc_prev = h->d_acc_prev_pt;
-    st.acc_slot = h->d_acc_slot; st.exch_slot = h->d_exch_slot; st.beta_local = h->d_beta;
+    st.acc_slot = h->d_acc_slot; st.exch_slot = h->d_exch_slot; st.beta_local = h->d_beta; st.sigma_local = h->d_sigma; st.prev_rep_of_slot = h->d_prev_rep_of_slot;
     st.accepted_pairs = h->d_accepted_pairs;
     return st;
 }
@@ -346,10 +346,10 @@ PtState pt_state(csmc_handle *h) {
 void free_pt(csmc_handle *h) {
     cudaFree(h->d_T_slot); cudaFree(h->d_meas_all); cudaFree(h->d_E_last); cudaFree(h->d_acc_prev_pt);
     cudaFree(h->d_acc_slot); cudaFree(h->d_exch_slot); cudaFree(h->d_series_E); cudaFree(h->d_series_M);
-    cudaFree(h->d_slot_of_rep); cudaFree(h->d_rep_of_slot); cudaFree(h->d_accepted_pairs);
+    cudaFree(h->d_slot_of_rep); cudaFree(h->d_rep_of_slot); cudaFree(h->d_accepted_pairs); cudaFree(h->d_prev_rep_of_slot);
     h->d_T_slot = h->d_meas_all = h->d_E_last = h->d_acc_prev_pt = h->d_acc_slot = h->d_exch_slot = nullptr;
     h->d_series_E = h->d_series_M = nullptr;
-    h->d_slot_of_rep = h->d_rep_of_slot = h->d_accepted_pairs = nullptr;
+    h->d_slot_of_rep = h->d_rep_of_slot = h->d_accepted_pairs = h->d_prev_rep_of_slot = nullptr;
     h->series_cap = 0; h->n_probes = 0; h->n_slots = 0;
 }
 
@@ -685,6 +685,21 @@ int32_t csmc_set_temperatures(csmc_handle *h, const double *T) {
     return upload_T(h, T);
 }
 
+int32_t csmc_set_sigma(csmc_handle *h, const double *sigma) {
+    NEED(h); NEEDARG(h, sigma);
+    for (int r = 0; r < h->R; ++r) if (!(sigma[r] >= 0.0)) return fail(h, CSMC_ERR_INVALID, "sigma must be >= 0");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->d_sigma, sigma, sizeof(double) * h->R, cudaMemcpyHostToDevice, h->stream));
+    return finish(h);
+}
+
+int32_t csmc_get_sigma(csmc_handle *h, double *sigma) {
+    NEED(h); NEEDARG(h, sigma);
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(sigma, h->d_sigma, sizeof(double) * h->R, cudaMemcpyDeviceToHost, h->stream));
+    return finish(h);
+}
+
 int32_t csmc_get_accepted(csmc_handle *h, double *accepted, int32_t reset) {
     NEED(h); NEEDARG(h, accepted);
     CK(cudaSetDevice(h->device));
@@ -728,7 +743,7 @@ int32_t csmc_metropolis_cone(csmc_handle *h, const double *T, double *sigma, int
         CK(cudaMemcpyAsync(h->d_acc_prev, prev.data(), sizeof(unsigned long long) * h->R, cudaMemcpyHostToDevice, h->stream));
         CK(cudaStreamSynchronize(h->stream));
     }
-    if (!adapt && n_sweeps > 0 && use_resident(h, n_sweeps)) enqueue_resident(h, 1, 0, n_sweeps, 1, 0, nullptr, 0);
+    if (n_sweeps > 0 && use_resident(h, n_sweeps)) enqueue_resident(h, 1, 0, n_sweeps, 1, 0, nullptr, 0, adapt ? 1 : 0);
     else for (int s = 0; s < n_sweeps; ++s) {
         enqueue_metropolis(h, true);
         if (adapt) { k_adapt_sigma<<<(h->R + 127) / 128, 128, 0, h->stream>>>(h->d_sigma, h->d_acc, h->d_acc_prev, (double)h->hm.N, h->R); h->launches++; }
@@ -863,6 +878,7 @@ int32_t csmc_pt_init(csmc_handle *h, int32_t n_slots, const double *T_all) {
     CK(dalloc(&h->d_T_slot, n_slots)); CK(dalloc(&h->d_meas_all, (size_t)n_slots * 8)); CK(dalloc(&h->d_E_last, n_slots));
     CK(dalloc(&h->d_acc_prev_pt, n_slots)); CK(dalloc(&h->d_acc_slot, n_slots)); CK(dalloc(&h->d_exch_slot, n_slots));
     CK(dalloc(&h->d_slot_of_rep, n_slots)); CK(dalloc(&h->d_rep_of_slot, n_slots)); CK(dalloc(&h->d_accepted_pairs, n_slots));
+    CK(dalloc(&h->d_prev_rep_of_slot, n_slots));
     std::vector<int> ident(n_slots);
     for (int s = 0; s < n_slots; ++s) ident[s] = s;
     CK(cudaMemcpyAsync(h->d_T_slot, T_all, sizeof(double) * n_slots, cudaMemcpyHostToDevice, h->stream));
@@ -933,6 +949,17 @@ int32_t csmc_pt_run(csmc_handle *h, const csmc_pt_params *p, int64_t sweep_begin
     CK(cudaSetDevice(h->device));
     const int rate = p->overrelaxation_rate;
     const int dosweep = rate == 0 ? 1 : rate;                                   // src/monte_carlo.jl:289-293
+    const int alg = p->algorithm;                                               // the `alg` kwarg, :236
+    if (alg < 0 || alg > 2) return fail(h, CSMC_ERR_INVALID, "PT algorithm must be 0 (Metropolis), 1 (adaptive) or 2 (fixed cone)");
+    const int cone = alg != 0, adapt = alg == 1;
+    if (adapt) {   // per-sweep acceptance of the adaptive rule is measured against the running totals
+        std::vector<double> now(h->R);
+        rc = csmc_get_accepted(h, now.data(), 0); if (rc) return rc;
+        std::vector<unsigned long long> prev(h->R);
+        for (int r = 0; r < h->R; ++r) prev[r] = (unsigned long long)now[r] + h->acc_base[r];
+        CK(cudaMemcpyAsync(h->d_acc_prev, prev.data(), sizeof(unsigned long long) * h->R, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
     // series capacity for the probes of this chunk
     long long probes = 0;
     for (int64_t s = std::max<int64_t>(sweep_begin, p->t_thermalization); s < sweep_end; ++s) if (s % p->probe_rate == 0) ++probes;
@@ -964,7 +991,7 @@ int32_t csmc_pt_run(csmc_handle *h, const csmc_pt_params *p, int64_t sweep_begin
         const bool meas = metro && energy_needed(sweep);
         if (resident && metro) {
             // one launch: the pending OR sweeps, the Metropolis sweep and (if consumed) E/M of every local replica
-            enqueue_resident(h, 1, pending_or, 1, 0, 0, meas ? mine : nullptr, 1);
+            enqueue_resident(h, 1, pending_or, 1, cone, 0, meas ? mine : nullptr, 1, adapt);
             pending_or = 0;
         } else if (metro || probe || sweep + 1 == sweep_end) {
             if (resident) { if (pending_or) enqueue_resident(h, 1, pending_or, 0, 0, 0, nullptr, 0); }
@@ -973,7 +1000,8 @@ int32_t csmc_pt_run(csmc_handle *h, const csmc_pt_params *p, int64_t sweep_begin
         }
         if (metro) {                                                            // :302-305
             if (!resident) {
-                enqueue_metropolis(h, false);
+                enqueue_metropolis(h, cone != 0);
+                if (adapt) { k_adapt_sigma<<<(h->R + 127) / 128, 128, 0, h->stream>>>(h->d_sigma, h->d_acc, h->d_acc_prev, (double)h->hm.N, h->R); h->launches++; }
                 if (meas) enqueue_measure(h, mine, true);
             }
             if (meas) {

@@ -359,7 +359,7 @@ struct Gen {
                 }
             };
             o << "extern \"C\" __global__ void __launch_bounds__(RES_TPB) csmc_resident(double *spins, const SweepArgs a, int n_cycles, int or_per_cycle,\n"
-                 "        int metro_per_cycle, int cone, int det_sweeps, double *meas, int write_energy) {\n";
+                 "        int metro_per_cycle, int cone, int adapt, int det_sweeps, double *meas, int write_energy) {\n";
             o << "    extern __shared__ double sh[];\n    const int rep = blockIdx.x;\n";
             o << "    double *g = spins + (size_t)rep * (3ull * NPAD);\n";
             o << "    for (int i = threadIdx.x; i < 3 * NPAD; i += blockDim.x) sh[i] = g[i];\n    __syncthreads();\n";
@@ -369,8 +369,9 @@ struct Gen {
             sweep_code(0, "0ULL");
             o << "        }\n        for (int k = 0; k < metro_per_cycle; ++k) {\n";
             o << "            const unsigned long long ce = (unsigned long long)cyc * metro_per_cycle + k;\n";
-            o << "            if (cone) {\n";
+            o << "            if (cone) {\n                const int acc_before = n_acc;\n";
             sweep_code(3, "ce");
+            o << "                if (adapt) resident_adapt_sigma(n_acc - acc_before, " << (double)hm.N << ", rep, a);\n";
             o << "            } else {\n";
             sweep_code(2, "ce");
             o << "            }\n        }\n    }\n";
@@ -391,7 +392,7 @@ struct Gen {
             o << "        if (threadIdx.x < 4) { double t = 0.0; for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[threadIdx.x][w];\n";
             o << "            if (threadIdx.x > 0 || write_energy) meas[(size_t)rep * 8 + threadIdx.x] = t; }\n";
             o << "        if (threadIdx.x == 4) { unsigned long long acc = 0; for (int k = 0; k < ACC_STRIPE; ++k) acc += a.accepted[(size_t)rep * ACC_STRIPE + k];\n";
-            o << "            meas[(size_t)rep * 8 + 4] = (double)acc; }\n    }\n}\n";
+            o << "            meas[(size_t)rep * 8 + 4] = (double)acc; meas[(size_t)rep * 8 + 5] = a.sigma[rep]; }\n    }\n}\n";
         }
         return o.str();
     }

@@ -230,6 +230,23 @@ __device__ __forceinline__ int resident_site(double *sh, int idx, int rep, const
     return site_finish<UPD, SEG, false>(d, sh, 0, a, rep, ctr_extra) ? 1 : 0;
 }
 
+// resident kernel, MetropolisAdaptive (src/metropolis.jl:129-131): block-wide acceptance of the sweep
+// that just finished, then sigma <- clamp(sigma * 0.5 / max(1 - a, 0.05), 0, 100) for this replica
+__device__ __forceinline__ void resident_adapt_sigma(int n_acc_sweep, double n_sites, int rep, const SweepArgs &a) {
+    __shared__ int sh_sweep_acc;
+    if (threadIdx.x == 0) sh_sweep_acc = 0;
+    __syncthreads();
+    const int w = __reduce_add_sync(0xffffffffu, n_acc_sweep);
+    if ((threadIdx.x & 31) == 0 && w) atomicAdd(&sh_sweep_acc, w);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double acc = (double)sh_sweep_acc / n_sites, f = 0.5 / fmax(1.0 - acc, 0.05);
+        double *sig = const_cast<double *>(a.sigma);
+        sig[rep] = fmin(fmax(sig[rep] * f, 0.0), 100.0);
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ void energy_block_reduce(const double (&v)[4], double *__restrict__ partials, int n_partials, int partial_base) {
     __shared__ double sh[4][TPB / 32];
 #pragma unroll

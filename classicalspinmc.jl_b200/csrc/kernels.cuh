@@ -298,6 +298,7 @@ __global__ void __launch_bounds__(TPB) k_energy(const __grid_constant__ P p, dou
 // the 8-double measurement record {E, Mx, My, Mz, accepted, 0, 0, 0}.
 __global__ void __launch_bounds__(256) k_reduce_partials(const double *__restrict__ partials, int n_partials,
                                                          const unsigned long long *__restrict__ accepted,
+                                                         const double *__restrict__ sigma,
                                                          double *__restrict__ meas, int write_energy) {
     const int rep = blockIdx.x;
     double v[4] = {0, 0, 0, 0};
@@ -322,6 +323,7 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const double *__restric
         unsigned long long acc = 0;
         for (int k = 0; k < ACC_STRIPE; ++k) acc += accepted[(size_t)rep * ACC_STRIPE + k];
         meas[(size_t)rep * 8 + 4] = (double)acc;
+        meas[(size_t)rep * 8 + 5] = sigma[rep];   // cone width travels with the temperature slot
     }
 }
 
@@ -414,6 +416,8 @@ struct PtState {
     double *acc_prev;              // [n_slots] accepted counter at the last flush
     double *acc_slot, *exch_slot;  // [n_slots] statistics attributed to temperature slots
     double *beta_local;            // [n_local] inverse temperatures of the local replicas (kernel input)
+    double *sigma_local;           // [n_local] cone widths of the local replicas (kernel input)
+    int *prev_rep_of_slot;         // [n_slots] scratch: occupancy before the exchange step
     int *accepted_pairs;           // [n_slots] decisions of the last exchange step
 };
 
@@ -433,7 +437,7 @@ __global__ void k_pt_update(PtState st, int update_energy) {
 // accept iff u < min(1, exp((1/T_b - 1/T_a)(E_b - E_a))); on accept the two replicas trade slots
 // (temperatures move, configurations stay).  Every rank runs this redundantly on identical inputs.
 __global__ void k_pt_exchange(PtState st, int first, unsigned long long exch_ctr, unsigned long long seed) {
-    for (int k = threadIdx.x; k < st.n_slots; k += blockDim.x) st.accepted_pairs[k] = 0;
+    for (int k = threadIdx.x; k < st.n_slots; k += blockDim.x) { st.accepted_pairs[k] = 0; st.prev_rep_of_slot[k] = st.rep_of_slot[k]; }
     __syncthreads();
     for (int a = first + 2 * (int)threadIdx.x; a + 1 < st.n_slots; a += 2 * blockDim.x) {
         const int b = a + 1;
@@ -450,7 +454,13 @@ __global__ void k_pt_exchange(PtState st, int first, unsigned long long exch_ctr
         }
     }
     __syncthreads();
-    for (int r = threadIdx.x; r < st.n_local; r += blockDim.x) st.beta_local[r] = 1.0 / st.T_slot[st.slot_of_rep[st.replica_base + r]];
+    // a replica that moved to another temperature slot takes over that slot's beta and cone width
+    // (the reference keeps mc.T and mc.sigma on the rank and moves the configuration, :336-347)
+    for (int r = threadIdx.x; r < st.n_local; r += blockDim.x) {
+        const int slot = st.slot_of_rep[st.replica_base + r];
+        st.beta_local[r] = 1.0 / st.T_slot[slot];
+        st.sigma_local[r] = st.meas_all[(size_t)st.prev_rep_of_slot[slot] * 8 + 5];
+    }
 }
 
 // probe, src/monte_carlo.jl:368-370: (E, |M|) of every slot appended to the series

@@ -210,8 +210,10 @@ def parallel_tempering(mc: MonteCarlo, saveIC=(), alg=None):
     per MPI rank in the reference).  The device loop (csmc_pt_run) is chunked at checkpoint / report
     boundaries, which are the only points where the host needs the state."""
     alg = Metropolis() if alg is None else alg
-    if not (isinstance(alg, SweepAlgorithm) and alg.kind == "metropolis"):
-        raise NotImplementedError("parallel_tempering on the device supports alg=Metropolis()")
+    kinds = {"metropolis": 0, "adaptive": 1, "fixed_cone": 2}
+    if not (isinstance(alg, SweepAlgorithm) and alg.kind in kinds):
+        raise NotImplementedError("parallel_tempering on the device supports alg=Metropolis(), MetropolisAdaptive() "
+                                  "and MetropolisFixedCone()")
     p = mc.parameters
     rank, comm_size = parallel.comm_info()
     out = len(mc.outpath) > 0
@@ -229,6 +231,7 @@ def parallel_tempering(mc: MonteCarlo, saveIC=(), alg=None):
         uid = parallel.broadcast_unique_id(_lib.comm_unique_id)
         eng.comm_init(comm_size, rank, uid)
     eng.pt_init(T_all)                                                               # E = total_energy, :265
+    eng.set_sigma(mc.sigma)                                                          # mc.sigma = sigma0 on every slot
 
     saveIC = [int(s) for s in saveIC]
     path = os.path.dirname(mc.outpath)
@@ -255,6 +258,7 @@ def parallel_tempering(mc: MonteCarlo, saveIC=(), alg=None):
 
     total = p.t_thermalization + p.t_measurement                                     # :276
     params = p._asdict()
+    params["algorithm"] = kinds[alg.kind]
     stats = {"acc_prev": np.zeros(n_slots), "exch_prev": np.zeros(n_slots), "t_prev": 0}
 
     def checkpoint(sweep):
@@ -296,7 +300,10 @@ def parallel_tempering(mc: MonteCarlo, saveIC=(), alg=None):
     E, M = eng.pt_series()
     slots = eng.pt_slots()
     acc, exch = eng.pt_stats()
-    mc.statistics = {"accepted_local": acc, "exchanges": exch, "slot_of_replica": slots,
+    sig = eng.get_sigma()            # cone widths of the local replicas (they travel with the temperature slot)
+    mc.sigma_all = {int(slots[base + r]): float(sig[r]) for r in range(R)}
+    mc.sigma = mc.sigma_all.get(base, float(sig[0]))
+    mc.statistics = {"accepted_local": acc, "exchanges": exch, "slot_of_replica": slots, "sigma": mc.sigma_all,
                      "temperatures": T_all, "energy_series": E, "magnetization_series": M}
     for r in range(R):                                                               # update_observables!, :368-370
         obs = mc.observables_all[r]

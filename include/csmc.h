@@ -197,6 +197,10 @@ int32_t csmc_anneal_temperature(csmc_handle *h, const double *T, int64_t t_therm
  * metro_per_cycle Metropolis sweeps) at the current temperatures, no host sync inside.
  * The `_async` form returns after enqueueing on the handle's stream. */
 int32_t csmc_set_temperatures(csmc_handle *h, const double *T);
+/* per-replica cone width `mc.sigma` (src/metropolis.jl:24, default sigma0 = 60) used by the cone-move
+ * variants inside csmc_pt_run; csmc_get_sigma reads the (possibly adapted) values back. */
+int32_t csmc_set_sigma(csmc_handle *h, const double *sigma);
+int32_t csmc_get_sigma(csmc_handle *h, double *sigma);
 int32_t csmc_cycles_async(csmc_handle *h, int64_t n_cycles, int32_t or_per_cycle,
                           int32_t metro_per_cycle);
 int32_t csmc_sync(csmc_handle *h);
@@ -219,7 +223,7 @@ typedef struct csmc_pt_params {
     int32_t probe_rate;
     int32_t swap_rate;
     int32_t overrelaxation_rate;
-    int32_t reserved;
+    int32_t algorithm; /* the `alg` kwarg: 0 Metropolis(), 1 MetropolisAdaptive(), 2 MetropolisFixedCone() */
 } csmc_pt_params;
 
 /* Replaces the body of the `while sweep < total_sweeps` loop, src/monte_carlo.jl:295-388, for

@@ -180,7 +180,8 @@ end
 
 # --- parallel tempering (src/monte_carlo.jl:235-398) ------------------------------------------------------------
 function parallel_tempering!(mc::MonteCarlo, saveIC::Vector{Int64}=Int64[]; alg::AlgWrapper=Metropolis())
-    is_plain_metropolis(alg) || error("parallel_tempering! on the device supports alg=Metropolis()")
+    algid = alg.obj[] === metropolis! ? 0 : alg.obj[] === metropolis_adaptive! ? 1 : alg.obj[] === metropolis_fixed_cone! ? 2 :
+            error("parallel_tempering! on the device supports Metropolis(), MetropolisAdaptive() and MetropolisFixedCone()")
     p = mc.parameters
     rank, nranks = comm_rank(), comm_size()
     R = length(mc.temperatures)
@@ -195,10 +196,11 @@ function parallel_tempering!(mc::MonteCarlo, saveIC::Vector{Int64}=Int64[]; alg:
         comm_init!(e, nranks, rank, bcast_bytes(id))
     end
     pt_init!(e, T_all)
+    set_sigma!(e, fill(Float64(mc.sigma), R))
     slotfile(s) = string(mc.outdir, mc.outprefix, "_", s, ".h5")
     rank == 0 && @printf("Running sweeps on %s.\n", Dates.format(Dates.now(), "dd u yyyy HH:MM:SS"))
     total = p.t_thermalization + p.t_measurement
-    cp = CsmcPtParams(p.t_thermalization, p.t_measurement, p.probe_rate, p.swap_rate, p.overrelaxation_rate, 0)
+    cp = CsmcPtParams(p.t_thermalization, p.t_measurement, p.probe_rate, p.swap_rate, p.overrelaxation_rate, algid)
     sweep = 0
     buf = similar(mc.lattice.spins)
     while sweep < total
@@ -231,6 +233,7 @@ function parallel_tempering!(mc::MonteCarlo, saveIC::Vector{Int64}=Int64[]; alg:
             end
         end
     end
+    mc.sigma = get_sigma(e)[1]
     E, M = pt_series(e, n_slots)
     for r in 1:R, k in 1:size(E, 2)
         update_observables!(mc.observables_all[r], E[base+r, k], M[base+r, k])

@@ -39,7 +39,7 @@ struct CsmcPtParams
     probe_rate::Int32
     swap_rate::Int32
     overrelaxation_rate::Int32
-    reserved::Int32
+    algorithm::Int32      # 0 Metropolis(), 1 MetropolisAdaptive(), 2 MetropolisFixedCone()
 end
 
 "Owns a `csmc_handle*`; destroyed by the finalizer."
@@ -113,6 +113,13 @@ function anneal_temperature!(e::Engine, T::Vector{Float64}, t_thermalization::In
     check(e, ccall((:csmc_anneal_temperature, libcsmc), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Ptr{Float64}),
                    e.ptr, T, t_thermalization, rate, acc))
     return acc
+end
+
+set_sigma!(e::Engine, sigma::Vector{Float64}) = check(e, ccall((:csmc_set_sigma, libcsmc), Int32, (Ptr{Cvoid}, Ptr{Float64}), e.ptr, sigma))
+function get_sigma(e::Engine)
+    s = zeros(e.n_replicas)
+    check(e, ccall((:csmc_get_sigma, libcsmc), Int32, (Ptr{Cvoid}, Ptr{Float64}), e.ptr, s))
+    return s
 end
 
 # --- parallel tempering --------------------------------------------------------------------------------------

@@ -99,6 +99,16 @@ def test_parallel_tempering_driver_single_process(tmp_path):
     assert np.isfinite(e0) and np.allclose(np.linalg.norm(mc.lattice.spins, axis=0), 1.0, atol=1e-9)
 
 
+def test_parallel_tempering_driver_with_adaptive_alg():
+    lat = csm.Lattice((4, 4), models.kitaev_honeycomb(), 1.0, rng=np.random.default_rng(4))
+    params = {"t_thermalization": 300, "t_measurement": 600, "probe_rate": 10, "swap_rate": 10, "overrelaxation_rate": 5}
+    mc = csm.MonteCarlo(np.geomspace(0.1, 1.0, 3), lat, params, seed=5)
+    csm.parallel_tempering(mc, alg=csm.MetropolisAdaptive())
+    assert set(mc.sigma_all) == {0, 1, 2} and mc.sigma_all[0] < mc.sigma_all[2] <= 100.0
+    with pytest.raises(NotImplementedError):
+        csm.parallel_tempering(mc, alg=csm.MetropolisConstraint())
+
+
 def test_errors_cross_the_abi_as_status_codes():
     L = _lib.lib()
     md = ModelData(models.square_heisenberg(), (4, 4), 1.0)

@@ -183,6 +183,37 @@ def test_resident_kernel_parallel_tempering_matches_pass_kernels():
         assert abs(ma - mb) < 5 * math.hypot(ea, eb) + 1e-5, (ma, mb, ea, eb)
 
 
+@pytest.mark.parametrize("flags", [0, FLAG_JIT], ids=["pass-kernels", "resident"])
+def test_parallel_tempering_with_adaptive_cone_moves(flags):
+    """parallel_tempering!(mc; alg=MetropolisAdaptive()): cone widths adapt per temperature slot (small at
+    low T, saturating at the clamp at high T), travel with the slot on exchanges, and the thermal averages
+    agree with plain Metropolis PT."""
+    from classicalspinmc.jl_b200._abi import FLAG_NO_RESIDENT
+    md = ModelData(models.kitaev_honeycomb(), (4, 4), 1.0)
+    N = md.n_sites
+    Ts = np.geomspace(0.05, 1.5, 6)
+    p = dict(t_thermalization=1500, t_measurement=15000, probe_rate=5, swap_rate=10, overrelaxation_rate=5)
+    out = {}
+    for alg in (0, 1):
+        eng = _lib.Engine(md, n_replicas=6, seed=321 + alg, flags=(flags or FLAG_NO_RESIDENT))
+        eng.randomize(17 + alg)
+        eng.pt_init(Ts)
+        eng.set_sigma(60.0)
+        eng.pt_run(dict(p, algorithm=alg), 0, 16500)
+        E, _ = eng.pt_series()
+        slots = eng.pt_slots()
+        sig = eng.get_sigma()
+        out[alg] = ([binned_error(E[:, k] / N) for k in range(6)], {int(slots[r]): sig[r] for r in range(6)}, eng.pt_stats())
+    for (ma, ea), (mb, eb) in zip(out[0][0], out[1][0]):
+        assert abs(ma - mb) < 5 * math.hypot(ea, eb) + 1e-4, (ma, mb, ea, eb)
+    sigma_by_slot = out[1][1]
+    assert sigma_by_slot[0] < 2.0 < sigma_by_slot[5]            # narrow cone when cold, wide when hot
+    assert all(0.0 <= v <= 100.0 for v in sigma_by_slot.values())
+    acc_plain, acc_adapt = out[0][2][0], out[1][2][0]
+    assert acc_adapt[0] > 2 * acc_plain[0]                       # adaptive cone: far higher acceptance at low T
+    assert np.all(out[1][1 + 1][1] > 0)                          # exchanges happened
+
+
 def test_annealing_reaches_the_reference_ground_state_energy():
     """test/mctests.jl:43-50 through the host mirror: simulated_annealing! + deterministic_updates! on
     the Kitaev-Gamma honeycomb, round(E/N, digits=4) == -0.6444."""

@@ -188,5 +188,4 @@ def test_unsupported_variants_are_loud():
         csm.MonteCarlo(1.0, lat, {}, corr=True)
     mc = csm.MonteCarlo(1.0, lat, {})
     with pytest.raises(NotImplementedError):
-        csm.MetropolisConstraint().__call__.__func__  # attribute exists
-        csm.parallel_tempering(mc, alg=csm.MetropolisAdaptive())
+        csm.parallel_tempering(mc, alg=csm.MetropolisConstraintAdaptive())
