@@ -25,7 +25,7 @@ EXPORTS = [
     "csmc_kernel_mode", "csmc_jit_check", "csmc_launch_count", "csmc_get_tables", "csmc_set_spins", "csmc_get_spins",
     "csmc_randomize_spins", "csmc_local_field", "csmc_local_field_all", "csmc_site_energy_all",
     "csmc_total_energy", "csmc_magnetization", "csmc_overrelax", "csmc_deterministic",
-    "csmc_metropolis", "csmc_metropolis_cone", "csmc_anneal_temperature", "csmc_set_temperatures",
+    "csmc_metropolis", "csmc_metropolis_cone", "csmc_anneal_temperature", "csmc_anneal_temperature_cone", "csmc_set_temperatures",
     "csmc_set_sigma", "csmc_get_sigma",
     "csmc_cycles_async", "csmc_sync", "csmc_get_accepted", "csmc_pt_init", "csmc_comm_unique_id",
     "csmc_comm_init", "csmc_pt_run", "csmc_pt_exchange", "csmc_pt_get_slots", "csmc_pt_get_series",
@@ -87,6 +87,7 @@ def lib():
     L.csmc_metropolis.argtypes = [vp, vp, i32, vp]
     L.csmc_metropolis_cone.argtypes = [vp, vp, vp, i32, i32, vp]
     L.csmc_anneal_temperature.argtypes = [vp, vp, i64, i32, vp]
+    L.csmc_anneal_temperature_cone.argtypes = [vp, vp, vp, i32, i64, i32, vp]
     L.csmc_set_temperatures.argtypes = [vp, vp]
     L.csmc_set_sigma.argtypes = [vp, vp]
     L.csmc_get_sigma.argtypes = [vp, vp]
@@ -315,6 +316,13 @@ class Engine:
         self._ck(self._L.csmc_anneal_temperature(self._h, _p(self._T(T)), t_thermalization,
                                                  overrelaxation_rate, _p(acc)))
         return acc
+
+    def anneal_temperature_cone(self, T, sigma, adapt, t_thermalization, overrelaxation_rate):
+        acc = np.zeros(self.n_replicas)
+        sig = self._T(sigma).copy()
+        self._ck(self._L.csmc_anneal_temperature_cone(self._h, _p(self._T(T)), _p(sig), int(adapt), t_thermalization,
+                                                      overrelaxation_rate, _p(acc)))
+        return acc, sig
 
     def set_temperatures(self, T):
         self._ck(self._L.csmc_set_temperatures(self._h, _p(self._T(T))))

@@ -867,6 +867,53 @@ int32_t csmc_anneal_temperature(csmc_handle *h, const double *T, int64_t t_therm
     return CSMC_OK;
 }
 
+int32_t csmc_anneal_temperature_cone(csmc_handle *h, const double *T, double *sigma, int32_t adapt, int64_t t_thermalization,
+                                     int32_t rate, double *accepted) {
+    NEED(h); NEEDARG(h, T); NEEDARG(h, sigma);
+    if (rate < 0) return fail(h, CSMC_ERR_INVALID, "overrelaxation_rate must be >= 0");
+    int rc = check_metropolis(h); if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    rc = upload_T(h, T); if (rc) return rc;
+    rc = csmc_set_sigma(h, sigma); if (rc) return rc;
+    std::vector<double> before(h->R), after(h->R);
+    rc = csmc_get_accepted(h, before.data(), 0); if (rc) return rc;
+    {
+        std::vector<unsigned long long> prev(h->R);
+        for (int r = 0; r < h->R; ++r) prev[r] = (unsigned long long)before[r] + h->acc_base[r];
+        CK(cudaMemcpyAsync(h->d_acc_prev, prev.data(), sizeof(unsigned long long) * h->R, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    const int64_t iters = t_thermalization - 1;                      // src/monte_carlo.jl:169-172
+    if (iters > 0) {
+        const int orc = rate == 0 ? 0 : rate;
+        const int64_t n_cycles = rate == 0 ? iters : iters / rate;
+        const int tail = rate == 0 ? 0 : (int)(iters % rate);
+        if (use_resident(h, iters)) {
+            for (int64_t done = 0; done < n_cycles;) {
+                const int chunk = (int)std::min<int64_t>(n_cycles - done, 1 << 20);
+                enqueue_resident(h, chunk, orc, 1, 1, 0, nullptr, 0, adapt ? 1 : 0);
+                done += chunk;
+            }
+            if (tail) enqueue_resident(h, 1, tail, 0, 0, 0, nullptr, 0);
+        } else {
+            for (int64_t c = 0; c < n_cycles; ++c) {
+                rc = enqueue_or_block(h, orc); if (rc) return rc;
+                enqueue_metropolis(h, true);
+                if (adapt) { k_adapt_sigma<<<(h->R + 127) / 128, 128, 0, h->stream>>>(h->d_sigma, h->d_acc, h->d_acc_prev, (double)h->hm.N, h->R); h->launches++; }
+                if ((c & 255) == 255) CK(cudaGetLastError());
+            }
+            rc = enqueue_or_block(h, tail); if (rc) return rc;
+        }
+    }
+    rc = finish(h); if (rc) return rc;
+    rc = csmc_get_sigma(h, sigma); if (rc) return rc;
+    if (accepted) {
+        rc = csmc_get_accepted(h, after.data(), 0); if (rc) return rc;
+        for (int r = 0; r < h->R; ++r) accepted[r] = after[r] - before[r];
+    }
+    return CSMC_OK;
+}
+
 // ---- parallel tempering ----------------------------------------------------------------------------------
 int32_t csmc_pt_init(csmc_handle *h, int32_t n_slots, const double *T_all) {
     NEED(h); NEEDARG(h, T_all);

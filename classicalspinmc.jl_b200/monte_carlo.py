@@ -127,8 +127,9 @@ def _print_acceptance(T, R, accept_total):
 
 
 def simulated_annealing(mc: MonteCarlo, schedule, T0: float = 1.0, alg=None):
-    """src/monte_carlo.jl:157-190.  One device call per temperature (csmc_anneal_temperature) for the
-    plain Metropolis algorithm; other ``alg`` objects are driven sweep by sweep."""
+    """src/monte_carlo.jl:157-190.  One device call per temperature (csmc_anneal_temperature[_cone]) for
+    Metropolis(), MetropolisAdaptive() and MetropolisFixedCone(); any other callable is driven sweep by
+    sweep through the ``alg(mc, T)`` seam."""
     alg = Metropolis() if alg is None else alg
     p = mc.parameters
     T = T0
@@ -138,12 +139,15 @@ def simulated_annealing(mc: MonteCarlo, schedule, T0: float = 1.0, alg=None):
     if p.overrelaxation_rate != 0:
         accept_total /= p.overrelaxation_rate
     eng = mc._upload()
-    fused = isinstance(alg, SweepAlgorithm) and alg.kind == "metropolis"
+    kind = alg.kind if isinstance(alg, SweepAlgorithm) else None
     while T > mc.T:                                                             # :168
         R = 0.0
         mc.sigma = mc.sigma0                                                    # :171
-        if fused:
+        if kind == "metropolis":
             R = float(eng.anneal_temperature(T, p.t_thermalization, p.overrelaxation_rate)[0])
+        elif kind in ("adaptive", "fixed_cone"):
+            acc, sig = eng.anneal_temperature_cone(T, mc.sigma, kind == "adaptive", p.t_thermalization, p.overrelaxation_rate)
+            R, mc.sigma = float(acc[0]), float(sig[0])
         else:
             t = 1
             while t < p.t_thermalization:                                       # :172-182

@@ -193,6 +193,13 @@ int32_t csmc_metropolis_cone(csmc_handle *h, const double *T, double *sigma, int
 int32_t csmc_anneal_temperature(csmc_handle *h, const double *T, int64_t t_thermalization,
                                 int32_t overrelaxation_rate, double *accepted);
 
+/* Same loop with the cone-move algorithms (alg=MetropolisAdaptive() when adapt != 0, else
+ * MetropolisFixedCone()): sigma[n_replicas] is in/out (the caller resets it to sigma0 per temperature,
+ * src/monte_carlo.jl:171). */
+int32_t csmc_anneal_temperature_cone(csmc_handle *h, const double *T, double *sigma, int32_t adapt,
+                                     int64_t t_thermalization, int32_t overrelaxation_rate,
+                                     double *accepted);
+
 /* Steady-state throughput loop used by bench.py: n_cycles x (or_per_cycle overrelaxation sweeps +
  * metro_per_cycle Metropolis sweeps) at the current temperatures, no host sync inside.
  * The `_async` form returns after enqueueing on the handle's stream. */

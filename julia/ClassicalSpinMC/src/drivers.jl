@@ -144,6 +144,10 @@ function simulated_annealing!(mc::MonteCarlo, schedule::Function, T0::Float64=1.
         mc.sigma = mc.sigma0
         if is_plain_metropolis(alg)
             R = anneal_temperature!(e, fill(T, e.n_replicas), p.t_thermalization, p.overrelaxation_rate)[1]
+        elseif alg.obj[] === metropolis_adaptive! || alg.obj[] === metropolis_fixed_cone!
+            sig = fill(Float64(mc.sigma), e.n_replicas)
+            R = anneal_temperature_cone!(e, fill(T, e.n_replicas), sig, alg.obj[] === metropolis_adaptive!, p.t_thermalization, p.overrelaxation_rate)[1]
+            mc.sigma = sig[1]
         else
             for t in 1:(p.t_thermalization-1)
                 if p.overrelaxation_rate != 0

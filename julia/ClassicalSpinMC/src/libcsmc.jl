@@ -122,6 +122,13 @@ function get_sigma(e::Engine)
     return s
 end
 
+function anneal_temperature_cone!(e::Engine, T::Vector{Float64}, sigma::Vector{Float64}, adapt::Bool, t_thermalization::Integer, rate::Integer)
+    acc = zeros(e.n_replicas)
+    check(e, ccall((:csmc_anneal_temperature_cone, libcsmc), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int32, Int64, Int32, Ptr{Float64}),
+                   e.ptr, T, sigma, adapt ? 1 : 0, t_thermalization, rate, acc))
+    return acc
+end
+
 # --- parallel tempering --------------------------------------------------------------------------------------
 function comm_unique_id()
     id = zeros(UInt8, 128)
