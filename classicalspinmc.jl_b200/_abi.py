@@ -64,6 +64,7 @@ FLAG_JIT = 4
 FLAG_NO_JIT = 8
 FLAG_PDL = 16
 FLAG_NO_RESIDENT = 32
+FLAG_NO_AUTOTUNE = 64
 
 
 def resolve_field_onsite(uc):

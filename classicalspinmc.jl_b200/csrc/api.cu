@@ -96,7 +96,8 @@ struct csmc_handle {
     std::vector<cudaKernel_t> jit_sweep[4], jit_energy;
     JitPlan jit_plan;
     cudaKernel_t jit_resident = nullptr;
-    bool jit_tried = false;
+    bool jit_tried = false, jit_pdl = false;
+    float tune_ms[2] = {0.f, 0.f};   // autotune: ms per probe run without / with programmatic dependent launch
     std::string jit_note;
 
     // CUDA graph of one bench cycle
@@ -146,7 +147,7 @@ void launch_sweep_pass(csmc_handle *h, int colour, const SweepArgs &a) {
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = (h->flags & CSMC_FLAG_PDL) ? 1 : 0;
+        cfg.numAttrs = h->jit_pdl ? 1 : 0;
         cudaLaunchKernelExC(&cfg, (const void *)h->jit_sweep[UPD][colour], args);
     } else if (h->large) {
         if (h->hm.structured) k_sweep<PassLarge, true, UPD><<<grid, block, 0, h->stream>>>(h->pl[colour], a);
@@ -220,20 +221,20 @@ void enqueue_eval(csmc_handle *h, int rep, int what, double *out) {
 std::map<size_t, std::vector<char>> g_cubin_cache;   // generated source hash -> cubin (same model, many handles)
 std::mutex g_cubin_mu;
 
-std::string build_jit(csmc_handle *h) {
-    if (h->jit) return "";
-    if (h->jit_tried) return h->jit_note;
-    h->jit_tried = true;
-    const HostModel &hm = h->hm;
-    std::string err;
-    if ((h->flags & CSMC_FLAG_NO_JIT) || !hm.structured || hm.self_loop) {
-        h->jit_note = "not applicable (no periodic colouring pattern, self-interaction, or CSMC_FLAG_NO_JIT)";
-        return h->jit_note;
-    }
-    std::string log;
+struct JitModule {
+    cudaLibrary_t lib = nullptr;
+    std::vector<cudaKernel_t> sweep[4], energy;
+    cudaKernel_t resident = nullptr;
+    JitPlan plan;
+    bool pdl = false;
+};
+
+// generate + compile (or fetch from the per-process cache) + load the kernels specialised for hm
+std::string load_jit_module(const HostModel &hm, bool pdl, JitModule &m) {
+    std::string err, log;
     std::vector<char> cubin;
     try {
-        const std::string src = jit_generate_source(hm, (h->flags & CSMC_FLAG_PDL) != 0, &h->jit_plan);
+        const std::string src = jit_generate_source(hm, pdl, &m.plan);
         const size_t key = std::hash<std::string>{}(src);
         {
             std::lock_guard<std::mutex> lk(g_cubin_mu);
@@ -251,41 +252,66 @@ std::string build_jit(csmc_handle *h) {
     } catch (const std::exception &ex) {
         err = std::string("code generation failed: ") + ex.what();
     }
-    if (err.empty()) {
-        cudaError_t ce = cudaLibraryLoadData(&h->jit_lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
-        if (ce != cudaSuccess) err = std::string("cudaLibraryLoadData: ") + cudaGetErrorString(ce);
-    }
-    if (err.empty()) {
-        for (int u = 0; u < 4 && err.empty(); ++u) {
-            h->jit_sweep[u].resize(hm.n_colours);
-            for (int c = 0; c < hm.n_colours; ++c) {
-                const std::string nm = "csmc_sweep_c" + std::to_string(c) + "_u" + std::to_string(u);
-                if (cudaLibraryGetKernel(&h->jit_sweep[u][c], h->jit_lib, nm.c_str()) != cudaSuccess) { err = "kernel not found: " + nm; break; }
-            }
-        }
-        h->jit_energy.resize(hm.n_colours);
-        for (int c = 0; c < hm.n_colours && err.empty(); ++c) {
-            const std::string nm = "csmc_energy_c" + std::to_string(c);
-            if (cudaLibraryGetKernel(&h->jit_energy[c], h->jit_lib, nm.c_str()) != cudaSuccess) err = "kernel not found: " + nm;
-        }
-        if (err.empty() && h->jit_plan.resident) {
-            if (cudaLibraryGetKernel(&h->jit_resident, h->jit_lib, "csmc_resident") != cudaSuccess) err = "kernel not found: csmc_resident";
-            else {
-                const int smem = 3 * hm.npad * (int)sizeof(double);
-                if (cudaFuncSetAttribute((const void *)h->jit_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
-                    cudaGetLastError();
-                    h->jit_resident = nullptr;     // pass kernels still work
-                }
-            }
+    if (!err.empty()) return err;
+    cudaError_t ce = cudaLibraryLoadData(&m.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (ce != cudaSuccess) return std::string("cudaLibraryLoadData: ") + cudaGetErrorString(ce);
+    for (int u = 0; u < 4; ++u) {
+        m.sweep[u].resize(hm.n_colours);
+        for (int c = 0; c < hm.n_colours; ++c) {
+            const std::string nm = "csmc_sweep_c" + std::to_string(c) + "_u" + std::to_string(u);
+            if (cudaLibraryGetKernel(&m.sweep[u][c], m.lib, nm.c_str()) != cudaSuccess) return "kernel not found: " + nm;
         }
     }
-    if (err.empty()) {
-        // graphs captured with the ahead-of-time kernels must not be replayed any more
-        if (h->cycle_graph) { cudaGraphExecDestroy(h->cycle_graph); h->cycle_graph = nullptr; h->cycle_or = h->cycle_metro = -1; }
-        for (auto &kv : h->or_graphs) cudaGraphExecDestroy(kv.second);
-        h->or_graphs.clear();
-        h->jit = true;
-    } else {
+    m.energy.resize(hm.n_colours);
+    for (int c = 0; c < hm.n_colours; ++c) {
+        const std::string nm = "csmc_energy_c" + std::to_string(c);
+        if (cudaLibraryGetKernel(&m.energy[c], m.lib, nm.c_str()) != cudaSuccess) return "kernel not found: " + nm;
+    }
+    if (m.plan.resident) {
+        if (cudaLibraryGetKernel(&m.resident, m.lib, "csmc_resident") != cudaSuccess) return "kernel not found: csmc_resident";
+        const int smem = 3 * hm.npad * (int)sizeof(double);
+        if (cudaFuncSetAttribute((const void *)m.resident, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+            cudaGetLastError();
+            m.resident = nullptr;     // pass kernels still work
+        }
+    }
+    m.pdl = pdl;
+    return "";
+}
+
+void drop_graphs(csmc_handle *h) {
+    if (h->cycle_graph) { cudaGraphExecDestroy(h->cycle_graph); h->cycle_graph = nullptr; h->cycle_or = h->cycle_metro = -1; }
+    for (auto &kv : h->or_graphs) cudaGraphExecDestroy(kv.second);
+    h->or_graphs.clear();
+}
+
+void install_jit_module(csmc_handle *h, const JitModule &m) {
+    drop_graphs(h);   // graphs captured with other kernels must not be replayed any more
+    h->jit_lib = m.lib;
+    for (int u = 0; u < 4; ++u) h->jit_sweep[u] = m.sweep[u];
+    h->jit_energy = m.energy;
+    h->jit_resident = m.resident;
+    h->jit_plan = m.plan;
+    h->jit_pdl = m.pdl;
+    h->jit = true;
+}
+
+// Builds (once) the kernels specialised for this handle's model; "" on success.  On failure the
+// ahead-of-time kernels stay in use and csmc_kernel_mode reports the reason.
+std::string build_jit(csmc_handle *h) {
+    if (h->jit) return "";
+    if (h->jit_tried) return h->jit_note;
+    h->jit_tried = true;
+    const HostModel &hm = h->hm;
+    if ((h->flags & CSMC_FLAG_NO_JIT) || !hm.structured || hm.self_loop) {
+        h->jit_note = "not applicable (no periodic colouring pattern, self-interaction, or CSMC_FLAG_NO_JIT)";
+        return h->jit_note;
+    }
+    JitModule m;
+    const std::string err = load_jit_module(hm, (h->flags & CSMC_FLAG_PDL) != 0, m);
+    if (err.empty()) install_jit_module(h, m);
+    else {
+        if (m.lib) cudaLibraryUnload(m.lib);
         cudaGetLastError();
         h->jit_note = err;
     }
@@ -373,6 +399,8 @@ extern "C" {
 int32_t csmc_version(void) { return CSMC_VERSION; }
 
 const char *csmc_last_error(const csmc_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+static int autotune_pdl(csmc_handle *h);
 
 int32_t csmc_create(const csmc_model *model, const csmc_opts *opts, csmc_handle **out) {
     csmc_handle *h = nullptr;
@@ -471,6 +499,7 @@ int32_t csmc_create(const csmc_model *model, const csmc_opts *opts, csmc_handle 
     if ((h->flags & CSMC_FLAG_JIT) || (int64_t)hm.N * h->R >= 32768) {
         std::string jerr = build_jit(h);
         if (!jerr.empty() && (h->flags & CSMC_FLAG_JIT)) return bail(CSMC_ERR_UNSUPPORTED, "runtime specialisation failed: " + jerr);
+        if (jerr.empty() && (int64_t)hm.N * h->R >= 32768 && autotune_pdl(h) != CSMC_OK) return bail(CSMC_ERR_CUDA, "autotune failed: " + h->err);
     }
 #undef CKC
     *out = h;
@@ -492,6 +521,52 @@ int32_t csmc_plan(const csmc_model *model, int32_t flags, int32_t *colour, int32
     if (storage_pos) std::memcpy(storage_pos, hm.pos_of_ref.data(), sizeof(int32_t) * hm.N);
     if (n_colours) *n_colours = hm.n_colours;
     if (structured) *structured = hm.structured ? 1 : 0;
+    return CSMC_OK;
+}
+
+// Autotune (eagerly specialised handles only): programmatic dependent launch helps some models and
+// hurts others on B200 (measured: +5 % square / 3-D pyrochlore L=64, -8 % honeycomb), so both variants
+// are built and the faster one on a short probe run (5 cycles of 10 OR + 1 Metropolis on random spins)
+// is kept.  Leaves the handle in its freshly created state.
+static int autotune_pdl(csmc_handle *h) {
+    if (!h->jit || (h->flags & (CSMC_FLAG_PDL | CSMC_FLAG_NO_AUTOTUNE | CSMC_FLAG_NO_GRAPH)) || h->hm.self_loop) return CSMC_OK;
+    JitModule other;
+    if (!load_jit_module(h->hm, true, other).empty()) { if (other.lib) cudaLibraryUnload(other.lib); cudaGetLastError(); return CSMC_OK; }
+    JitModule base;
+    base.lib = h->jit_lib; for (int u = 0; u < 4; ++u) base.sweep[u] = h->jit_sweep[u];
+    base.energy = h->jit_energy; base.resident = h->jit_resident; base.plan = h->jit_plan; base.pdl = false;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const int npad = h->hm.npad;
+    dim3 grid((npad + 255) / 256, h->R);
+    k_randomize<<<grid, 256, 0, h->stream>>>(h->d_spins, h->d_ref_of_pos, npad, 3LL * npad, h->hm.S, 0x7e57ULL, h->replica_base);
+    const JitModule *mods[2] = {&base, &other};
+    for (int v = 0; v < 2; ++v) {
+        install_jit_module(h, *mods[v]);
+        float best = 1e30f;
+        int rc = csmc_cycles_async(h, 3, 10, 1); if (rc) return rc;   // builds the graph, warms up
+        for (int rep = 0; rep < 3; ++rep) {
+            CK(cudaEventRecord(e0, h->stream));
+            rc = csmc_cycles_async(h, 5, 10, 1); if (rc) return rc;
+            CK(cudaEventRecord(e1, h->stream));
+            CK(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            best = std::min(best, ms);
+        }
+        h->tune_ms[v] = best;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    const int keep = h->tune_ms[1] < 0.97f * h->tune_ms[0] ? 1 : 0;
+    install_jit_module(h, *mods[keep]);
+    cudaLibraryUnload(mods[1 - keep]->lib);
+    // back to the freshly created state
+    CK(cudaMemsetAsync(h->d_spins, 0, sizeof(double) * h->R * 3 * npad, h->stream));
+    CK(cudaMemsetAsync(h->d_acc, 0, sizeof(unsigned long long) * h->R * ACC_STRIPE, h->stream));
+    CK(cudaMemsetAsync(h->d_ctr, 0, sizeof(unsigned long long), h->stream));
+    h->metro_ctr = 0;
+    h->launches = 0;
+    CK(cudaStreamSynchronize(h->stream));
     return CSMC_OK;
 }
 

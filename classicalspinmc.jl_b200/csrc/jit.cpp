@@ -322,7 +322,7 @@ struct Gen {
                 if (u == 0) plan.groups[c] = ngroups;
                 if (u == 2) plan.groups_metro.resize(hm.n_colours), plan.groups_metro[c] = ngroups;
                 o << "extern \"C\" __global__ void __launch_bounds__(" << sw_tpb << ", " << (u >= 2 ? mb_mc : mb_or) << ") csmc_sweep_c" << c << "_u" << u << "(double *spins, const SweepArgs a) {\n";
-                o << "#ifdef CSMC_PDL\n    pdl_launch_dependents();\n    pdl_wait();\n#endif\n";
+                o << "#ifdef CSMC_PDL\n#if CSMC_PDL == 1\n    pdl_launch_dependents();\n#endif\n    pdl_wait();\n#endif\n";
                 o << "    const int rep = blockIdx.z;\n    int t = blockIdx.x;\n";
                 o << "    const int t2 = t % " << NT[2] << "; t /= " << NT[2] << "; const int t1 = t % " << NT[1] << "; const int t0 = t / " << NT[1] << ";\n";
                 o << "    const int l2 = threadIdx.x & " << (T[2] - 1) << ", l1 = (threadIdx.x >> " << ilog2(T[2]) << ") & " << (T[1] - 1)
@@ -337,7 +337,7 @@ struct Gen {
                     if (u >= 2) o << "        count_accepted(n_acc, rep, a);\n";
                     o << "    } break;\n";
                 }
-                o << "    default: break;\n    }\n}\n";
+                o << "    default: break;\n    }\n#if defined(CSMC_PDL) && CSMC_PDL == 2\n    pdl_launch_dependents();\n#endif\n}\n";
             }
             o << "extern \"C\" __global__ void __launch_bounds__(TPB) csmc_energy_c" << c << "(const double *spins, double *__restrict__ partials, int n_partials, int partial_base) {\n";
             o << "    double v[4] = {0.0, 0.0, 0.0, 0.0};\n    switch (blockIdx.y) {\n";
@@ -441,7 +441,8 @@ std::string jit_generate_source(const HostModel &hm, bool pdl, JitPlan *plan) {
     Gen g(hm);
     JitPlan local;
     std::string src = g.run(plan ? *plan : local);
-    return pdl ? "#define CSMC_PDL 1\n" + src : src;
+    const char *mode = std::getenv("CSMC_JIT_PDL_MODE");   // 1: trigger dependents at kernel start, 2: at kernel end
+    return pdl ? std::string("#define CSMC_PDL ") + (mode && mode[0] == '2' ? "2" : "1") + "\n" + src : src;
 }
 
 // returns "" on success

@@ -90,10 +90,12 @@ typedef struct csmc_opts {
 #define CSMC_FLAG_JIT 4           /* require the runtime-specialised (NVRTC) kernels: fail     \
                                      csmc_create if they cannot be built                      */
 #define CSMC_FLAG_NO_JIT 8        /* never specialise at run time (ahead-of-time kernels only) */
-#define CSMC_FLAG_PDL 16          /* launch the specialised passes with programmatic dependent  \
-                                     launch (griddepcontrol); measured slower on B200 for the   \
-                                     BASELINE sizes, kept for A/B measurements                  */
+#define CSMC_FLAG_PDL 16          /* always launch the specialised passes with programmatic      \
+                                     dependent launch (griddepcontrol); by default csmc_create    \
+                                     times both modes on the model and keeps the faster          */
 #define CSMC_FLAG_NO_RESIDENT 32  /* never use the resident (one CTA per replica) kernel           */
+#define CSMC_FLAG_NO_AUTOTUNE 64  /* skip the launch-mode autotune at csmc_create (eager path):      \
+                                     programmatic dependent launch is then off unless CSMC_FLAG_PDL */
 /* Default: models whose colouring is a periodic pattern get kernels specialised for that model
  * (unrolled terms, literal coefficients, constant geometry; compiled for sm_100a with NVRTC at
  * csmc_create) when n_sites * n_replicas >= 32768; smaller problems are launch-latency bound and
