@@ -346,6 +346,7 @@ def run_ours(args):
     if rank == 0:
         cfg.update(cycle=f"{orc_} OR + {mc_} Metropolis", cycles_per_step=args.cycles_per_step,
                    colours=n_col, kernel_mode=eng.kernel_mode, parallelism=f"replicas x{world}",
+                   launch_autotune=dict(zip(("ms_plain", "ms_pdl", "pdl_selected"), eng.autotune_report())),
                    l2="flushed between timed steps (256 MiB memset); lattice (24 MiB at L=1024) is L2-resident within a step")
         line = {"metric": "single-spin updates/sec (Metropolis+overrelax)", "value": value, "unit": "updates/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -22,7 +22,7 @@ EXPORTS = [
     "csmc_version", "csmc_last_error", "csmc_create", "csmc_destroy", "csmc_plan", "csmc_reference_tables",
     "csmc_n_sites",
     "csmc_n_replicas", "csmc_n_colours", "csmc_get_colouring", "csmc_is_structured",
-    "csmc_kernel_mode", "csmc_jit_check", "csmc_launch_count", "csmc_get_tables", "csmc_set_spins", "csmc_get_spins",
+    "csmc_kernel_mode", "csmc_autotune_report", "csmc_jit_check", "csmc_launch_count", "csmc_get_tables", "csmc_set_spins", "csmc_get_spins",
     "csmc_randomize_spins", "csmc_local_field", "csmc_local_field_all", "csmc_site_energy_all",
     "csmc_total_energy", "csmc_magnetization", "csmc_overrelax", "csmc_deterministic",
     "csmc_metropolis", "csmc_metropolis_cone", "csmc_anneal_temperature", "csmc_anneal_temperature_cone", "csmc_set_temperatures",
@@ -72,6 +72,7 @@ def lib():
     L.csmc_is_structured.argtypes = [vp, P(i32)]
     L.csmc_launch_count.argtypes = [vp, P(i64)]
     L.csmc_kernel_mode.argtypes = [vp, P(i32)]
+    L.csmc_autotune_report.argtypes = [vp, vp, P(i32)]
     L.csmc_jit_check.argtypes = [P(CsmcModel), i32, vp, i64, P(i64), vp, i64]
     L.csmc_get_tables.argtypes = [vp, vp, vp, vp]
     L.csmc_set_spins.argtypes = [vp, i32, vp]
@@ -226,6 +227,13 @@ class Engine:
         c = C.c_int32()
         self._ck(self._L.csmc_kernel_mode(self._h, C.byref(c)))
         return c.value
+
+    def autotune_report(self):
+        """(ms without PDL, ms with PDL, selected) of the launch-mode autotune at create (zeros if skipped)."""
+        ms = (C.c_float * 2)()
+        sel = C.c_int32()
+        self._ck(self._L.csmc_autotune_report(self._h, ms, C.byref(sel)))
+        return float(ms[0]), float(ms[1]), bool(sel.value)
 
     @property
     def launches(self):

@@ -615,6 +615,13 @@ int32_t csmc_kernel_mode(const csmc_handle *h, int32_t *mode) {
     return CSMC_OK;
 }
 
+int32_t csmc_autotune_report(const csmc_handle *h, float ms[2], int32_t *pdl_selected) {
+    NEED(h);
+    if (ms) { ms[0] = h->tune_ms[0]; ms[1] = h->tune_ms[1]; }
+    if (pdl_selected) *pdl_selected = h->jit_pdl ? 1 : 0;
+    return CSMC_OK;
+}
+
 int32_t csmc_jit_check(const csmc_model *model, int32_t compile, char *source, int64_t source_cap,
                        int64_t *source_len, char *log, int64_t log_cap) {
     if (!model) return fail(nullptr, CSMC_ERR_INVALID, "csmc_jit_check: NULL model");

@@ -139,6 +139,9 @@ int32_t csmc_is_structured(const csmc_handle *h, int32_t *flag);
  * time), 2 runtime-specialised for this model (NVRTC, sm_100a), 3 runtime-specialised with the
  * resident small-lattice kernel for sweep schedules. */
 int32_t csmc_kernel_mode(const csmc_handle *h, int32_t *mode);
+/* Result of the launch-mode autotune of csmc_create: ms[0] / ms[1] = time of the probe run without /
+ * with programmatic dependent launch (0 when the autotune did not run), *pdl_selected = mode in use. */
+int32_t csmc_autotune_report(const csmc_handle *h, float ms[2], int32_t *pdl_selected);
 /* Host-only (no GPU needed): generate the specialised kernel source for `model` and, if
  * compile != 0, compile it with NVRTC for sm_100a.  source/log may be NULL; *_cap are buffer sizes;
  * *source_len receives the full source length.  Used by build checks and tests. */
