@@ -15,6 +15,7 @@ from .metropolis import (Metropolis, MetropolisAdaptive, MetropolisConstraint,
                          MetropolisConstraintAdaptive, MetropolisFixedCone)
 from .monte_carlo import (MonteCarlo, MCParamsBuffer, SimulationParameters, deterministic_updates,
                           parallel_tempering, simulated_annealing)
+from .spin_correlations import compute_equal_time_correlations
 from .hdf5 import (create_params_file, overwrite_keys, read_lattice, read_spin_configuration,
                    write_MC_checkpoint)
 
@@ -26,4 +27,5 @@ __all__ = [
     "MonteCarlo", "simulated_annealing", "deterministic_updates", "parallel_tempering",
     "total_energy", "energy_density", "get_local_field",
     "Triangular", "Square", "Honeycomb", "FCC", "Pyrochlore", "BreathingPyrochlore",
+    "compute_equal_time_correlations",
 ]

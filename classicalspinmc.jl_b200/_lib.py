@@ -24,7 +24,7 @@ EXPORTS = [
     "csmc_n_replicas", "csmc_n_colours", "csmc_get_colouring", "csmc_is_structured",
     "csmc_kernel_mode", "csmc_autotune_report", "csmc_jit_check", "csmc_launch_count", "csmc_get_tables", "csmc_set_spins", "csmc_get_spins",
     "csmc_randomize_spins", "csmc_local_field", "csmc_local_field_all", "csmc_site_energy_all",
-    "csmc_total_energy", "csmc_magnetization", "csmc_overrelax", "csmc_deterministic",
+    "csmc_total_energy", "csmc_magnetization", "csmc_structure_factor", "csmc_overrelax", "csmc_deterministic",
     "csmc_metropolis", "csmc_metropolis_cone", "csmc_anneal_temperature", "csmc_anneal_temperature_cone", "csmc_set_temperatures",
     "csmc_set_sigma", "csmc_get_sigma",
     "csmc_cycles_async", "csmc_sync", "csmc_get_accepted", "csmc_pt_init", "csmc_comm_unique_id",
@@ -83,6 +83,7 @@ def lib():
     L.csmc_site_energy_all.argtypes = [vp, i32, vp]
     L.csmc_total_energy.argtypes = [vp, vp]
     L.csmc_magnetization.argtypes = [vp, vp]
+    L.csmc_structure_factor.argtypes = [vp, i32, vp, vp, vp, i64, vp]
     L.csmc_overrelax.argtypes = [vp, i32]
     L.csmc_deterministic.argtypes = [vp, i32]
     L.csmc_metropolis.argtypes = [vp, vp, i32, vp]
@@ -296,6 +297,16 @@ class Engine:
         M = np.zeros((self.n_replicas, 3))
         self._ck(self._L.csmc_magnetization(self._h, _p(M)))
         return M
+
+    def structure_factor(self, lattice_vectors, basis, ks, replica=0):
+        """lattice_vectors: sequence of D vectors a_d; basis: sequence of n_basis D-vectors; ks: (D, N_k).
+        Returns Suv (9, N_k) as compute_equal_time_correlations does."""
+        A = np.ascontiguousarray(np.stack([np.asarray(a, dtype=np.float64) for a in lattice_vectors]))   # row d = a_d == column-major D x D
+        B = np.ascontiguousarray(np.stack([np.asarray(b, dtype=np.float64) for b in basis]))
+        K = np.ascontiguousarray(np.asarray(ks, dtype=np.float64).T)                                      # (N_k, D) == column-major D x N_k
+        out = np.zeros((K.shape[0], 9))
+        self._ck(self._L.csmc_structure_factor(self._h, replica, _p(A), _p(B), _p(K), K.shape[0], _p(out)))
+        return np.ascontiguousarray(out.T)
 
     # -- sweeps -------------------------------------------------------------------------------
     def _T(self, T):

@@ -100,6 +100,11 @@ struct csmc_handle {
     float tune_ms[2] = {0.f, 0.f};   // autotune: ms per probe run without / with programmatic dependent launch
     std::string jit_note;
 
+    // equal-time structure factor
+    SsfGeom ssf{};
+    int ssf_chunks = 0;
+    double *d_ssf_theta = nullptr, *d_ssf_phib = nullptr, *d_ssf_partial = nullptr, *d_ssf_out = nullptr;
+
     // CUDA graph of one bench cycle
     cudaGraphExec_t cycle_graph = nullptr;
     int cycle_or = -1, cycle_metro = -1;
@@ -596,6 +601,7 @@ int32_t csmc_destroy(csmc_handle *h) {
     cudaFree(h->d_spins); cudaFree(h->d_stage); cudaFree(h->d_out); cudaFree(h->d_nbr); cudaFree(h->d_ref_of_pos);
     cudaFree(h->d_beta); cudaFree(h->d_sigma); cudaFree(h->d_acc); cudaFree(h->d_acc_prev); cudaFree(h->d_ctr);
     cudaFree(h->d_partials); cudaFree(h->d_meas);
+    cudaFree(h->d_ssf_theta); cudaFree(h->d_ssf_phib); cudaFree(h->d_ssf_partial); cudaFree(h->d_ssf_out);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return CSMC_OK;
@@ -994,6 +1000,69 @@ int32_t csmc_anneal_temperature_cone(csmc_handle *h, const double *T, double *si
         for (int r = 0; r < h->R; ++r) accepted[r] = after[r] - before[r];
     }
     return CSMC_OK;
+}
+
+// ---- equal-time structure factor ---------------------------------------------------------------------------
+static int ssf_prepare(csmc_handle *h, const double *lattice_vectors, const double *basis, const double *ks, int64_t n_k) {
+    const HostModel &hm = h->hm;
+    const int D = hm.D;
+    if (n_k < 1 || n_k > (1 << 24)) return fail(h, CSMC_ERR_INVALID, "n_k out of range");
+    std::vector<double> theta((size_t)n_k * MAXD, 0.0), phib((size_t)n_k * hm.n_basis, 0.0);
+    for (int64_t k = 0; k < n_k; ++k) {
+        for (int d = 0; d < D; ++d) {            // theta_d = k . a_d  (a_d = column d of lattice_vectors, D x D column-major)
+            double t = 0.0;
+            for (int c = 0; c < D; ++c) t += ks[k * D + c] * lattice_vectors[d * D + c];
+            theta[k * MAXD + d] = t;
+        }
+        for (int b = 0; b < hm.n_basis; ++b) {   // basis: n_basis x D row-major
+            double t = 0.0;
+            for (int c = 0; c < D; ++c) t += ks[k * D + c] * basis[b * D + c];
+            phib[k * hm.n_basis + b] = t;
+        }
+    }
+    cudaFree(h->d_ssf_theta); cudaFree(h->d_ssf_phib); cudaFree(h->d_ssf_partial); cudaFree(h->d_ssf_out);
+    h->d_ssf_theta = h->d_ssf_phib = h->d_ssf_partial = h->d_ssf_out = nullptr;
+    SsfGeom &g = h->ssf;
+    g.D = D; g.n_basis = hm.n_basis; g.npad = hm.npad; g.n_k = (int)n_k;
+    g.table_len = hm.n_basis;
+    for (int d = 0; d < MAXD; ++d) { g.L[d] = hm.L[d]; if (d < D) g.table_len += hm.L[d]; }
+    const size_t per_k = (size_t)g.table_len * sizeof(double2);
+    const size_t budget = 160 * 1024;
+    if (per_k > budget) return fail(h, CSMC_ERR_UNSUPPORTED, "structure factor: lattice extents too large for the shared-memory phase tables");
+    g.KT = (int)std::max<size_t>(1, std::min<size_t>(8, budget / per_k));
+    const int k_tiles = (g.n_k + g.KT - 1) / g.KT;
+    int chunks = std::max(1, (2 * 148 + k_tiles - 1) / k_tiles);
+    chunks = std::min(chunks, std::max(1, hm.npad / 2048));
+    g.chunk = ((hm.npad + chunks - 1) / chunks + 255) / 256 * 256;
+    h->ssf_chunks = (hm.npad + g.chunk - 1) / g.chunk;
+    CK(dalloc(&h->d_ssf_theta, theta.size())); CK(dalloc(&h->d_ssf_phib, phib.size()));
+    CK(dalloc(&h->d_ssf_partial, (size_t)h->ssf_chunks * n_k * 6)); CK(dalloc(&h->d_ssf_out, (size_t)n_k * 9));
+    CK(cudaMemcpyAsync(h->d_ssf_theta, theta.data(), sizeof(double) * theta.size(), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_ssf_phib, phib.data(), sizeof(double) * phib.size(), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaFuncSetAttribute(k_ssf_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(g.KT * per_k)));
+    return CSMC_OK;
+}
+
+static void ssf_enqueue(csmc_handle *h, int replica, double *out, int accumulate) {
+    const SsfGeom &g = h->ssf;
+    const int k_tiles = (g.n_k + g.KT - 1) / g.KT;
+    const size_t smem = (size_t)g.KT * g.table_len * sizeof(double2);
+    k_ssf_partial<<<dim3(k_tiles, h->ssf_chunks), 256, smem, h->stream>>>(h->d_spins + (size_t)replica * 3 * h->hm.npad, h->d_ref_of_pos,
+                                                                             h->d_ssf_theta, h->d_ssf_phib, g, h->d_ssf_partial);
+    k_ssf_finish<<<(g.n_k + 127) / 128, 128, 0, h->stream>>>(h->d_ssf_partial, h->ssf_chunks, g.n_k, 1.0 / (double)h->hm.N, out, accumulate);
+    h->launches += 2;
+}
+
+int32_t csmc_structure_factor(csmc_handle *h, int32_t replica, const double *lattice_vectors, const double *basis,
+                              const double *ks, int64_t n_k, double *Suv) {
+    NEED(h); NEEDARG(h, lattice_vectors); NEEDARG(h, basis); NEEDARG(h, ks); NEEDARG(h, Suv);
+    if (replica < 0 || replica >= h->R) return fail(h, CSMC_ERR_INVALID, "replica out of range");
+    CK(cudaSetDevice(h->device));
+    int rc = ssf_prepare(h, lattice_vectors, basis, ks, n_k); if (rc) return rc;
+    ssf_enqueue(h, replica, h->d_ssf_out, 0);
+    CK(cudaMemcpyAsync(Suv, h->d_ssf_out, sizeof(double) * 9 * n_k, cudaMemcpyDeviceToHost, h->stream));
+    return finish(h);
 }
 
 // ---- parallel tempering ----------------------------------------------------------------------------------

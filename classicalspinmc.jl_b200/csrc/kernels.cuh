@@ -394,6 +394,100 @@ __global__ void k_randomize(double *__restrict__ spins, const int32_t *__restric
 
 __global__ void k_add_u64(unsigned long long *ctr, unsigned long long v) { *ctr += v; }
 
+// ---- equal-time structure factor (src/spin_correlations.jl:6-43) ----------------------------------------
+// A_u(k) = sum_i exp(-i k.r_i) s_i^u with r_i = sum_d i_d a_d + basis_b: the phase factorises into one
+// factor per lattice dimension and one per basis site, so each CTA tabulates exp(-i i_d k.a_d) for its
+// tile of KT wavevectors in shared memory (sum_d L_d + n_basis sincos per wavevector instead of N) and
+// every (site, k) costs D complex multiplications.  Partial sums per (site chunk, k) are reduced in a
+// fixed order by k_ssf_finish (deterministic).
+struct SsfGeom {
+    int D, n_basis, L[MAXD];
+    int npad, n_k, KT, chunk;      // chunk = storage positions per blockIdx.y
+    int table_len;                 // sum_d L_d + n_basis
+};
+
+__global__ void __launch_bounds__(256) k_ssf_partial(const double *__restrict__ spins, const int32_t *__restrict__ ref_of_pos,
+                                                     const double *__restrict__ theta /* [n_k][MAXD] k.a_d */,
+                                                     const double *__restrict__ phib /* [n_k][n_basis] k.basis_b */,
+                                                     SsfGeom g, double *__restrict__ partial /* [chunks][n_k][6] */) {
+    extern __shared__ double2 tab[];          // [KT][table_len]
+    const int k0 = blockIdx.x * g.KT;
+    const int nk = min(g.KT, g.n_k - k0);
+    for (int e = threadIdx.x; e < nk * g.table_len; e += blockDim.x) {
+        const int kk = e / g.table_len, j = e % g.table_len;
+        double ang;
+        int off = 0, d = 0;
+        for (; d < g.D; ++d) { if (j < off + g.L[d]) break; off += g.L[d]; }
+        if (d < g.D) ang = -theta[(size_t)(k0 + kk) * MAXD + d] * (double)(j - off);
+        else ang = -phib[(size_t)(k0 + kk) * g.n_basis + (j - off)];
+        double sn, cs;
+        sincos(ang, &sn, &cs);
+        tab[e] = make_double2(cs, sn);
+    }
+    __syncthreads();
+    constexpr int KTMAX = 8;
+    double acc[KTMAX][6];
+#pragma unroll
+    for (int kk = 0; kk < KTMAX; ++kk)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) acc[kk][c] = 0.0;
+    const double *sx = spins, *sy = sx + g.npad, *sz = sy + g.npad;
+    const int p_begin = blockIdx.y * g.chunk, p_end = min(g.npad, p_begin + g.chunk);
+    const int off1 = g.L[0], off2 = g.L[0] + (g.D > 1 ? g.L[1] : 0), offb = off2 + (g.D > 2 ? g.L[2] : 0);
+    for (int pos = p_begin + threadIdx.x; pos < p_end; pos += blockDim.x) {
+        int ref = __ldg(ref_of_pos + pos);
+        if (ref < 0) continue;
+        int i2 = 0, i1 = 0;
+        if (g.D > 2) { i2 = ref % g.L[2]; ref /= g.L[2]; }
+        if (g.D > 1) { i1 = ref % g.L[1]; ref /= g.L[1]; }
+        const int i0 = ref % g.L[0], b = ref / g.L[0];
+        const double s0 = sx[pos], s1 = sy[pos], s2 = sz[pos];
+#pragma unroll
+        for (int kk = 0; kk < KTMAX; ++kk) {
+            if (kk < nk) {
+                const double2 *t = tab + kk * g.table_len;
+                double2 z = t[i0];
+                if (g.D > 1) { const double2 w = t[off1 + i1]; z = make_double2(z.x * w.x - z.y * w.y, z.x * w.y + z.y * w.x); }
+                if (g.D > 2) { const double2 w = t[off2 + i2]; z = make_double2(z.x * w.x - z.y * w.y, z.x * w.y + z.y * w.x); }
+                { const double2 w = t[offb + b]; z = make_double2(z.x * w.x - z.y * w.y, z.x * w.y + z.y * w.x); }
+                acc[kk][0] += z.x * s0; acc[kk][1] += z.y * s0;
+                acc[kk][2] += z.x * s1; acc[kk][3] += z.y * s1;
+                acc[kk][4] += z.x * s2; acc[kk][5] += z.y * s2;
+            }
+        }
+    }
+    __shared__ double red[8][6 * KTMAX];
+#pragma unroll
+    for (int kk = 0; kk < KTMAX; ++kk)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            const double w = warp_sum(acc[kk][c]);
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][kk * 6 + c] = w;
+        }
+    __syncthreads();
+    if (threadIdx.x < 6 * nk) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+        partial[((size_t)blockIdx.y * g.n_k + k0 + threadIdx.x / 6) * 6 + threadIdx.x % 6] = t;
+    }
+}
+
+// Suv[3u+v, k] = Re(A_u conj(A_v)) / N (src/spin_correlations.jl:31-42); out is 9 x n_k column-major;
+// accumulate != 0 adds to out (running sum for the PT loop's mean)
+__global__ void k_ssf_finish(const double *__restrict__ partial, int n_chunks, int n_k, double inv_n, double *__restrict__ out, int accumulate) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_k) return;
+    double a[6] = {0, 0, 0, 0, 0, 0};
+    for (int c = 0; c < n_chunks; ++c)
+        for (int j = 0; j < 6; ++j) a[j] += partial[((size_t)c * n_k + k) * 6 + j];
+    for (int u = 0; u < 3; ++u)
+        for (int v = 0; v < 3; ++v) {
+            const double val = (a[2 * u] * a[2 * v] + a[2 * u + 1] * a[2 * v + 1]) * inv_n;
+            double *o = out + (size_t)k * 9 + 3 * u + v;
+            *o = accumulate ? *o + val : val;
+        }
+}
+
 // MetropolisAdaptive rule after a sweep, src/metropolis.jl:129-131, per replica
 __global__ void k_adapt_sigma(double *sigma, const unsigned long long *accepted, unsigned long long *prev, double n_sites, int R) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;

@@ -175,6 +175,13 @@ int32_t csmc_total_energy(csmc_handle *h, double *E);
  * (the caller takes the norm). */
 int32_t csmc_magnetization(csmc_handle *h, double *M3);
 
+/* Replaces compute_equal_time_correlations(lat, ks), src/spin_correlations.jl:6-43:
+ * Suv[3u+v, n] = Re(A_u(k_n) conj(A_v(k_n))) / N, A_u(k) = sum_i exp(-i k.r_i) s_i^u.
+ * lattice_vectors: D x D column-major (column d = a_d, as unit_cell/lattice_vectors); basis: n_basis x D
+ * row-major; ks: D x n_k column-major (Julia Matrix{Float64}(D, N_k)); Suv: 9 x n_k column-major. */
+int32_t csmc_structure_factor(csmc_handle *h, int32_t replica, const double *lattice_vectors,
+                              const double *basis, const double *ks, int64_t n_k, double *Suv);
+
 /* ---- sweeps ------------------------------------------------------------------------------ */
 /* Replaces overrelaxation!(lattice), src/monte_carlo.jl:126-139: n_sweeps colour-ordered sweeps. */
 int32_t csmc_overrelax(csmc_handle *h, int32_t n_sweeps);

@@ -680,6 +680,24 @@ int64_t orc_parallel_tempering(const orc_lattice *L, double *spins, const double
     return n_probe;
 }
 
+/* compute_equal_time_correlations(lat, ks): src/spin_correlations.jl:6-43.  pos: D x N column-major
+   (site_positions), ks: D x N_k column-major, out: 9 x N_k column-major (Suv[3u+v, n]). */
+void orc_structure_factor(const orc_lattice *L, const double *spins, const double *pos, const double *ks, int64_t n_k, double *out) {
+    const int D = L->D;
+    for (int64_t n = 0; n < n_k; ++n) {
+        double re[3] = {0, 0, 0}, im[3] = {0, 0, 0};
+        for (int64_t i = 0; i < L->N; ++i) {
+            double kr = 0.0;
+            for (int d = 0; d < D; ++d) kr += ks[n * D + d] * pos[i * D + d];      /* transpose(ks[:, n]) * pos, :20 */
+            const double c = cos(kr), sn = -sin(kr);                                /* exp(-im * kr) */
+            for (int u = 0; u < 3; ++u) { re[u] += c * spins[3 * i + u]; im[u] += sn * spins[3 * i + u]; }   /* :21-23 */
+        }
+        for (int u = 0; u < 3; ++u)
+            for (int v = 0; v < 3; ++v)
+                out[n * 9 + 3 * u + v] = (re[u] * re[v] + im[u] * im[v]) / (double)L->N;   /* real(s_u conj(s_v)) / N, :31-42 */
+    }
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* timed CPU baseline for bench.py: n_threads independent replicas of the lattice, each running
    n_cycles x (or_per_cycle overrelaxation! sweeps + metro_per_cycle metropolis! sweeps) with the

@@ -62,6 +62,7 @@ def lib():
     L.orc_parallel_tempering.restype = C.c_int64
     L.orc_parallel_tempering.argtypes = [vp, f64p, f64p, C.c_int, C.c_int64, C.c_int64, C.c_int,
                                          C.c_int, C.c_int, C.c_uint64, C.c_int, vp, vp, vp, vp]
+    L.orc_structure_factor.argtypes = [vp, f64p, f64p, f64p, C.c_int64, f64p]
     L.orc_cycles.restype = C.c_double
     L.orc_cycles.argtypes = [vp, f64p, C.c_int, C.c_double, C.c_int64, C.c_int, C.c_int, C.c_uint64]
     L.orc_max_threads.restype = C.c_int
@@ -177,6 +178,14 @@ class OracleLattice:
         n = self._L.orc_parallel_tempering(self._h, spins, T, R, t_th, t_meas, probe_rate, swap_rate,
                                            rate, seed, n_threads, _ptr(E), _ptr(M), _ptr(acc), _ptr(exch))
         return E[:n], M[:n], acc, exch
+
+    def structure_factor(self, spins, site_positions, ks):
+        """site_positions: (D, N) and ks: (D, N_k) as in the reference; returns (9, N_k)."""
+        pos = np.ascontiguousarray(np.asarray(site_positions, dtype=np.float64).T)      # column-major D x N
+        kk = np.ascontiguousarray(np.asarray(ks, dtype=np.float64).T)
+        out = np.zeros((kk.shape[0], 9))
+        self._L.orc_structure_factor(self._h, spins, pos, kk, kk.shape[0], out)
+        return np.ascontiguousarray(out.T)
 
     def cycles(self, spins, n_threads, T, n_cycles, or_per_cycle, metro_per_cycle, seed=5):
         return self._L.orc_cycles(self._h, spins, n_threads, T, n_cycles, or_per_cycle, metro_per_cycle, seed)

@@ -117,6 +117,30 @@ def test_parallel_tempering_driver_with_adaptive_alg():
         csm.parallel_tempering(mc, alg=csm.MetropolisConstraint())
 
 
+@pytest.mark.parametrize("case", ["honeycomb", "pyrochlore", "chain"])
+def test_structure_factor_matches_reference_formula(case):
+    """compute_equal_time_correlations (src/spin_correlations.jl:6-43) vs the oracle's literal restatement."""
+    from oracle import oracle as orc
+    rng = np.random.default_rng(3)
+    if case == "honeycomb":
+        uc, shape = models.kitaev_honeycomb(), (6, 5)
+    elif case == "pyrochlore":
+        uc, shape = models.pyrochlore_local(), (3, 4, 2)
+    else:
+        uc, shape = models.chain_heisenberg(), (37,)
+    lat = csm.Lattice(shape, uc, 1.0, rng=rng)
+    ks = rng.uniform(-2 * np.pi, 2 * np.pi, size=(uc.D, 23))
+    ks[:, 0] = 0.0
+    S = csm.compute_equal_time_correlations(lat, ks)
+    o = orc.OracleLattice(lat._model)
+    S_ref = o.structure_factor(np.ascontiguousarray(lat.spins.T), lat.site_positions, ks)
+    assert S.shape == S_ref.shape == (9, 23)
+    assert np.abs(S - S_ref).max() <= 1e-10 * np.abs(S_ref).max()
+    # k = 0: S^{uv}(0) = M_u M_v / N
+    M = lat.spins.sum(axis=1)
+    assert np.allclose(S[:, 0].reshape(3, 3), np.outer(M, M) / lat.size, rtol=1e-12, atol=1e-12)
+
+
 def test_errors_cross_the_abi_as_status_codes():
     L = _lib.lib()
     md = ModelData(models.square_heisenberg(), (4, 4), 1.0)
