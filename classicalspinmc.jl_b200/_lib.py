@@ -29,7 +29,7 @@ EXPORTS = [
     "csmc_set_sigma", "csmc_get_sigma",
     "csmc_cycles_async", "csmc_sync", "csmc_get_accepted", "csmc_pt_init", "csmc_comm_unique_id",
     "csmc_comm_init", "csmc_pt_run", "csmc_pt_exchange", "csmc_pt_get_slots", "csmc_pt_get_series",
-    "csmc_pt_get_stats",
+    "csmc_pt_get_stats", "csmc_pt_set_momenta", "csmc_pt_get_ssf",
 ]
 
 
@@ -104,6 +104,8 @@ def lib():
     L.csmc_pt_get_slots.argtypes = [vp, vp]
     L.csmc_pt_get_series.argtypes = [vp, P(i64), vp, vp]
     L.csmc_pt_get_stats.argtypes = [vp, vp, vp]
+    L.csmc_pt_set_momenta.argtypes = [vp, vp, vp, vp, i64]
+    L.csmc_pt_get_ssf.argtypes = [vp, vp, P(i64)]
     for name in EXPORTS:
         if name not in ("csmc_last_error",):
             getattr(L, name).restype = i32
@@ -398,6 +400,20 @@ class Engine:
         n = C.c_int64(cnt)
         self._ck(self._L.csmc_pt_get_series(self._h, C.byref(n), _p(E), _p(M)))
         return E, M
+
+    def pt_set_momenta(self, lattice_vectors, basis, ks):
+        A = np.ascontiguousarray(np.stack([np.asarray(a, dtype=np.float64) for a in lattice_vectors]))
+        B = np.ascontiguousarray(np.stack([np.asarray(b, dtype=np.float64) for b in basis]))
+        K = np.ascontiguousarray(np.asarray(ks, dtype=np.float64).T)
+        self._n_k = K.shape[0]
+        self._ck(self._L.csmc_pt_set_momenta(self._h, _p(A), _p(B), _p(K), K.shape[0]))
+
+    def pt_ssf(self):
+        """(sums[n_slots, 9, n_k], n_probes): this rank's per-slot structure-factor sums."""
+        sums = np.zeros((self.n_slots, self._n_k, 9))
+        n = C.c_int64(0)
+        self._ck(self._L.csmc_pt_get_ssf(self._h, _p(sums), C.byref(n)))
+        return np.ascontiguousarray(np.transpose(sums, (0, 2, 1))), n.value
 
     def pt_stats(self):
         a = np.zeros(self.n_slots); e = np.zeros(self.n_slots)

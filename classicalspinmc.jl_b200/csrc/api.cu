@@ -103,7 +103,8 @@ struct csmc_handle {
     // equal-time structure factor
     SsfGeom ssf{};
     int ssf_chunks = 0;
-    double *d_ssf_theta = nullptr, *d_ssf_phib = nullptr, *d_ssf_partial = nullptr, *d_ssf_out = nullptr;
+    double *d_ssf_theta = nullptr, *d_ssf_phib = nullptr, *d_ssf_partial = nullptr, *d_ssf_out = nullptr, *d_ssf_sum = nullptr;
+    long long ssf_probes = 0;
 
     // CUDA graph of one bench cycle
     cudaGraphExec_t cycle_graph = nullptr;
@@ -382,6 +383,7 @@ void free_pt(csmc_handle *h) {
     h->d_series_E = h->d_series_M = nullptr;
     h->d_slot_of_rep = h->d_rep_of_slot = h->d_accepted_pairs = h->d_prev_rep_of_slot = nullptr;
     h->series_cap = 0; h->n_probes = 0; h->n_slots = 0;
+    cudaFree(h->d_ssf_sum); h->d_ssf_sum = nullptr; h->ssf_probes = 0;
 }
 
 // measurement + gather across ranks into d_meas_all (in place)
@@ -601,7 +603,7 @@ int32_t csmc_destroy(csmc_handle *h) {
     cudaFree(h->d_spins); cudaFree(h->d_stage); cudaFree(h->d_out); cudaFree(h->d_nbr); cudaFree(h->d_ref_of_pos);
     cudaFree(h->d_beta); cudaFree(h->d_sigma); cudaFree(h->d_acc); cudaFree(h->d_acc_prev); cudaFree(h->d_ctr);
     cudaFree(h->d_partials); cudaFree(h->d_meas);
-    cudaFree(h->d_ssf_theta); cudaFree(h->d_ssf_phib); cudaFree(h->d_ssf_partial); cudaFree(h->d_ssf_out);
+    cudaFree(h->d_ssf_theta); cudaFree(h->d_ssf_phib); cudaFree(h->d_ssf_partial); cudaFree(h->d_ssf_out); cudaFree(h->d_ssf_sum);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return CSMC_OK;
@@ -1044,13 +1046,14 @@ static int ssf_prepare(csmc_handle *h, const double *lattice_vectors, const doub
     return CSMC_OK;
 }
 
-static void ssf_enqueue(csmc_handle *h, int replica, double *out, int accumulate) {
+static void ssf_enqueue(csmc_handle *h, int replica, double *out, int accumulate, const int *slot_of_rep = nullptr) {
     const SsfGeom &g = h->ssf;
     const int k_tiles = (g.n_k + g.KT - 1) / g.KT;
     const size_t smem = (size_t)g.KT * g.table_len * sizeof(double2);
     k_ssf_partial<<<dim3(k_tiles, h->ssf_chunks), 256, smem, h->stream>>>(h->d_spins + (size_t)replica * 3 * h->hm.npad, h->d_ref_of_pos,
                                                                              h->d_ssf_theta, h->d_ssf_phib, g, h->d_ssf_partial);
-    k_ssf_finish<<<(g.n_k + 127) / 128, 128, 0, h->stream>>>(h->d_ssf_partial, h->ssf_chunks, g.n_k, 1.0 / (double)h->hm.N, out, accumulate);
+    k_ssf_finish<<<(g.n_k + 127) / 128, 128, 0, h->stream>>>(h->d_ssf_partial, h->ssf_chunks, g.n_k, 1.0 / (double)h->hm.N, out, accumulate,
+                                                              slot_of_rep, h->replica_base + replica);
     h->launches += 2;
 }
 
@@ -1058,10 +1061,32 @@ int32_t csmc_structure_factor(csmc_handle *h, int32_t replica, const double *lat
                               const double *ks, int64_t n_k, double *Suv) {
     NEED(h); NEEDARG(h, lattice_vectors); NEEDARG(h, basis); NEEDARG(h, ks); NEEDARG(h, Suv);
     if (replica < 0 || replica >= h->R) return fail(h, CSMC_ERR_INVALID, "replica out of range");
+    if (h->d_ssf_sum) return fail(h, CSMC_ERR_INVALID, "momenta of a running parallel-tempering measurement are attached (csmc_pt_set_momenta)");
     CK(cudaSetDevice(h->device));
     int rc = ssf_prepare(h, lattice_vectors, basis, ks, n_k); if (rc) return rc;
     ssf_enqueue(h, replica, h->d_ssf_out, 0);
     CK(cudaMemcpyAsync(Suv, h->d_ssf_out, sizeof(double) * 9 * n_k, cudaMemcpyDeviceToHost, h->stream));
+    return finish(h);
+}
+
+int32_t csmc_pt_set_momenta(csmc_handle *h, const double *lattice_vectors, const double *basis, const double *ks, int64_t n_k) {
+    NEED(h); NEEDARG(h, lattice_vectors); NEEDARG(h, basis); NEEDARG(h, ks);
+    if (h->n_slots == 0) return fail(h, CSMC_ERR_INVALID, "csmc_pt_init has not been called");
+    CK(cudaSetDevice(h->device));
+    int rc = ssf_prepare(h, lattice_vectors, basis, ks, n_k); if (rc) return rc;
+    cudaFree(h->d_ssf_sum); h->d_ssf_sum = nullptr;
+    CK(dalloc(&h->d_ssf_sum, (size_t)h->n_slots * 9 * n_k));
+    CK(cudaMemsetAsync(h->d_ssf_sum, 0, sizeof(double) * h->n_slots * 9 * n_k, h->stream));
+    h->ssf_probes = 0;
+    return finish(h);
+}
+
+int32_t csmc_pt_get_ssf(csmc_handle *h, double *sums, int64_t *n_probes) {
+    NEED(h); NEEDARG(h, sums);
+    if (!h->d_ssf_sum) return fail(h, CSMC_ERR_INVALID, "csmc_pt_set_momenta has not been called");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(sums, h->d_ssf_sum, sizeof(double) * h->n_slots * 9 * h->ssf.n_k, cudaMemcpyDeviceToHost, h->stream));
+    if (n_probes) *n_probes = h->ssf_probes;
     return finish(h);
 }
 
@@ -1219,6 +1244,10 @@ int32_t csmc_pt_run(csmc_handle *h, const csmc_pt_params *p, int64_t sweep_begin
             }
             k_pt_probe<<<nb, 128, 0, h->stream>>>(st, h->d_series_E, h->d_series_M, h->n_probes); h->launches++;
             h->n_probes++;
+            if (h->d_ssf_sum) {   // mc.corr: structure factor of every local replica, summed per temperature slot (:371-375)
+                for (int r = 0; r < h->R; ++r) ssf_enqueue(h, r, h->d_ssf_sum, 1, h->d_slot_of_rep);
+                h->ssf_probes++;
+            }
         }
         if ((sweep & 63) == 63) CK(cudaGetLastError());
     }

@@ -474,9 +474,12 @@ __global__ void __launch_bounds__(256) k_ssf_partial(const double *__restrict__ 
 
 // Suv[3u+v, k] = Re(A_u conj(A_v)) / N (src/spin_correlations.jl:31-42); out is 9 x n_k column-major;
 // accumulate != 0 adds to out (running sum for the PT loop's mean)
-__global__ void k_ssf_finish(const double *__restrict__ partial, int n_chunks, int n_k, double inv_n, double *__restrict__ out, int accumulate) {
+// slot_of_rep != nullptr: out is the per-temperature-slot accumulator block of the replica's current slot
+__global__ void k_ssf_finish(const double *__restrict__ partial, int n_chunks, int n_k, double inv_n, double *__restrict__ out, int accumulate,
+                             const int *__restrict__ slot_of_rep, int rep_global) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_k) return;
+    if (slot_of_rep) out += (size_t)slot_of_rep[rep_global] * 9 * n_k;
     double a[6] = {0, 0, 0, 0, 0, 0};
     for (int c = 0; c < n_chunks; ++c)
         for (int j = 0; j < 6; ++j) a[j] += partial[((size_t)c * n_k + k) * 6 + j];

@@ -52,8 +52,11 @@ class MonteCarlo:
                  outpath: str = "", outprefix: str = "configuration", inparams: dict | None = None,
                  overwrite: bool = True, sigma0: float = 60, corr: bool = False, ks=None, seed: int | None = None,
                  device: int | None = None):
-        if corr:
-            raise NotImplementedError("equal-time structure factor (corr=true) is out of scope (SURVEY.md 8f)")
+        ks = None if ks is None else np.asarray(ks, dtype=np.float64)
+        if corr and (ks is None or ks.size == 0):
+            raise ValueError("No momentum vectors provided for correlation calculations!")        # src/monte_carlo.jl:64-65
+        if not corr and ks is not None and ks.size != 0:
+            warnings.warn("Momentum vectors provided but correlation calculations not requested!")  # :66-67
         self.temperatures = np.atleast_1d(np.asarray(T, dtype=np.float64)).copy()
         self.T = float(self.temperatures[0])
         self.observables = Observables(0)
@@ -236,6 +239,8 @@ def parallel_tempering(mc: MonteCarlo, saveIC=(), alg=None):
         eng.comm_init(comm_size, rank, uid)
     eng.pt_init(T_all)                                                               # E = total_energy, :265
     eng.set_sigma(mc.sigma)                                                          # mc.sigma = sigma0 on every slot
+    if mc.corr:                                                                      # :371-375
+        eng.pt_set_momenta(mc.lattice.unit_cell.lattice_vectors, mc.lattice.unit_cell.basis, mc.momentum_vectors)
 
     saveIC = [int(s) for s in saveIC]
     path = os.path.dirname(mc.outpath)
@@ -314,6 +319,11 @@ def parallel_tempering(mc: MonteCarlo, saveIC=(), alg=None):
         for k in range(E.shape[0]):
             obs.energy.push(E[k, base + r], E[k, base + r] ** 2)
             obs.magnetization.push(M[k, base + r], M[k, base + r] ** 2)
+    if mc.corr:   # mean(SSF) per temperature slot: sum the ranks' contributions, divide by the probe count
+        sums, n_ssf = eng.pt_ssf()
+        total = sum(parallel.allgather_objects(sums))
+        for r in range(R):
+            mc.observables_all[r].correlations = total[base + r] / max(n_ssf, 1)
     # configurations by slot: the reference leaves in mc.lattice.spins the configuration that sits at
     # temperature mc.T at the end (it swapped configurations between ranks, :336-347)
     local_cfg = [np.asfortranarray(eng.get_spins(replica=r).T) for r in range(R)]
@@ -328,6 +338,11 @@ def parallel_tempering(mc: MonteCarlo, saveIC=(), alg=None):
         for r in range(R):
             h5.write_final_observables(mc, outpath=slot_paths(base + r), spins=mc.replica_spins[r],
                                        observables=mc.observables_all[r], T=T_all[base + r])
+            if mc.corr:                                                              # src/hdf5.jl:229-236
+                f = h5._open(slot_paths(base + r), "r+")
+                h5.overwrite_keys(f, {"spin_correlations/SSF": mc.observables_all[r].correlations,
+                                      "spin_correlations/SSF_momentum": mc.momentum_vectors})
+                f.close()
     if rank == 0:
         print("Simulation finished on %s." % datetime.datetime.now().strftime("%d %b %Y %H:%M:%S"))   # :396
     return

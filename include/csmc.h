@@ -252,6 +252,13 @@ typedef struct csmc_pt_params {
  * sweep >= t_thermalization and sweep % probe_rate == 0 (:353,368-370). */
 int32_t csmc_pt_run(csmc_handle *h, const csmc_pt_params *p, int64_t sweep_begin,
                     int64_t sweep_end);
+/* mc.corr = true (src/monte_carlo.jl:371-375, src/observables.jl:27-30): from now on every probe also
+ * computes the equal-time structure factor of each local replica at the given momenta and adds it to
+ * the accumulator of the replica's current temperature slot.  csmc_pt_get_ssf returns the per-slot sums
+ * [n_slots x n_k x 9] (this rank's contributions; the host adds the ranks and divides by *n_probes). */
+int32_t csmc_pt_set_momenta(csmc_handle *h, const double *lattice_vectors, const double *basis,
+                            const double *ks, int64_t n_k);
+int32_t csmc_pt_get_ssf(csmc_handle *h, double *sums, int64_t *n_probes);
 /* Replaces the exchange block alone (src/monte_carlo.jl:308-349) on fresh energies;
  * parity = (sweep / swap_rate) % 2.  accepted_pairs[n_slots] (may be NULL): 1 where the
  * pair starting at that slot swapped. */

@@ -18,5 +18,6 @@ export Metropolis, MetropolisAdaptive, MetropolisConstraint, MetropolisConstrain
 export MonteCarlo, simulated_annealing!, deterministic_updates!, parallel_tempering!
 export total_energy, energy_density, get_local_field
 export Triangular, Square, Honeycomb, FCC, Pyrochlore, BreathingPyrochlore
+export compute_equal_time_correlations
 
 end

@@ -93,3 +93,11 @@ function get_magnetization(lat::Lattice)::Float64
     upload!(lat)
     return norm(magnetization_vectors(lat.engine)[:, 1])
 end
+
+# equal-time structure factor, body of src/spin_correlations.jl:6-43 on the GPU
+function compute_equal_time_correlations(lat::Lattice{D}, ks::Array{Float64,2}) where {D}
+    upload!(lat)
+    A = reduce(hcat, lat.unit_cell.lattice_vectors)                  # D x D, column d = a_d
+    B = permutedims(reduce(hcat, lat.unit_cell.basis))               # n_basis x D; the ABI wants row-major n_basis x D
+    return structure_factor(lat.engine, A, collect(transpose(B)), ks)  # column-major D x n_basis == row-major n_basis x D
+end

@@ -94,6 +94,14 @@ function magnetization_vectors(e::Engine)
     return M
 end
 
+"Suv (9 x N_k) of the current device spins; ks is D x N_k (src/spin_correlations.jl:6-43)"
+function structure_factor(e::Engine, lattice_vectors::Matrix{Float64}, basis::Matrix{Float64}, ks::Matrix{Float64}, replica=0)
+    Suv = zeros(9, size(ks, 2))
+    check(e, ccall((:csmc_structure_factor, libcsmc), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}),
+                   e.ptr, replica, lattice_vectors, basis, ks, size(ks, 2), Suv))
+    return Suv
+end
+
 # --- sweeps ------------------------------------------------------------------------------------------------
 overrelax!(e::Engine, n=1) = check(e, ccall((:csmc_overrelax, libcsmc), Int32, (Ptr{Cvoid}, Int32), e.ptr, n))
 deterministic!(e::Engine, n=1) = check(e, ccall((:csmc_deterministic, libcsmc), Int32, (Ptr{Cvoid}, Int32), e.ptr, n))

@@ -141,6 +141,26 @@ def test_structure_factor_matches_reference_formula(case):
     assert np.allclose(S[:, 0].reshape(3, 3), np.outer(M, M) / lat.size, rtol=1e-12, atol=1e-12)
 
 
+def test_parallel_tempering_accumulates_structure_factor(tmp_path):
+    """mc.corr = true: mean structure factor per temperature slot (src/monte_carlo.jl:371-375); at high T the
+    spins are uncorrelated, so trace S(k) ~ S^2 for every k, while the cold slot of the ferromagnet peaks at k=0."""
+    uc = models.square_heisenberg(J=-1.0, h=None)
+    lat = csm.Lattice((8, 8), uc, 1.0, rng=np.random.default_rng(6))
+    ks = np.array([[0.0, np.pi, np.pi / 2], [0.0, np.pi, 0.0]])
+    params = {"t_thermalization": 400, "t_measurement": 2000, "probe_rate": 10, "swap_rate": 10, "overrelaxation_rate": 5}
+    out = str(tmp_path) + "/"
+    mc = csm.MonteCarlo(np.array([0.05, 0.5, 50.0]), lat, params, corr=True, ks=ks, seed=8, outpath=out)
+    csm.parallel_tempering(mc)
+    S_cold, S_hot = mc.observables_all[0].correlations, mc.observables_all[2].correlations
+    assert S_cold.shape == (9, 3)
+    tr = lambda S: S[0] + S[4] + S[8]
+    assert tr(S_cold)[0] > 0.9 * lat.size and tr(S_cold)[1] < 0.05 * lat.size     # ordered: Bragg peak at k = 0
+    assert np.all(np.abs(tr(S_hot) - 1.0) < 0.25)                                  # paramagnet: flat, = S^2
+    f = h5._open(out + "configuration_0.h5", "r")
+    assert np.allclose(h5._get(f, "spin_correlations/SSF"), S_cold) and np.allclose(h5._get(f, "spin_correlations/SSF_momentum"), ks)
+    f.close()
+
+
 def test_errors_cross_the_abi_as_status_codes():
     L = _lib.lib()
     md = ModelData(models.square_heisenberg(), (4, 4), 1.0)

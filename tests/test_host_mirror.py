@@ -184,7 +184,7 @@ def test_pairing_and_slot_bookkeeping():
 def test_unsupported_variants_are_loud():
     uc = models.square_heisenberg()
     lat = csm.Lattice((2, 2), uc, 1.0)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError, match="No momentum vectors"):
         csm.MonteCarlo(1.0, lat, {}, corr=True)
     mc = csm.MonteCarlo(1.0, lat, {})
     with pytest.raises(NotImplementedError):
