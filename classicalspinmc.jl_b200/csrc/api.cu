@@ -537,6 +537,7 @@ int32_t csmc_plan(const csmc_model *model, int32_t flags, int32_t *colour, int32
 // is kept.  Leaves the handle in its freshly created state.
 static int autotune_pdl(csmc_handle *h) {
     if (!h->jit || (h->flags & (CSMC_FLAG_PDL | CSMC_FLAG_NO_AUTOTUNE | CSMC_FLAG_NO_GRAPH)) || h->hm.self_loop) return CSMC_OK;
+    if (h->jit_resident && h->hm.N <= 4096 && !(h->flags & CSMC_FLAG_NO_RESIDENT)) return CSMC_OK;   // sweeps run on the resident kernel
     JitModule other;
     if (!load_jit_module(h->hm, true, other).empty()) { if (other.lib) cudaLibraryUnload(other.lib); cudaGetLastError(); return CSMC_OK; }
     JitModule base;

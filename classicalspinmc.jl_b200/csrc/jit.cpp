@@ -446,8 +446,29 @@ std::string jit_generate_source(const HostModel &hm, bool pdl, JitPlan *plan) {
 }
 
 // returns "" on success
+// Optional on-disk cache of compiled cubins (CSMC_CACHE_DIR=<dir>), keyed by a hash of the generated
+// source: repeated runs of the same model skip NVRTC (seconds for cubic / quartic models).
+static std::string cache_path(const std::string &src) {
+    const char *dir = std::getenv("CSMC_CACHE_DIR");
+    if (!dir || !*dir) return "";
+    char buf[80];
+    std::snprintf(buf, sizeof buf, "/csmc_%016zx_%zu.sm_100a.cubin", std::hash<std::string>{}(src), src.size());
+    return std::string(dir) + buf;
+}
+
 std::string jit_compile(const std::string &src, std::vector<char> &cubin, std::string &log) {
     std::lock_guard<std::mutex> lk(g_rtc_mu);
+    const std::string cpath = cache_path(src);
+    if (!cpath.empty()) {
+        if (FILE *f = std::fopen(cpath.c_str(), "rb")) {
+            std::fseek(f, 0, SEEK_END);
+            const long n = std::ftell(f);
+            std::fseek(f, 0, SEEK_SET);
+            if (n > 0) { cubin.resize((size_t)n); if (std::fread(cubin.data(), 1, (size_t)n, f) != (size_t)n) cubin.clear(); }
+            std::fclose(f);
+            if (!cubin.empty()) return "";
+        }
+    }
     if (!load_nvrtc()) return g_rtc.err;
     nvrtcProgram prog = nullptr;
     // CSMC_JIT_DUMP=<dir>: keep the generated source on disk under the name the cubin's line table
@@ -479,6 +500,14 @@ std::string jit_compile(const std::string &src, std::vector<char> &cubin, std::s
     cubin.resize(n);
     rc = g_rtc.GetCUBIN(prog, cubin.data());
     g_rtc.DestroyProgram(&prog);
+    if (rc == 0 && !cpath.empty()) {
+        const std::string tmp = cpath + ".tmp";
+        if (FILE *f = std::fopen(tmp.c_str(), "wb")) {
+            const bool ok = std::fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+            std::fclose(f);
+            if (ok) std::rename(tmp.c_str(), cpath.c_str()); else std::remove(tmp.c_str());
+        }
+    }
     return rc == 0 ? "" : "nvrtcGetCUBIN failed";
 }
 

@@ -15,6 +15,12 @@ from bench import B_ALG, workload_model  # noqa: E402
 from classicalspinmc.jl_b200 import _lib  # noqa: E402
 
 
+def _unit_cell(name):
+    from tests import models
+    return {"C2": models.square_heisenberg, "C3": models.kitaev_honeycomb, "C4": models.pyrochlore_local,
+            "C5": models.triangular_multispin}[name]()
+
+
 def time_cycles(eng, stream, n, orc, mc):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     eng.cycles_async(max(2, n // 10), orc, mc)
@@ -31,16 +37,19 @@ def main():
     ap.add_argument("--workloads", default="C2,C2:4096,C3:256:8,C4:32:16,C5:512:1")
     ap.add_argument("--n", type=int, default=200)
     ap.add_argument("--flags", type=int, default=0)
+    ap.add_argument("--ssf", type=int, default=0, help="also time the structure factor at this many wavevectors")
     args = ap.parse_args()
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     peak = 6547.8
+    md_uc = {}
     for spec in args.workloads.split(","):
         parts = spec.split(":")
         name = parts[0]
         L = int(parts[1]) if len(parts) > 1 else None
         R = int(parts[2]) if len(parts) > 2 else 1
         md, cfg = workload_model(name, L)
+        md_uc[spec] = _unit_cell(name)
         eng = _lib.Engine(md, n_replicas=R, seed=1, stream=stream.cuda_stream, flags=args.flags)
         eng.randomize(7)
         eng.set_temperatures(np.geomspace(0.5, 2.0, R))
@@ -53,6 +62,18 @@ def main():
             upd = n * (orc + mc) * N * R
             out[label] = {"Gupd_s": upd / dt / 1e9, "us_per_pass": dt / (n * (orc + mc) * C) * 1e6,
                           "GBs_alg": upd * balg / dt / 1e9, "frac": upd * balg / dt / 1e9 / peak}
+        if args.ssf:
+            # equal-time structure factor: n_k wavevectors x N sites (src/spin_correlations.jl:6-43)
+            import time
+            uc = md_uc[spec]
+            ks = np.random.default_rng(1).uniform(-np.pi, np.pi, size=(uc.D, args.ssf))
+            eng.structure_factor(uc.lattice_vectors, uc.basis, ks)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                eng.structure_factor(uc.lattice_vectors, uc.basis, ks)
+            dt = (time.perf_counter() - t0) / 5
+            out["ssf"] = {"n_k": args.ssf, "ms": dt * 1e3, "Gpairs_s": args.ssf * N / dt / 1e9}
         print(json.dumps(out))
         eng.close()
 
