@@ -17,8 +17,11 @@ from classicalspinmc.jl_b200 import _lib  # noqa: E402
 
 def _unit_cell(name):
     from tests import models
-    return {"C2": models.square_heisenberg, "C3": models.kitaev_honeycomb, "C4": models.pyrochlore_local,
-            "C5": models.triangular_multispin}[name]()
+    uc = {"C2": models.square_heisenberg, "C3": models.kitaev_honeycomb, "C4": models.pyrochlore_local,
+          "C5": models.triangular_multispin}[name]()
+    if not uc.basis:
+        uc.basis.append(np.zeros(uc.D))
+    return uc
 
 
 def time_cycles(eng, stream, n, orc, mc):
