@@ -38,6 +38,7 @@ int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 struct Gen {
     const HostModel &hm;
     std::ostringstream o;
+    std::vector<int> seg_split;               // per segment: warps a site's slots are split over (1, 2, 4)
     std::vector<double> ktab;                 // coefficients placed in the constant bank
     std::map<uint64_t, int> kslot;
     // interaction coefficient as an operand: simple values stay literals (the compiler folds +-1 into
@@ -91,7 +92,7 @@ struct Gen {
         const HostSeg &hs = hm.segs[s];
         const int b = hs.basis;
         // which terms are live (some non-zero coefficient, every neighbour class exists)
-        struct Live { const HostTerm *t; int slot; int bit; };
+        struct Live { const HostTerm *t; int slot; int bit; int part; };
         std::vector<Live> live;
         int nnb = 0;
         for (const auto &t : hm.basis_terms[b]) {
@@ -106,13 +107,40 @@ struct Gen {
                 exists &= seg_of_class.count(std::make_tuple(t.nb_basis[k], r2[0], r2[1], r2[2])) > 0;
             }
             if (!any || !exists) continue;
-            live.push_back({&t, nnb, (int)live.size()});
+            live.push_back({&t, nnb, (int)live.size(), 0});
             nnb += t.kind - 1;
         }
         if (live.size() > 32) throw std::runtime_error("more than 32 live interaction slots per site");
+        // Heavy sites (cubic / quartic slots) are split over SP warps of the CTA: each warp evaluates a
+        // subset of the slots for the same 32 sites, partial fields are summed through shared memory in a
+        // fixed order.  4x the threads per site and a quarter of the live registers per thread.
+        auto slot_cost = [](const HostTerm &t) { return t.kind == 2 ? 9 : t.kind == 3 ? 36 : 117; };
+        int total_cost = 0;
+        for (const auto &lv : live) total_cost += slot_cost(*lv.t);
+        static const int sp_env = std::getenv("CSMC_JIT_SPLIT") ? std::atoi(std::getenv("CSMC_JIT_SPLIT")) : 0;
+        // Measured on B200 (C5, L=512 / 1024): splitting is slower than one thread per site (8.7 / 7.2 us per
+        // pass at SP = 4 / 2 against 5.7 us), the replicated index arithmetic and the barrier outweigh the
+        // occupancy gain -- so it stays an experiment behind CSMC_JIT_SPLIT=2|4.
+        (void)total_cost;
+        int SP = sp_env > 0 ? sp_env : 1;
+        if (SP != 1 && SP != 2 && SP != 4) SP = 1;
+        if (nnb > 64) SP = 1;   // streaming variant is not split
+        {
+            std::vector<int> order(live.size()), load_of(SP, 0);
+            for (size_t i = 0; i < live.size(); ++i) order[i] = (int)i;
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return slot_cost(*live[a].t) > slot_cost(*live[b].t); });
+            for (int i : order) {
+                int best = 0;
+                for (int p = 1; p < SP; ++p) if (load_of[p] < load_of[best]) best = p;
+                live[i].part = best;
+                load_of[best] += slot_cost(*live[i].t);
+            }
+        }
+        seg_split.resize(hm.segs.size(), 1);
+        seg_split[s] = SP;
 
         o << "struct Seg" << s << " {\n";
-        o << "    static constexpr int START = " << hs.start << ", COUNT = " << hs.count << ", NNB = " << nnb << ";\n";
+        o << "    static constexpr int START = " << hs.start << ", COUNT = " << hs.count << ", NNB = " << nnb << ", SP = " << SP << ";\n";
         o << "    static constexpr double H0 = " << lit(hm.field[3 * b]) << ", H1 = " << lit(hm.field[3 * b + 1]) << ", H2 = " << lit(hm.field[3 * b + 2]) << ";\n";
         const bool ons = hm.onsite_coef[b] >= 0;
         o << "    static constexpr bool ONSITE = " << (ons ? "true" : "false") << ";\n";
@@ -208,12 +236,12 @@ struct Gen {
         };
         const char *nm[3] = {"p", "q", "w"};
         // phase 1 (PRELOAD): all neighbour loads up front (read-only during the pass: other colours) via ld.global.nc
-        o << "    template <bool NC> static __device__ __forceinline__ void load(const double *__restrict__ sx, const double *__restrict__ sy, const double *__restrict__ sz,\n"
+        o << "    template <bool NC, int PART> static __device__ __forceinline__ void load(const double *__restrict__ sx, const double *__restrict__ sy, const double *__restrict__ sz,\n"
              "            int m0, int m1, int m2, double (&nb)[PRELOAD ? 3 * NNB + 1 : 1], unsigned &ok) {\n";
         if (preload)
             for (const auto &lv : live) {
                 const HostTerm &t = *lv.t;
-                o << "        { // slot " << lv.bit << " kind " << t.kind << "\n";
+                o << "        if (PART < 0 || PART == " << lv.part << ") { // slot " << lv.bit << " kind " << t.kind << "\n";
                 if (!hm.periodic) o << "          bool okt = true;\n";
                 for (int k = 0; k < t.kind - 1; ++k) neighbour(hs, t, k);
                 if (!hm.periodic) o << "          if (okt) {\n";
@@ -233,12 +261,12 @@ struct Gen {
             }
         o << "    }\n";
         // phase 2 (PRELOAD): unrolled neighbour field from registers: a* bilinear, b* cubic, c* quartic accumulators
-        o << "    static __device__ __forceinline__ void field(const double (&nb)[PRELOAD ? 3 * NNB + 1 : 1], unsigned ok,\n"
+        o << "    template <int PART> static __device__ __forceinline__ void field(const double (&nb)[PRELOAD ? 3 * NNB + 1 : 1], unsigned ok,\n"
              "            double &a0, double &a1, double &a2, double &b0, double &b1, double &b2, double &c0, double &c1, double &c2) {\n";
         if (preload)
             for (const auto &lv : live) {
                 const HostTerm &t = *lv.t;
-                o << "      " << (hm.periodic ? "" : "if (ok & (1u << " + std::to_string(lv.bit) + ")) ") << "{ // slot " << lv.bit << "\n";
+                o << "      if ((PART < 0 || PART == " << lv.part << ")" << (hm.periodic ? "" : " && (ok & (1u << " + std::to_string(lv.bit) + "))") << ") { // slot " << lv.bit << "\n";
                 for (int k = 0; k < t.kind - 1; ++k) {
                     const int base = 3 * (lv.slot + k);
                     o << "        const double " << nm[k] << "0 = nb[" << base << "], " << nm[k] << "1 = nb[" << base + 1 << "], " << nm[k] << "2 = nb[" << base + 2 << "];\n";
@@ -315,6 +343,54 @@ struct Gen {
             auto env_int = [](const char *n, int dflt) { const char *v = std::getenv(n); return v ? std::atoi(v) : dflt; };
             const int fuse_or = std::max(1, env_int("CSMC_JIT_FUSE", 2)), fuse_mc = std::max(1, env_int("CSMC_JIT_FUSE_METRO", 1));
             const int mb_or = std::max(1, env_int("CSMC_JIT_MB", 1)), mb_mc = std::max(1, env_int("CSMC_JIT_MB_METRO", mb_or));
+            int SPc = 1;
+            for (int sg = s0; sg < s1; ++sg) SPc = std::max(SPc, seg_split[sg]);
+            if (SPc > 1) {
+                // ---- heavy sites: SPc warps share one site (see segment()); tile = sw_tpb / SPc sites ----
+                const int TS = sw_tpb / SPc;
+                int Ts[MAXD] = {1, 1, 1}, NTs[MAXD] = {1, 1, 1};
+                {
+                    int left2 = TS;
+                    Ts[last] = std::min(std::min(32, pow2_ceil(M[last])), left2);
+                    left2 /= Ts[last];
+                    for (int d = last - 1; d >= 0; --d) { Ts[d] = (d == 0) ? left2 : std::min(left2, pow2_ceil(M[d])); if (d == 0) Ts[d] = left2; left2 /= Ts[d]; }
+                    if (hm.D == 1) Ts[0] = TS;
+                    for (int d = 0; d < MAXD; ++d) NTs[d] = (M[d] + Ts[d] - 1) / Ts[d];
+                }
+                plan.tiles[c] = NTs[0] * NTs[1] * NTs[2];
+                plan.groups[c] = nseg;
+                plan.groups_metro.resize(hm.n_colours);
+                plan.groups_metro[c] = nseg;
+                for (int u = 0; u < 4; ++u) {
+                    o << "extern \"C\" __global__ void __launch_bounds__(" << sw_tpb << ", " << (u >= 2 ? mb_mc : mb_or) << ") csmc_sweep_c" << c << "_u" << u << "(double *spins, const SweepArgs a) {\n";
+                    o << "#ifdef CSMC_PDL\n#if CSMC_PDL == 1\n    pdl_launch_dependents();\n#endif\n    pdl_wait();\n#endif\n";
+                    o << "    __shared__ double part_g[" << (SPc - 1) << "][3][" << TS << "];\n";
+                    o << "    const int rep = blockIdx.z;\n    int t = blockIdx.x;\n";
+                    o << "    const int warp = threadIdx.x >> 5, part = warp % " << SPc << ", ls = (warp / " << SPc << ") * 32 + (threadIdx.x & 31);\n";
+                    o << "    const int t2 = t % " << NTs[2] << "; t /= " << NTs[2] << "; const int t1 = t % " << NTs[1] << "; const int t0 = t / " << NTs[1] << ";\n";
+                    o << "    const int l2 = ls & " << (Ts[2] - 1) << ", l1 = (ls >> " << ilog2(Ts[2]) << ") & " << (Ts[1] - 1) << ", l0 = ls >> " << (ilog2(Ts[2]) + ilog2(Ts[1])) << ";\n";
+                    o << "    const int m0 = t0 * " << Ts[0] << " + l0, m1 = t1 * " << Ts[1] << " + l1, m2 = t2 * " << Ts[2] << " + l2;\n";
+                    o << "    int n_acc = 0;\n    switch (blockIdx.y) {\n";
+                    for (int sg = s0; sg < s1; ++sg) {
+                        o << "    case " << (sg - s0) << ": {\n";
+                        o << "        double g0 = 0.0, g1 = 0.0, g2 = 0.0;\n        Site<Seg" << sg << "> d;\n";
+                        o << "        switch (part) {\n";
+                        o << "        case 0: site_load<Seg" << sg << ", true, 0>(d, spins, rep, m0, m1, m2); break;\n";
+                        for (int pp = 1; pp < SPc; ++pp)
+                            o << "        case " << pp << ": site_partial<Seg" << sg << ", " << pp << ">(spins, rep, m0, m1, m2, g0, g1, g2); break;\n";
+                        o << "        default: break;\n        }\n";
+                        o << "        if (part > 0) { part_g[part - 1][0][ls] = g0; part_g[part - 1][1][ls] = g1; part_g[part - 1][2][ls] = g2; }\n";
+                        o << "        __syncthreads();\n";
+                        o << "        if (part == 0) {\n            double x0 = 0.0, x1 = 0.0, x2 = 0.0;\n";
+                        o << "            for (int pp = 0; pp < " << (SPc - 1) << "; ++pp) { x0 += part_g[pp][0][ls]; x1 += part_g[pp][1][ls]; x2 += part_g[pp][2][ls]; }\n";
+                        o << "            n_acc += site_finish<" << u << ", Seg" << sg << ", true, 0>(d, spins, rep, a, -1, 0ULL, x0, x1, x2) ? 1 : 0;\n        }\n";
+                        o << "    } break;\n";
+                    }
+                    o << "    default: break;\n    }\n";
+                    if (u >= 2) o << "    count_accepted(n_acc, rep, a);\n";
+                    o << "#if defined(CSMC_PDL) && CSMC_PDL == 2\n    pdl_launch_dependents();\n#endif\n}\n";
+                }
+            } else {
             plan.groups[c] = 0;
             for (int u = 0; u < 4; ++u) {
                 const int G = std::min(nseg, u >= 2 ? fuse_mc : fuse_or);
@@ -338,6 +414,7 @@ struct Gen {
                     o << "    } break;\n";
                 }
                 o << "    default: break;\n    }\n#if defined(CSMC_PDL) && CSMC_PDL == 2\n    pdl_launch_dependents();\n#endif\n}\n";
+            }
             }
             o << "extern \"C\" __global__ void __launch_bounds__(TPB) csmc_energy_c" << c << "(const double *spins, double *__restrict__ partials, int n_partials, int partial_base) {\n";
             o << "    double v[4] = {0.0, 0.0, 0.0, 0.0};\n    switch (blockIdx.y) {\n";

@@ -85,7 +85,7 @@ struct Site {
     double nb[SEG::PRELOAD ? 3 * SEG::NNB + 1 : 1];   // neighbour spins, compile-time indexed (registers)
 };
 
-template <class SEG, bool NC = true>
+template <class SEG, bool NC = true, int PART = -1>
 __device__ __forceinline__ void site_load(Site<SEG> &d, const double *spins, int rep, int m0, int m1, int m2) {
     const double *sx = spins + (size_t)rep * (3ull * NPAD), *sy = sx + NPAD, *sz = sy + NPAD;
     d.valid = SEG::valid(m0, m1, m2);
@@ -94,13 +94,14 @@ __device__ __forceinline__ void site_load(Site<SEG> &d, const double *spins, int
     if (d.valid) {
         d.pos = SEG::pos(m0, m1, m2);
         d.s0 = sx[d.pos]; d.s1 = sy[d.pos]; d.s2 = sz[d.pos];
-        if (SEG::PRELOAD) SEG::template load<NC>(sx, sy, sz, m0, m1, m2, d.nb, d.ok);
+        if (SEG::PRELOAD) SEG::template load<NC, PART>(sx, sy, sz, m0, m1, m2, d.nb, d.ok);
     }
 }
 
-template <int UPD, class SEG, bool NC = true>
+// PART >= 0: this thread evaluated only the slots of its part; (x0, x1, x2) carries the other parts' sums
+template <int UPD, class SEG, bool NC = true, int PART = -1>
 __device__ __forceinline__ bool site_finish(Site<SEG> &d, double *spins, int rep, const SweepArgs &a, int grep_override = -1,
-                                            unsigned long long ctr_extra = 0ULL) {
+                                            unsigned long long ctr_extra = 0ULL, double x0 = 0.0, double x1 = 0.0, double x2 = 0.0) {
     double *sx = spins + (size_t)rep * (3ull * NPAD), *sy = sx + NPAD, *sz = sy + NPAD;
     bool accepted = false;
     if (d.valid) {
@@ -132,8 +133,9 @@ __device__ __forceinline__ bool site_finish(Site<SEG> &d, double *spins, int rep
                 g2 = 2 * (SEG::O6 * s0 + SEG::O7 * s1 + SEG::O8 * s2);
             }
         }
-        if (SEG::PRELOAD) SEG::field(d.nb, d.ok, g0, g1, g2, g0, g1, g2, g0, g1, g2);
+        if (SEG::PRELOAD) SEG::template field<PART>(d.nb, d.ok, g0, g1, g2, g0, g1, g2, g0, g1, g2);
         else SEG::template field_stream<NC>(sx, sy, sz, d.m0, d.m1, d.m2, g0, g1, g2, g0, g1, g2, g0, g1, g2);
+        g0 += x0; g1 += x1; g2 += x2;
         const double F0 = g0 - SEG::H0, F1 = g1 - SEG::H1, F2 = g2 - SEG::H2;
         if (UPD == UPD_OR) {
             if (!(F0 == 0.0 && F1 == 0.0 && F2 == 0.0)) {
@@ -161,6 +163,15 @@ __device__ __forceinline__ bool site_finish(Site<SEG> &d, double *spins, int rep
     return accepted;
 }
 
+// a non-zero part: evaluate its slots' contribution to the neighbour field of the site
+template <class SEG, int PART>
+__device__ __forceinline__ void site_partial(const double *spins, int rep, int m0, int m1, int m2, double &g0, double &g1, double &g2) {
+    Site<SEG> d;
+    site_load<SEG, true, PART>(d, spins, rep, m0, m1, m2);
+    g0 = g1 = g2 = 0.0;
+    if (d.valid) SEG::template field<PART>(d.nb, d.ok, g0, g1, g2, g0, g1, g2, g0, g1, g2);
+}
+
 // one atomic per CTA, striped over ACC_STRIPE addresses per replica (same-address L2 atomics serialise)
 __device__ __forceinline__ void count_accepted(int n_mine, int rep, const SweepArgs &a) {
     __shared__ int sh_acc;
@@ -184,7 +195,7 @@ __device__ __forceinline__ void energy_site(const double *spins, double (&v)[4])
         site_load(d, spins, rep, m0, m1, m2);
         const double s0 = d.s0, s1 = d.s1, s2 = d.s2;
         double a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0, c0 = 0, c1 = 0, c2 = 0;
-        if (SEG::PRELOAD) SEG::field(d.nb, d.ok, a0, a1, a2, b0, b1, b2, c0, c1, c2);
+        if (SEG::PRELOAD) SEG::template field<-1>(d.nb, d.ok, a0, a1, a2, b0, b1, b2, c0, c1, c2);
         else {
             const double *sx = spins + (size_t)rep * (3ull * NPAD), *sy = sx + NPAD, *sz = sy + NPAD;
             SEG::template field_stream<true>(sx, sy, sz, m0, m1, m2, a0, a1, a2, b0, b1, b2, c0, c1, c2);
@@ -208,7 +219,7 @@ __device__ __forceinline__ void energy_site_at(const double *spins, int idx, dou
         site_load<SEG, false>(d, spins, 0, m0, m1, m2);
         const double s0 = d.s0, s1 = d.s1, s2 = d.s2;
         double a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0, c0 = 0, c1 = 0, c2 = 0;
-        if (SEG::PRELOAD) SEG::field(d.nb, d.ok, a0, a1, a2, b0, b1, b2, c0, c1, c2);
+        if (SEG::PRELOAD) SEG::template field<-1>(d.nb, d.ok, a0, a1, a2, b0, b1, b2, c0, c1, c2);
         else SEG::template field_stream<false>(spins, spins + NPAD, spins + 2 * NPAD, m0, m1, m2, a0, a1, a2, b0, b1, b2, c0, c1, c2);
         double e = (s0 * a0 + s1 * a1 + s2 * a2) / 2 + (s0 * b0 + s1 * b1 + s2 * b2) / 3 +
                    (s0 * c0 + s1 * c1 + s2 * c2) / 4 - (s0 * SEG::H0 + s1 * SEG::H1 + s2 * SEG::H2);
