@@ -385,7 +385,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--L", type=int, default=None)
-    ap.add_argument("--cycles-per-step", type=int, default=20)
+    ap.add_argument("--cycles-per-step", type=int, default=100,
+                    help="cycles per step: 100 x (10 OR + 1 Metropolis) = 1100 sweeps, ~1 % of one annealing temperature of the README example")
     ap.add_argument("--or-per-cycle", type=int, default=10)
     ap.add_argument("--metro-per-cycle", type=int, default=1)
     ap.add_argument("--ref-cycles", type=int, default=4, help="cycles per host thread per step in the CPU legs")

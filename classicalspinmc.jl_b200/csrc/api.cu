@@ -457,8 +457,10 @@ int32_t csmc_create(const csmc_model *model, const csmc_opts *opts, csmc_handle 
     CKC(cudaMemsetAsync(h->d_spins, 0, sizeof(double) * h->R * 3 * npad, h->stream));
     CKC(dalloc(&h->d_stage, (size_t)3 * hm.N));
     CKC(dalloc(&h->d_out, (size_t)3 * hm.N));
-    CKC(dalloc(&h->d_nbr, hm.nbr.size()));
-    CKC(cudaMemcpyAsync(h->d_nbr, hm.nbr.data(), sizeof(int32_t) * hm.nbr.size(), cudaMemcpyHostToDevice, h->stream));
+    if (!hm.nbr.empty()) {   // explicit-table kernels only
+        CKC(dalloc(&h->d_nbr, hm.nbr.size()));
+        CKC(cudaMemcpyAsync(h->d_nbr, hm.nbr.data(), sizeof(int32_t) * hm.nbr.size(), cudaMemcpyHostToDevice, h->stream));
+    }
     CKC(dalloc(&h->d_ref_of_pos, npad));
     CKC(cudaMemcpyAsync(h->d_ref_of_pos, hm.ref_of_pos.data(), sizeof(int32_t) * npad, cudaMemcpyHostToDevice, h->stream));
     CKC(dalloc(&h->d_beta, h->R)); CKC(dalloc(&h->d_sigma, h->R));

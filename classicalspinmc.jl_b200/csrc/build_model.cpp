@@ -463,7 +463,21 @@ std::string build_host_model(const csmc_model *m, int flags, HostModel &hm) {
     for (const auto &s : hm.segs) hm.colour_seg_begin[s.colour + 1]++;
     for (int c = 0; c < hm.n_colours; ++c) hm.colour_seg_begin[c + 1] += hm.colour_seg_begin[c];
 
-    // explicit neighbour table, storage order
+    // can the arithmetic-neighbour kernels be used?
+    hm.structured = hm.pattern && !(flags & CSMC_FLAG_FORCE_GENERIC);
+    if (hm.structured) {
+        for (const auto &s : hm.segs)
+            for (const auto &t : hm.basis_terms[s.basis])
+                for (int k = 0; k < t.kind - 1; ++k)
+                    for (int d = 0; d < D; ++d) {
+                        const int delta = floordiv(s.r[d] + t.off[k][d], hm.P[d]);
+                        if (std::abs(delta) > 120) hm.structured = false;
+                        if (hm.periodic && std::abs(delta) > hm.L[d] / hm.P[d]) hm.structured = false;
+                    }
+    }
+
+    // explicit neighbour table, storage order: only the explicit-table kernels read it (1 GB at L=8192)
+    if (!hm.structured) {
     hm.nbr.assign((size_t)std::max(hm.n_rows, 1) * hm.npad, -1);
     for (int64_t p = 0; p < hm.N; ++p) {
         int b, i[MAXD], j[MAXD];
@@ -482,18 +496,6 @@ std::string build_host_model(const csmc_model *m, int flags, HostModel &hm) {
             for (int k = 0; k < nn; ++k) hm.nbr[(size_t)(t.row + k) * hm.npad + pp] = hm.pos_of_ref[q[k]];
         }
     }
-
-    // can the arithmetic-neighbour kernels be used?
-    hm.structured = hm.pattern && !(flags & CSMC_FLAG_FORCE_GENERIC);
-    if (hm.structured) {
-        for (const auto &s : hm.segs)
-            for (const auto &t : hm.basis_terms[s.basis])
-                for (int k = 0; k < t.kind - 1; ++k)
-                    for (int d = 0; d < D; ++d) {
-                        const int delta = floordiv(s.r[d] + t.off[k][d], hm.P[d]);
-                        if (std::abs(delta) > 120) hm.structured = false;
-                        if (hm.periodic && std::abs(delta) > hm.L[d] / hm.P[d]) hm.structured = false;
-                    }
     }
 
     // parameter-struct size class
