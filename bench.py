@@ -347,7 +347,8 @@ def run_ours(args):
         cfg.update(cycle=f"{orc_} OR + {mc_} Metropolis", cycles_per_step=args.cycles_per_step,
                    colours=n_col, kernel_mode=eng.kernel_mode, parallelism=f"replicas x{world}",
                    launch_autotune=dict(zip(("ms_plain", "ms_pdl", "pdl_selected"), eng.autotune_report())),
-                   l2="flushed between timed steps (256 MiB memset); lattice (24 MiB at L=1024) is L2-resident within a step")
+                   l2=f"flushed between timed steps (256 MiB memset); lattice is {N * 24 / 2 ** 20:.0f} MiB "
+                      + ("(L2-resident within a step)" if N * 24 < 100 * 2 ** 20 else "(larger than L2: HBM-bound)"))
         line = {"metric": "single-spin updates/sec (Metropolis+overrelax)", "value": value, "unit": "updates/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
