@@ -79,26 +79,35 @@ class MonteCarlo:
         rank, comm_size = parallel.comm_info()                          # :85-92
         self.rank, self.comm_size = rank, comm_size
         self.outdir, self.outprefix, self.paramsfile = outpath, outprefix, None
+        # temperature slots: the reference has one per MPI rank and names its files by rank; with several
+        # slots per process the files are named by global slot (== rank when there is one slot per process)
+        if comm_size > 1:
+            _, self.slot_base, _ = parallel.gather_temperatures(self.temperatures)
+        else:
+            self.slot_base = 0
         if len(outpath) > 0:                                            # :95-113
-            filename = f"{outprefix}_{rank}.h5"
             if rank == 0 and not os.path.isdir(outpath):
                 os.makedirs(outpath, exist_ok=True)
             parallel.barrier()
-            self.outpath = outpath + filename
+            self.outpath = outpath + f"{outprefix}_{self.slot_base}.h5"
             self.paramsfile = outpath + outprefix + ".h5.params"
             if rank == 0 and not os.path.isfile(self.paramsfile) and overwrite:
                 h5.create_params_file(self, self.paramsfile)
                 if inparams:
                     h5.write_attributes(self.paramsfile, inparams)
-            if not os.path.isfile(self.outpath) and overwrite:
-                print(f"Creating new file {filename} for output on rank {rank}")
-                h5.initialize_hdf5(self, self.paramsfile)
+            parallel.barrier()
+            for r, T_r in enumerate(self.temperatures):
+                path = outpath + f"{outprefix}_{self.slot_base + r}.h5"
+                if not os.path.isfile(path) and overwrite:
+                    print(f"Creating new file {os.path.basename(path)} for output on rank {rank}")
+                    h5.initialize_hdf5(self, self.paramsfile, outpath=path, T=T_r, spins=self.replica_spins[r])
         else:
             self.outpath = outpath
 
     # ---- device state ------------------------------------------------------------------------------
-    def _device(self, n_replicas=None, replica_base=0):
+    def _device(self, n_replicas=None, replica_base=None):
         n_replicas = len(self.temperatures) if n_replicas is None else n_replicas
+        replica_base = self.slot_base if replica_base is None else replica_base   # global index of local replica 0
         if self._engine is None or self._engine.n_replicas != n_replicas or self._engine.replica_base != replica_base:
             from . import _lib
             if self._engine is not None:
@@ -255,11 +264,7 @@ def parallel_tempering(mc: MonteCarlo, saveIC=(), alg=None):
     def slot_paths(slot):
         return os.path.join(mc.outdir, f"{mc.outprefix}_{slot}.h5") if out else None
 
-    if out:  # one configuration file per slot this process starts with
-        for r in range(R):
-            sp = slot_paths(base + r)
-            if not os.path.isfile(sp):
-                h5.initialize_hdf5(mc, mc.paramsfile, outpath=sp, T=T_all[base + r], spins=mc.replica_spins[r])
+    if out:  # the configuration files (one per slot) were created by MonteCarlo(); wait for every rank's
         parallel.barrier()
 
     if rank == 0:

@@ -72,15 +72,22 @@ function MonteCarlo(T::Union{Float64,Vector{Float64}}, lattice::Lattice{D}, para
     if length(outpath) > 0
         mc.rank == 0 && !isdir(outpath) && mkdir(outpath)
         barrier()
-        mc.outpath = string(outpath, outprefix, "_", mc.rank, ".h5")
+        # files are named by global temperature slot (== rank with one temperature per process, as in the
+        # reference); every process holds the same number of slots
+        base = mc.rank * length(temps)
+        mc.outpath = string(outpath, outprefix, "_", base, ".h5")
         paramsfile = string(outpath, outprefix, ".h5.params")
         if mc.rank == 0 && !isfile(paramsfile) && overwrite
             create_params_file(mc, paramsfile)
             isempty(inparams) || write_attributes(paramsfile, inparams)
         end
-        if !isfile(mc.outpath) && overwrite
-            println("Creating new file $(basename(mc.outpath)) for output on rank $(mc.rank)")
-            initialize_hdf5(mc, paramsfile)
+        barrier()
+        for r in eachindex(temps)
+            path = string(outpath, outprefix, "_", base + r - 1, ".h5")
+            if !isfile(path) && overwrite
+                println("Creating new file $(basename(path)) for output on rank $(mc.rank)")
+                initialize_hdf5(path, temps[r], paramsfile, mc.replica_spins[r], lat.site_positions)
+            end
         end
     end
     return mc

@@ -44,12 +44,13 @@ function read_lattice(fid)::Lattice
     return Lattice(tuple(read(l["size"])...), read_unit_cell(fid), read(l["S"]), bc=read(l["bc"]))
 end
 
-function initialize_hdf5(mc, paramsfile::String)
-    h5open(mc.outpath, "w") do f
-        write_attribute(f, "T", mc.T); write_attribute(f, "paramsfile", paramsfile)
-        f["spins"] = mc.lattice.spins; f["site_positions"] = mc.lattice.site_positions
+function initialize_hdf5(path::String, T::Float64, paramsfile::String, spins, site_positions)
+    h5open(path, "w") do f
+        write_attribute(f, "T", T); write_attribute(f, "paramsfile", paramsfile)
+        f["spins"] = spins; f["site_positions"] = site_positions
     end
 end
+initialize_hdf5(mc, paramsfile::String) = initialize_hdf5(mc.outpath, mc.T, paramsfile, mc.lattice.spins, mc.lattice.site_positions)
 
 write_spins(path::String, spins) = h5open(f -> (f["spins"][:, :] = spins), path, "r+")
 write_MC_checkpoint(mc) = write_spins(mc.outpath, mc.lattice.spins)

@@ -29,3 +29,17 @@ def test_sharded_parallel_tempering_is_bit_identical_to_single_gpu(world):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert line["ok"] and line["world"] == world and line["exchanges"] > 0
+
+
+def test_parallel_tempering_driver_across_processes(tmp_path):
+    """examples/parallel_tempering/runner.jl through the host mirror on 2 GPUs: slots block-partitioned over
+    processes, files per temperature slot written by whichever process holds the slot's replica."""
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29521", os.path.join(ROOT, "tests", "pt_driver_worker.py"),
+           str(tmp_path) + "/"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["ok"] and line["E_cold"] < line["E_hot"]
