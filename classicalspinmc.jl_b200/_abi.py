@@ -65,6 +65,7 @@ FLAG_NO_JIT = 8
 FLAG_PDL = 16
 FLAG_NO_RESIDENT = 32
 FLAG_NO_AUTOTUNE = 64
+FLAG_FUSED = 128
 
 
 def resolve_field_onsite(uc):

@@ -69,6 +69,7 @@ struct csmc_handle {
     bool own_stream = false;
 
     double *d_spins = nullptr, *d_stage = nullptr, *d_out = nullptr;
+    double *d_spins_alt = nullptr;     // second spin buffer of the fused full-sweep kernels (ping-pong), allocated on first use
     int32_t *d_nbr = nullptr, *d_ref_of_pos = nullptr;
     double *d_beta = nullptr, *d_sigma = nullptr;
     unsigned long long *d_acc = nullptr, *d_acc_prev = nullptr, *d_ctr = nullptr;
@@ -96,6 +97,7 @@ struct csmc_handle {
     std::vector<cudaKernel_t> jit_sweep[4], jit_energy;
     JitPlan jit_plan;
     cudaKernel_t jit_resident = nullptr;
+    cudaKernel_t jit_fused[4] = {nullptr, nullptr, nullptr, nullptr};
     bool jit_tried = false, jit_pdl = false;
     float tune_ms[2] = {0.f, 0.f};   // autotune: ms per probe run without / with programmatic dependent launch
     std::string jit_note;
@@ -109,8 +111,10 @@ struct csmc_handle {
     // CUDA graph of one bench cycle
     cudaGraphExec_t cycle_graph = nullptr;
     int cycle_or = -1, cycle_metro = -1;
+    long long cycle_launches = 0;
     // CUDA graphs of n consecutive overrelaxation sweeps (parallel-tempering loop)
     std::map<int, cudaGraphExec_t> or_graphs;
+    std::map<int, long long> or_graph_launches;
 
     std::string err;
     long long launches = 0;
@@ -180,6 +184,63 @@ void enqueue_sweep(csmc_handle *h, unsigned long long ctr_off = 0, bool device_c
     for (int c = 0; c < h->hm.n_colours; ++c) launch_sweep_pass<UPD>(h, c, a);
 }
 
+// ---- fused full-sweep kernels (jit.cpp emit_fused): one launch per sweep, ping-pong between d_spins and d_spins_alt
+bool fused_ready(csmc_handle *h) {
+    if (!h->jit || !h->jit_plan.fused || !(h->flags & CSMC_FLAG_FUSED)) return false;
+    if (!h->d_spins_alt) {   // not during stream capture: callers prepare before cudaStreamBeginCapture
+        if (dalloc(&h->d_spins_alt, (size_t)h->R * 3 * h->hm.npad) != cudaSuccess) {
+            cudaGetLastError();
+            h->d_spins_alt = nullptr;
+            h->jit_plan.fused = false;
+            return false;
+        }
+    }
+    return true;
+}
+
+void launch_fused(csmc_handle *h, int upd, const double *in, double *out, const SweepArgs &a) {
+    void *args[] = {(void *)&in, (void *)&out, (void *)&a};
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(h->jit_plan.fused_tiles, 1, h->R);
+    cfg.blockDim = dim3(h->jit_plan.fused_tpb);
+    cfg.dynamicSmemBytes = h->jit_plan.fused_smem;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = h->jit_pdl ? 1 : 0;
+    cudaLaunchKernelExC(&cfg, (const void *)h->jit_fused[upd], args);
+    h->launches++;
+}
+
+struct SweepOp { int upd; unsigned long long ctr_off; bool device_ctr; };
+
+void enqueue_pass_sweep(csmc_handle *h, const SweepOp &op) {
+    switch (op.upd) {
+    case UPD_OR: enqueue_sweep<UPD_OR>(h, op.ctr_off, op.device_ctr); break;
+    case UPD_DET: enqueue_sweep<UPD_DET>(h, op.ctr_off, op.device_ctr); break;
+    case UPD_METRO: enqueue_sweep<UPD_METRO>(h, op.ctr_off, op.device_ctr); break;
+    default: enqueue_sweep<UPD_CONE>(h, op.ctr_off, op.device_ctr); break;
+    }
+}
+
+// consecutive sweeps.  With the fused kernels they run in pairs (d_spins -> alt -> d_spins) so the state is
+// back in d_spins at the end; an odd sweep out runs on the per-colour pass kernels (in place) first.
+// fused == true requires a successful fused_ready(h) beforehand.
+void enqueue_sweep_seq(csmc_handle *h, const SweepOp *seq, int n, bool fused) {
+    int i = 0;
+    if (fused && n >= 2) {
+        if (n & 1) enqueue_pass_sweep(h, seq[i++]);
+        for (; i < n; i += 2) {
+            launch_fused(h, seq[i].upd, h->d_spins, h->d_spins_alt, sweep_args(h, seq[i].ctr_off, seq[i].device_ctr));
+            launch_fused(h, seq[i + 1].upd, h->d_spins_alt, h->d_spins, sweep_args(h, seq[i + 1].ctr_off, seq[i + 1].device_ctr));
+        }
+    } else {
+        for (; i < n; ++i) enqueue_pass_sweep(h, seq[i]);
+    }
+}
+
 void enqueue_metropolis(csmc_handle *h, bool cone) {
     if (cone) enqueue_sweep<UPD_CONE>(h, h->metro_ctr); else enqueue_sweep<UPD_METRO>(h, h->metro_ctr);
     h->metro_ctr++;
@@ -231,12 +292,14 @@ struct JitModule {
     cudaLibrary_t lib = nullptr;
     std::vector<cudaKernel_t> sweep[4], energy;
     cudaKernel_t resident = nullptr;
+    cudaKernel_t fused[4] = {nullptr, nullptr, nullptr, nullptr};
     JitPlan plan;
     bool pdl = false;
 };
 
 // generate + compile (or fetch from the per-process cache) + load the kernels specialised for hm
-std::string load_jit_module(const HostModel &hm, bool pdl, JitModule &m) {
+std::string load_jit_module(const HostModel &hm, bool pdl, JitModule &m, bool want_fused = false) {
+    m.plan.want_fused = want_fused;
     std::string err, log;
     std::vector<char> cubin;
     try {
@@ -281,6 +344,16 @@ std::string load_jit_module(const HostModel &hm, bool pdl, JitModule &m) {
             m.resident = nullptr;     // pass kernels still work
         }
     }
+    if (m.plan.fused) {
+        for (int u = 0; u < 4 && m.plan.fused; ++u) {
+            const std::string nm = "csmc_fused_u" + std::to_string(u);
+            if (cudaLibraryGetKernel(&m.fused[u], m.lib, nm.c_str()) != cudaSuccess ||
+                cudaFuncSetAttribute((const void *)m.fused[u], cudaFuncAttributeMaxDynamicSharedMemorySize, m.plan.fused_smem) != cudaSuccess) {
+                cudaGetLastError();
+                m.plan.fused = false;   // pass kernels still work
+            }
+        }
+    }
     m.pdl = pdl;
     return "";
 }
@@ -297,6 +370,7 @@ void install_jit_module(csmc_handle *h, const JitModule &m) {
     for (int u = 0; u < 4; ++u) h->jit_sweep[u] = m.sweep[u];
     h->jit_energy = m.energy;
     h->jit_resident = m.resident;
+    for (int u = 0; u < 4; ++u) h->jit_fused[u] = m.fused[u];
     h->jit_plan = m.plan;
     h->jit_pdl = m.pdl;
     h->jit = true;
@@ -314,7 +388,7 @@ std::string build_jit(csmc_handle *h) {
         return h->jit_note;
     }
     JitModule m;
-    const std::string err = load_jit_module(hm, (h->flags & CSMC_FLAG_PDL) != 0, m);
+    const std::string err = load_jit_module(hm, (h->flags & CSMC_FLAG_PDL) != 0, m, (h->flags & CSMC_FLAG_FUSED) != 0);
     if (err.empty()) install_jit_module(h, m);
     else {
         if (m.lib) cudaLibraryUnload(m.lib);
@@ -541,10 +615,11 @@ static int autotune_pdl(csmc_handle *h) {
     if (!h->jit || (h->flags & (CSMC_FLAG_PDL | CSMC_FLAG_NO_AUTOTUNE | CSMC_FLAG_NO_GRAPH)) || h->hm.self_loop) return CSMC_OK;
     if (h->jit_resident && h->hm.N <= 4096 && !(h->flags & CSMC_FLAG_NO_RESIDENT)) return CSMC_OK;   // sweeps run on the resident kernel
     JitModule other;
-    if (!load_jit_module(h->hm, true, other).empty()) { if (other.lib) cudaLibraryUnload(other.lib); cudaGetLastError(); return CSMC_OK; }
+    if (!load_jit_module(h->hm, true, other, (h->flags & CSMC_FLAG_FUSED) != 0).empty()) { if (other.lib) cudaLibraryUnload(other.lib); cudaGetLastError(); return CSMC_OK; }
     JitModule base;
     base.lib = h->jit_lib; for (int u = 0; u < 4; ++u) base.sweep[u] = h->jit_sweep[u];
     base.energy = h->jit_energy; base.resident = h->jit_resident; base.plan = h->jit_plan; base.pdl = false;
+    for (int u = 0; u < 4; ++u) base.fused[u] = h->jit_fused[u];
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     const int npad = h->hm.npad;
@@ -603,7 +678,7 @@ int32_t csmc_destroy(csmc_handle *h) {
     if (h->jit_lib) cudaLibraryUnload(h->jit_lib);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     free_pt(h);
-    cudaFree(h->d_spins); cudaFree(h->d_stage); cudaFree(h->d_out); cudaFree(h->d_nbr); cudaFree(h->d_ref_of_pos);
+    cudaFree(h->d_spins); cudaFree(h->d_spins_alt); cudaFree(h->d_stage); cudaFree(h->d_out); cudaFree(h->d_nbr); cudaFree(h->d_ref_of_pos);
     cudaFree(h->d_beta); cudaFree(h->d_sigma); cudaFree(h->d_acc); cudaFree(h->d_acc_prev); cudaFree(h->d_ctr);
     cudaFree(h->d_partials); cudaFree(h->d_meas);
     cudaFree(h->d_ssf_theta); cudaFree(h->d_ssf_phib); cudaFree(h->d_ssf_partial); cudaFree(h->d_ssf_out); cudaFree(h->d_ssf_sum);
@@ -641,7 +716,9 @@ int32_t csmc_jit_check(const csmc_model *model, int32_t compile, char *source, i
     try {
         e = build_host_model(model, 0, hm);
         if (e.empty() && !hm.structured) e = "model has no periodic colouring pattern: explicit-table kernels only";
-        if (e.empty()) src = jit_generate_source(hm);
+        JitPlan plan;
+        plan.want_fused = true;   // the build check covers the experimental fused kernels too
+        if (e.empty()) src = jit_generate_source(hm, false, &plan);
         if (e.empty() && compile) {
             std::vector<char> cubin;
             e = jit_compile(src, cubin, lg);
@@ -856,21 +933,21 @@ static int build_cycle_graph(csmc_handle *h, int orc, int mc) {
     if (h->cycle_graph) { cudaGraphExecDestroy(h->cycle_graph); h->cycle_graph = nullptr; }
     cudaGraph_t graph = nullptr;
     const long long before = h->launches;
+    const bool fused = fused_ready(h);
+    std::vector<SweepOp> seq;
+    for (int s = 0; s < orc; ++s) seq.push_back({UPD_OR, 0ULL, false});
+    for (int s = 0; s < mc; ++s) seq.push_back({UPD_METRO, (unsigned long long)s, true});
     CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-    for (int s = 0; s < orc; ++s) enqueue_sweep<UPD_OR>(h);
-    for (int s = 0; s < mc; ++s) enqueue_sweep<UPD_METRO>(h, (unsigned long long)s, true);
+    enqueue_sweep_seq(h, seq.data(), (int)seq.size(), fused);
     if (mc > 0) { k_add_u64<<<1, 1, 0, h->stream>>>(h->d_ctr, (unsigned long long)mc); h->launches++; }
     CK(cudaStreamEndCapture(h->stream, &graph));
+    h->cycle_launches = h->launches - before;
     h->launches = before;  // capture enqueues nothing
     cudaError_t e = cudaGraphInstantiate(&h->cycle_graph, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) return fail(h, CSMC_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
     h->cycle_or = orc; h->cycle_metro = mc;
     return CSMC_OK;
-}
-
-static long long cycle_launches(const csmc_handle *h, int orc, int mc) {
-    return (long long)(orc + mc) * h->hm.n_colours + (mc > 0 ? 1 : 0);
 }
 
 int32_t csmc_cycles_async(csmc_handle *h, int64_t n_cycles, int32_t orc, int32_t mc) {
@@ -888,9 +965,14 @@ int32_t csmc_cycles_async(csmc_handle *h, int64_t n_cycles, int32_t orc, int32_t
         return CSMC_OK;
     }
     if (h->flags & CSMC_FLAG_NO_GRAPH) {
+        const bool fused = fused_ready(h);
+        std::vector<SweepOp> seq;
         for (int64_t c = 0; c < n_cycles; ++c) {
-            for (int s = 0; s < orc; ++s) enqueue_sweep<UPD_OR>(h);
-            for (int s = 0; s < mc; ++s) enqueue_metropolis(h, false);
+            seq.clear();
+            for (int s = 0; s < orc; ++s) seq.push_back({UPD_OR, 0ULL, false});
+            for (int s = 0; s < mc; ++s) seq.push_back({UPD_METRO, h->metro_ctr + s, false});
+            enqueue_sweep_seq(h, seq.data(), (int)seq.size(), fused);
+            h->metro_ctr += mc;
         }
         CK(cudaGetLastError());
         return CSMC_OK;
@@ -900,7 +982,7 @@ int32_t csmc_cycles_async(csmc_handle *h, int64_t n_cycles, int32_t orc, int32_t
     int rc = build_cycle_graph(h, orc, mc); if (rc) return rc;
     for (int64_t c = 0; c < n_cycles; ++c) CK(cudaGraphLaunch(h->cycle_graph, h->stream));
     h->metro_ctr += (unsigned long long)n_cycles * mc;
-    h->launches += n_cycles * cycle_launches(h, orc, mc);
+    h->launches += n_cycles * h->cycle_launches;
     CK(cudaGetLastError());
     return CSMC_OK;
 }
@@ -908,8 +990,10 @@ int32_t csmc_cycles_async(csmc_handle *h, int64_t n_cycles, int32_t orc, int32_t
 // n consecutive overrelaxation sweeps: one graph replay instead of 2*n*colours launches
 static int enqueue_or_block(csmc_handle *h, int n) {
     if (n <= 0) return CSMC_OK;
+    const bool fused = fused_ready(h);
+    const std::vector<SweepOp> seq((size_t)n, SweepOp{UPD_OR, 0ULL, false});
     if ((h->flags & CSMC_FLAG_NO_GRAPH) || n < 2) {
-        for (int s = 0; s < n; ++s) enqueue_sweep<UPD_OR>(h);
+        enqueue_sweep_seq(h, seq.data(), n, fused);
         return CSMC_OK;
     }
     auto it = h->or_graphs.find(n);
@@ -917,8 +1001,9 @@ static int enqueue_or_block(csmc_handle *h, int n) {
         cudaGraph_t graph = nullptr;
         const long long before = h->launches;
         CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-        for (int s = 0; s < n; ++s) enqueue_sweep<UPD_OR>(h);
+        enqueue_sweep_seq(h, seq.data(), n, fused);
         CK(cudaStreamEndCapture(h->stream, &graph));
+        h->or_graph_launches[n] = h->launches - before;
         h->launches = before;
         cudaGraphExec_t exec = nullptr;
         cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
@@ -928,7 +1013,7 @@ static int enqueue_or_block(csmc_handle *h, int n) {
         it = h->or_graphs.emplace(n, exec).first;
     }
     CK(cudaGraphLaunch(it->second, h->stream));
-    h->launches += (long long)n * h->hm.n_colours;
+    h->launches += h->or_graph_launches[n];
     return CSMC_OK;
 }
 

@@ -111,7 +111,14 @@ std::string build_host_model(const csmc_model *m, int flags, HostModel &out);
 void reference_tables(const csmc_model *m, int64_t *bil, int64_t *cub, int64_t *quar);
 
 // runtime specialisation (jit.cpp): model -> CUDA C++ source -> sm_100a cubin (NVRTC); "" on success
-struct JitPlan { std::vector<int> tiles, groups, groups_metro; bool resident = false; int sweep_tpb = 256; };   // per colour: grid.x (CTA tiles), grid.y (class groups)
+struct JitPlan {
+    std::vector<int> tiles, groups, groups_metro;
+    bool resident = false;
+    int sweep_tpb = 256;
+    bool want_fused = false;     // in: also generate the fused full-sweep kernels (CSMC_FLAG_FUSED)
+    bool fused = false;          // full-sweep kernel with shared-memory tiles (two-colour periodic models)
+    int fused_tiles = 0, fused_smem = 0, fused_tpb = 256;
+};   // per colour: grid.x (CTA tiles), grid.y (class groups)
 std::string jit_generate_source(const HostModel &hm, bool pdl = false, JitPlan *plan = nullptr);
 std::string jit_compile(const std::string &src, std::vector<char> &cubin, std::string &log);
 

@@ -4,6 +4,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <stdexcept>
 #include <cstdio>
@@ -35,9 +36,13 @@ int pow2_floor(int v) { int p = 1; while (2 * p <= v) p *= 2; return p; }
 int pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
 int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
+struct LiveSlot { const HostTerm *t; int slot; int bit; int part; };
+
 struct Gen {
     const HostModel &hm;
     std::ostringstream o;
+    std::vector<std::vector<LiveSlot>> seg_live;   // per segment: live interaction slots (filled by segment())
+    std::vector<int> seg_preload;             // per segment: neighbours preloaded into registers
     std::vector<int> seg_split;               // per segment: warps a site's slots are split over (1, 2, 4)
     std::vector<double> ktab;                 // coefficients placed in the constant bank
     std::map<uint64_t, int> kslot;
@@ -92,8 +97,7 @@ struct Gen {
         const HostSeg &hs = hm.segs[s];
         const int b = hs.basis;
         // which terms are live (some non-zero coefficient, every neighbour class exists)
-        struct Live { const HostTerm *t; int slot; int bit; int part; };
-        std::vector<Live> live;
+        std::vector<LiveSlot> live;
         int nnb = 0;
         for (const auto &t : hm.basis_terms[b]) {
             const double *C = hm.coefs.data() + t.coef;
@@ -138,6 +142,9 @@ struct Gen {
         }
         seg_split.resize(hm.segs.size(), 1);
         seg_split[s] = SP;
+        seg_live.resize(hm.segs.size());
+        seg_live[s] = live;
+        seg_preload.resize(hm.segs.size(), 1);
 
         o << "struct Seg" << s << " {\n";
         o << "    static constexpr int START = " << hs.start << ", COUNT = " << hs.count << ", NNB = " << nnb << ", SP = " << SP << ";\n";
@@ -156,51 +163,60 @@ struct Gen {
           << " + (m1 * " << hs.P[1] << " + " << hs.r[1] << ")) * " << hm.L[2] << " + (m2 * " << hs.P[2] << " + " << hs.r[2] << "));\n    }\n";
         static const int preload_max = std::getenv("CSMC_JIT_PRELOAD_MAX") ? std::atoi(std::getenv("CSMC_JIT_PRELOAD_MAX")) : 64;
         const bool preload = nnb <= preload_max;
+        seg_preload[s] = preload ? 1 : 0;
         o << "    static constexpr bool PRELOAD = " << (preload ? "true" : "false") << ";\n";
         static const bool staged = !(std::getenv("CSMC_JIT_CONTRACT") && std::string(std::getenv("CSMC_JIT_CONTRACT")) == "outer");
+        // sum_k x_k * y_k (+ init) as an explicit fma chain: the rounding order is fixed by the generator, so
+        // the same term rounds identically in every kernel it is inlined into
+        auto chain = [](const std::vector<std::pair<std::string, std::string>> &xy, const std::string &init) {
+            std::string e = init;
+            for (const auto &p : xy) e = e.empty() ? p.first + " * " + p.second : "fma(" + p.first + ", " + p.second + ", " + e + ")";
+            return e;
+        };
+        using Terms = std::vector<std::pair<std::string, std::string>>;
         auto emit_accumulate = [&](const HostTerm &t) {
             const double *C = hm.coefs.data() + t.coef;
             if (t.kind == 2) {
                 for (int a = 0; a < 3; ++a) {
-                    std::string e;
+                    Terms e;
                     for (int c = 0; c < 3; ++c)
-                        if (C[3 * a + c] != 0.0) e += (e.empty() ? "" : " + ") + coef(C[3 * a + c]) + " * p" + std::to_string(c);
-                    if (!e.empty()) o << "        a" << a << " += " << e << ";\n";
+                        if (C[3 * a + c] != 0.0) e.push_back({coef(C[3 * a + c]), "p" + std::to_string(c)});
+                    if (!e.empty()) o << "        a" << a << " = " << chain(e, "a" + std::to_string(a)) << ";\n";
                 }
             } else if (staged && t.kind == 3) {
                 // b_a += sum_b (sum_c C[a,b,c] q_c) p_b : innermost index first, few live temporaries
                 for (int a = 0; a < 3; ++a) {
-                    std::string outer;
+                    Terms outer;
                     for (int bb = 0; bb < 3; ++bb) {
-                        std::string inner;
+                        Terms inner;
                         for (int c = 0; c < 3; ++c)
-                            if (C[a * 9 + bb * 3 + c] != 0.0) inner += (inner.empty() ? "" : " + ") + coef(C[a * 9 + bb * 3 + c]) + " * q" + std::to_string(c);
-                        if (!inner.empty()) outer += (outer.empty() ? "" : " + ") + std::string("(") + inner + ") * p" + std::to_string(bb);
+                            if (C[a * 9 + bb * 3 + c] != 0.0) inner.push_back({coef(C[a * 9 + bb * 3 + c]), "q" + std::to_string(c)});
+                        if (!inner.empty()) outer.push_back({"(" + chain(inner, "") + ")", "p" + std::to_string(bb)});
                     }
-                    if (!outer.empty()) o << "        b" << a << " += " << outer << ";\n";
+                    if (!outer.empty()) o << "        b" << a << " = " << chain(outer, "b" + std::to_string(a)) << ";\n";
                 }
             } else if (staged && t.kind == 4) {
                 // c_a += sum_b (sum_c (sum_d R[a,b,c,d] w_d) q_c) p_b
                 for (int a = 0; a < 3; ++a) {
-                    std::string sum_b;
+                    Terms sum_b;
                     for (int bb = 0; bb < 3; ++bb) {
-                        std::string sum_c;
+                        Terms sum_c;
                         for (int c = 0; c < 3; ++c) {
-                            std::string sum_d;
+                            Terms sum_d;
                             for (int d = 0; d < 3; ++d)
                                 if (C[a * 27 + bb * 9 + c * 3 + d] != 0.0)
-                                    sum_d += (sum_d.empty() ? "" : " + ") + coef(C[a * 27 + bb * 9 + c * 3 + d]) + " * w" + std::to_string(d);
-                            if (!sum_d.empty()) sum_c += (sum_c.empty() ? "" : " + ") + std::string("(") + sum_d + ") * q" + std::to_string(c);
+                                    sum_d.push_back({coef(C[a * 27 + bb * 9 + c * 3 + d]), "w" + std::to_string(d)});
+                            if (!sum_d.empty()) sum_c.push_back({"(" + chain(sum_d, "") + ")", "q" + std::to_string(c)});
                         }
                         if (!sum_c.empty()) {
-                            o << "        { const double t" << bb << " = " << sum_c << ";";
-                            sum_b += (sum_b.empty() ? "" : " + ") + std::string("t") + std::to_string(bb) + " * p" + std::to_string(bb);
+                            o << "        { const double t" << bb << " = " << chain(sum_c, "") << ";";
+                            sum_b.push_back({"t" + std::to_string(bb), "p" + std::to_string(bb)});
                         } else {
                             o << "        {";
                         }
                         o << "\n";
                     }
-                    if (!sum_b.empty()) o << "        c" << a << " += " << sum_b << ";\n";
+                    if (!sum_b.empty()) o << "        c" << a << " = " << chain(sum_b, "c" + std::to_string(a)) << ";\n";
                     o << "        }}}\n";
                 }
             } else if (t.kind == 3) {
@@ -293,6 +309,182 @@ struct Gen {
                 o << "      }\n";
             }
         o << "    }\n};\n\n";
+    }
+
+    // neighbour class and supercell shift of neighbour k of term t seen from class hs
+    int nbr_class(const HostSeg &hs, const HostTerm &t, int k, int (&delta)[MAXD]) {
+        int r2[MAXD] = {0, 0, 0};
+        for (int d = 0; d < MAXD; ++d) delta[d] = 0;
+        for (int d = 0; d < hm.D; ++d) {
+            r2[d] = posmod(hs.r[d] + t.off[k][d], hm.P[d]);
+            delta[d] = floordiv(hs.r[d] + t.off[k][d], hm.P[d]);
+        }
+        auto it = seg_of_class.find(std::make_tuple(t.nb_basis[k], r2[0], r2[1], r2[2]));
+        return it == seg_of_class.end() ? -1 : it->second;
+    }
+
+    // ---- fused full-sweep kernel (two-colour periodic models) ------------------------------------------
+    // One launch = one full sweep.  A CTA loads a tile of supercells plus the halo it needs into shared
+    // memory, updates colour 0 on the tile extended by the ring colour 1 will read (recomputed by the
+    // neighbouring CTAs with identical arithmetic, so identical values), then colour 1 on the tile, and
+    // writes the tile to the *other* spin buffer (ping-pong: CTAs never read what another CTA writes in
+    // the same launch).  Traffic per sweep: ~1.2 x 24 B read + 24 B written per site instead of
+    // 2 x 72 B, and half the launches.
+    bool emit_fused(JitPlan &plan) {
+        plan.fused = false;
+        if (!plan.want_fused || !hm.periodic || hm.n_colours != 2 || hm.D > 2) return false;
+        const int nq = (int)hm.segs.size();
+        for (int q = 0; q < nq; ++q) if (!seg_preload[q] || seg_split[q] != 1) return false;
+        int W[MAXD] = {1, 1, 1}, NT[MAXD] = {1, 1, 1};
+        int target[MAXD] = {hm.D == 1 ? 1024 : 16, 32, 1};
+        int tpb = 256;
+        if (const char *e = std::getenv("CSMC_JIT_FUSED_TILE")) std::sscanf(e, "%dx%d", &target[0], &target[1]);
+        if (const char *e = std::getenv("CSMC_JIT_FUSED_TPB")) tpb = std::atoi(e);
+        plan.fused_tpb = tpb;
+        for (int d = 0; d < hm.D; ++d) {
+            const int M = hm.segs[0].M[d];
+            for (int q = 0; q < nq; ++q) if (hm.segs[q].M[d] != M) return false;
+            int w = std::min(target[d], M);
+            while (w > 1 && M % w != 0) --w;
+            if (w < 4) return false;
+            W[d] = w; NT[d] = M / w;
+        }
+        // extents: ext = update region of colour-0 classes beyond the tile, halo = data region
+        std::vector<std::array<int, 2 * MAXD>> ext(nq), halo(nq);
+        for (auto &e : ext) e.fill(0);
+        for (auto &e : halo) e.fill(0);
+        for (int q1 = 0; q1 < nq; ++q1) {
+            if (hm.segs[q1].colour != 1) continue;
+            for (const auto &lv : seg_live[q1])
+                for (int k = 0; k < lv.t->kind - 1; ++k) {
+                    int dl[MAXD];
+                    const int q = nbr_class(hm.segs[q1], *lv.t, k, dl);
+                    if (q < 0 || hm.segs[q].colour != 0) return false;
+                    for (int d = 0; d < hm.D; ++d) {
+                        if (std::abs(dl[d]) > 2) return false;
+                        if (dl[d] < 0) ext[q][2 * d] = std::max(ext[q][2 * d], -dl[d]);
+                        if (dl[d] > 0) ext[q][2 * d + 1] = std::max(ext[q][2 * d + 1], dl[d]);
+                    }
+                }
+        }
+        for (int q = 0; q < nq; ++q) halo[q] = ext[q];
+        for (int q0 = 0; q0 < nq; ++q0) {
+            if (hm.segs[q0].colour != 0) continue;
+            for (const auto &lv : seg_live[q0])
+                for (int k = 0; k < lv.t->kind - 1; ++k) {
+                    int dl[MAXD];
+                    const int q = nbr_class(hm.segs[q0], *lv.t, k, dl);
+                    if (q < 0 || hm.segs[q].colour != 1) return false;
+                    for (int d = 0; d < hm.D; ++d) {
+                        if (std::abs(dl[d]) > 2) return false;
+                        halo[q][2 * d] = std::max(halo[q][2 * d], ext[q0][2 * d] - dl[d]);
+                        halo[q][2 * d + 1] = std::max(halo[q][2 * d + 1], ext[q0][2 * d + 1] + dl[d]);
+                    }
+                }
+        }
+        for (int q = 0; q < nq; ++q)
+            for (int d = 0; d < hm.D; ++d)
+                if (std::max(halo[q][2 * d], halo[q][2 * d + 1]) > hm.segs[q].M[d]) return false;   // single wrap-around only
+        // shared-memory layout
+        std::vector<int> shb(nq, 0);
+        std::vector<std::array<int, MAXD>> S(nq);
+        int total = 0;
+        for (int q = 0; q < nq; ++q) {
+            int n = 1;
+            for (int d = 0; d < MAXD; ++d) { S[q][d] = d < hm.D ? W[d] + halo[q][2 * d] + halo[q][2 * d + 1] : 1; n *= S[q][d]; }
+            shb[q] = total;
+            total += (n + 1) / 2 * 2;
+        }
+        const size_t smem = (size_t)3 * total * sizeof(double);
+        if (smem > 100 * 1024) return false;
+        plan.fused = true;
+        plan.fused_tiles = NT[0] * NT[1] * NT[2];
+        plan.fused_smem = (int)smem;
+
+        auto shpos = [&](int q, const std::string (&l)[MAXD]) {
+            std::ostringstream e;
+            e << shb[q] << " + ((" << l[0] << " + " << halo[q][0] << ") * " << S[q][1] << " + (" << l[1] << " + " << halo[q][2] << ")) * " << S[q][2]
+              << " + (" << l[2] << " + " << halo[q][4] << ")";
+            return e.str();
+        };
+        o << "#define SH_TOTAL " << total << "\n";
+        // per class: tile-local neighbour loads + thin wrappers
+        for (int q = 0; q < nq; ++q) {
+            const HostSeg &hs = hm.segs[q];
+            o << "struct Tile" << q << " {\n";
+            o << "    static __device__ __forceinline__ int pos(int l0, int l1, int l2) { return " << shpos(q, {"l0", "l1", "l2"}) << "; }\n";
+            o << "    static __device__ __forceinline__ void load(const double *__restrict__ shx, const double *__restrict__ shy, const double *__restrict__ shz,\n"
+                 "            int l0, int l1, int l2, double (&nb)[3 * Seg" << q << "::NNB + 1]) {\n";
+            for (const auto &lv : seg_live[q])
+                for (int k = 0; k < lv.t->kind - 1; ++k) {
+                    int dl[MAXD];
+                    const int qn = nbr_class(hs, *lv.t, k, dl);
+                    const std::string l[MAXD] = {"l0 + (" + std::to_string(dl[0]) + ")", "l1 + (" + std::to_string(dl[1]) + ")", "l2 + (" + std::to_string(dl[2]) + ")"};
+                    const int base = 3 * (lv.slot + k);
+                    o << "        { const int j = " << shpos(qn, l) << "; nb[" << base << "] = shx[j]; nb[" << base + 1 << "] = shy[j]; nb[" << base + 2 << "] = shz[j]; }\n";
+                }
+            o << "    }\n};\n";
+        }
+        for (int u = 0; u < 4; ++u) {
+            o << "extern \"C\" __global__ void __launch_bounds__(" << tpb << ") csmc_fused_u" << u << "(const double *__restrict__ in, double *__restrict__ out, const SweepArgs a) {\n";
+            o << "    extern __shared__ double sh[];\n    double *shx = sh, *shy = sh + SH_TOTAL, *shz = sh + 2 * SH_TOTAL;\n";
+            o << "    const int rep = blockIdx.z;\n    int t = blockIdx.x;\n";
+            o << "    const int t2 = t % " << NT[2] << "; t /= " << NT[2] << "; const int t1 = t % " << NT[1] << "; const int t0 = t / " << NT[1] << ";\n";
+            o << "    const int o0 = t0 * " << W[0] << ", o1 = t1 * " << W[1] << ", o2 = t2 * " << W[2] << ";\n";
+            o << "    const double *gx = in + (size_t)rep * (3ull * NPAD), *gy = gx + NPAD, *gz = gy + NPAD;\n";
+            // load phase
+            for (int q = 0; q < nq; ++q) {
+                const HostSeg &hs = hm.segs[q];
+                const int n = S[q][0] * S[q][1] * S[q][2];
+                o << "    for (int e = threadIdx.x; e < " << n << "; e += " << tpb << ") {\n";
+                o << "        const int e2 = e % " << S[q][2] << ", e1 = (e / " << S[q][2] << ") % " << S[q][1] << ", e0 = e / " << (S[q][2] * S[q][1]) << ";\n";
+                o << "        int m0 = o0 + e0 - " << halo[q][0] << ", m1 = o1 + e1 - " << halo[q][2] << ", m2 = o2 + e2 - " << halo[q][4] << ";\n";
+                for (int d = 0; d < hm.D; ++d)
+                    o << "        m" << d << " = m" << d << " < 0 ? m" << d << " + " << hs.M[d] << " : (m" << d << " >= " << hs.M[d] << " ? m" << d << " - " << hs.M[d] << " : m" << d << ");\n";
+                o << "        const int g = Seg" << q << "::pos(m0, m1, m2), j = " << shb[q] << " + e;\n";
+                o << "        shx[j] = __ldg(gx + g); shy[j] = __ldg(gy + g); shz[j] = __ldg(gz + g);\n    }\n";
+            }
+            o << "    __syncthreads();\n    int n_acc = 0;\n";
+            // update phases
+            for (int c = 0; c < 2; ++c) {
+                for (int q = 0; q < nq; ++q) {
+                    if (hm.segs[q].colour != c) continue;
+                    const HostSeg &hs = hm.segs[q];
+                    int U[MAXD], lo[MAXD];
+                    for (int d = 0; d < MAXD; ++d) { lo[d] = (c == 0 && d < hm.D) ? ext[q][2 * d] : 0; U[d] = d < hm.D ? W[d] + lo[d] + ((c == 0) ? ext[q][2 * d + 1] : 0) : 1; }
+                    const int n = U[0] * U[1] * U[2];
+                    o << "    for (int e = threadIdx.x; e < " << n << "; e += " << tpb << ") {\n";
+                    o << "        const int l2 = e % " << U[2] << " - " << lo[2] << ", l1 = (e / " << U[2] << ") % " << U[1] << " - " << lo[1] << ", l0 = e / " << (U[2] * U[1]) << " - " << lo[0] << ";\n";
+                    o << "        Site<Seg" << q << "> d;\n        d.valid = true; d.ok = 0xffffffffu;\n";
+                    o << "        d.m0 = o0 + l0; d.m1 = o1 + l1; d.m2 = o2 + l2;\n";
+                    for (int dd = 0; dd < hm.D; ++dd)
+                        o << "        d.m" << dd << " = d.m" << dd << " < 0 ? d.m" << dd << " + " << hs.M[dd] << " : (d.m" << dd << " >= " << hs.M[dd] << " ? d.m" << dd << " - " << hs.M[dd] << " : d.m" << dd << ");\n";
+                    o << "        d.pos = Tile" << q << "::pos(l0, l1, l2);\n";
+                    o << "        d.s0 = shx[d.pos]; d.s1 = shy[d.pos]; d.s2 = shz[d.pos];\n";
+                    o << "        Tile" << q << "::load(shx, shy, shz, l0, l1, l2, d.nb);\n";
+                    o << "        const bool acc = site_finish_ptr<" << u << ", Seg" << q << ", false, -1>(d, shx, shy, shz, rep, a, 0ULL, 0.0, 0.0, 0.0);\n";
+                    if (c == 0) {
+                        o << "        if (acc && l0 >= 0 && l0 < " << W[0] << " && l1 >= 0 && l1 < " << W[1] << " && l2 >= 0 && l2 < " << W[2] << ") ++n_acc;\n";
+                    } else {
+                        o << "        if (acc) ++n_acc;\n";
+                    }
+                    o << "    }\n";
+                }
+                o << "    __syncthreads();\n";
+            }
+            // store phase
+            o << "    double *hx = out + (size_t)rep * (3ull * NPAD), *hy = hx + NPAD, *hz = hy + NPAD;\n";
+            for (int q = 0; q < nq; ++q) {
+                const int n = W[0] * W[1] * W[2];
+                o << "    for (int e = threadIdx.x; e < " << n << "; e += " << tpb << ") {\n";
+                o << "        const int l2 = e % " << W[2] << ", l1 = (e / " << W[2] << ") % " << W[1] << ", l0 = e / " << (W[2] * W[1]) << ";\n";
+                o << "        const int g = Seg" << q << "::pos(o0 + l0, o1 + l1, o2 + l2), j = Tile" << q << "::pos(l0, l1, l2);\n";
+                o << "        hx[g] = shx[j]; hy[g] = shy[j]; hz[g] = shz[j];\n    }\n";
+            }
+            if (u >= 2) o << "    count_accepted(n_acc, rep, a);\n";
+            o << "}\n";
+        }
+        return true;
     }
 
     std::string run(JitPlan &plan) {
@@ -421,6 +613,7 @@ struct Gen {
             for (int s = s0; s < s1; ++s) o << "    case " << (s - s0) << ": energy_site<Seg" << s << ">(spins, v); break;\n";
             o << "    default: break;\n    }\n    energy_block_reduce(v, partials, n_partials, partial_base);\n}\n";
         }
+        emit_fused(plan);
         // ---- resident kernel: one CTA per replica keeps the whole lattice in shared memory and runs
         // whole sweep schedules (n_cycles x (or_per_cycle OR + metro_per_cycle Metropolis), then det_sweeps
         // deterministic sweeps) with __syncthreads() between colour passes: one launch instead of

@@ -98,11 +98,20 @@ __device__ __forceinline__ void site_load(Site<SEG> &d, const double *spins, int
     }
 }
 
-// PART >= 0: this thread evaluated only the slots of its part; (x0, x1, x2) carries the other parts' sums
-template <int UPD, class SEG, bool NC = true, int PART = -1>
-__device__ __forceinline__ bool site_finish(Site<SEG> &d, double *spins, int rep, const SweepArgs &a, int grep_override = -1,
-                                            unsigned long long ctr_extra = 0ULL, double x0 = 0.0, double x1 = 0.0, double x2 = 0.0) {
-    double *sx = spins + (size_t)rep * (3ull * NPAD), *sy = sx + NPAD, *sz = sy + NPAD;
+// Dot product with the fused-multiply-add order written out: left to the compiler, the contraction of
+// a0*b0 + a1*b1 + a2*b2 depends on the code around it, and the same update inlined into different kernels
+// (per-colour pass, resident, fused sweep) must round identically.
+__device__ __forceinline__ double dot3(double a0, double a1, double a2, double b0, double b1, double b2) {
+    return fma(a2, b2, fma(a1, b1, a0 * b0));
+}
+
+// PART >= 0: this thread evaluated only the slots of its part; (x0, x1, x2) carries the other parts' sums.
+// (sx, sy, sz) are the component arrays d.pos indexes (global memory or a shared-memory tile); prep is the
+// local replica index used for beta / sigma / the Philox stream.
+template <int UPD, class SEG, bool NC, int PART>
+__device__ __forceinline__ bool site_finish_ptr(Site<SEG> &d, double *sx, double *sy, double *sz, int prep, const SweepArgs &a,
+                                                unsigned long long ctr_extra, double x0, double x1, double x2) {
+    const int rep = prep, grep_override = -1;
     bool accepted = false;
     if (d.valid) {
         const int pos = d.pos;
@@ -121,16 +130,16 @@ __device__ __forceinline__ bool site_finish(Site<SEG> &d, double *spins, int rep
             if (UPD == UPD_CONE) {
                 const double sg = a.sigma[grep_override >= 0 ? grep_override : rep];
                 n0 = s0 + sg * n0; n1 = s1 + sg * n1; n2 = s2 + sg * n2;
-                const double nrm = sqrt(n0 * n0 + n1 * n1 + n2 * n2);
+                const double nrm = sqrt(dot3(n0, n1, n2, n0, n1, n2));
                 n0 = n0 / nrm * SPIN_S; n1 = n1 / nrm * SPIN_S; n2 = n2 / nrm * SPIN_S;
             }
         }
         double g0 = 0.0, g1 = 0.0, g2 = 0.0;
         if (UPD == UPD_OR || UPD == UPD_DET) {
             if (SEG::ONSITE) {
-                g0 = 2 * (SEG::O0 * s0 + SEG::O1 * s1 + SEG::O2 * s2);
-                g1 = 2 * (SEG::O3 * s0 + SEG::O4 * s1 + SEG::O5 * s2);
-                g2 = 2 * (SEG::O6 * s0 + SEG::O7 * s1 + SEG::O8 * s2);
+                g0 = 2 * dot3(SEG::O0, SEG::O1, SEG::O2, s0, s1, s2);
+                g1 = 2 * dot3(SEG::O3, SEG::O4, SEG::O5, s0, s1, s2);
+                g2 = 2 * dot3(SEG::O6, SEG::O7, SEG::O8, s0, s1, s2);
             }
         }
         if (SEG::PRELOAD) SEG::template field<PART>(d.nb, d.ok, g0, g1, g2, g0, g1, g2, g0, g1, g2);
@@ -139,21 +148,21 @@ __device__ __forceinline__ bool site_finish(Site<SEG> &d, double *spins, int rep
         const double F0 = g0 - SEG::H0, F1 = g1 - SEG::H1, F2 = g2 - SEG::H2;
         if (UPD == UPD_OR) {
             if (!(F0 == 0.0 && F1 == 0.0 && F2 == 0.0)) {
-                const double proj = 2.0 * (s0 * F0 + s1 * F1 + s2 * F2) / (F0 * F0 + F1 * F1 + F2 * F2);
-                sx[pos] = -s0 + proj * F0; sy[pos] = -s1 + proj * F1; sz[pos] = -s2 + proj * F2;
+                const double proj = 2.0 * dot3(s0, s1, s2, F0, F1, F2) / dot3(F0, F1, F2, F0, F1, F2);
+                sx[pos] = fma(proj, F0, -s0); sy[pos] = fma(proj, F1, -s1); sz[pos] = fma(proj, F2, -s2);
             }
         } else if (UPD == UPD_DET) {
             if (!(F0 == 0.0 && F1 == 0.0 && F2 == 0.0)) {
-                const double nrm = sqrt(F0 * F0 + F1 * F1 + F2 * F2);
+                const double nrm = sqrt(dot3(F0, F1, F2, F0, F1, F2));
                 sx[pos] = -F0 / nrm * SPIN_S; sy[pos] = -F1 / nrm * SPIN_S; sz[pos] = -F2 / nrm * SPIN_S;
             }
         } else {
-            double dE = (n0 - s0) * F0 + (n1 - s1) * F1 + (n2 - s2) * F2;
+            double dE = dot3(n0 - s0, n1 - s1, n2 - s2, F0, F1, F2);
             if (SEG::ONSITE) {
-                const double en = n0 * (SEG::O0 * n0 + SEG::O1 * n1 + SEG::O2 * n2) + n1 * (SEG::O3 * n0 + SEG::O4 * n1 + SEG::O5 * n2) +
-                                  n2 * (SEG::O6 * n0 + SEG::O7 * n1 + SEG::O8 * n2);
-                const double eo = s0 * (SEG::O0 * s0 + SEG::O1 * s1 + SEG::O2 * s2) + s1 * (SEG::O3 * s0 + SEG::O4 * s1 + SEG::O5 * s2) +
-                                  s2 * (SEG::O6 * s0 + SEG::O7 * s1 + SEG::O8 * s2);
+                const double en = dot3(n0, n1, n2, dot3(SEG::O0, SEG::O1, SEG::O2, n0, n1, n2), dot3(SEG::O3, SEG::O4, SEG::O5, n0, n1, n2),
+                                       dot3(SEG::O6, SEG::O7, SEG::O8, n0, n1, n2));
+                const double eo = dot3(s0, s1, s2, dot3(SEG::O0, SEG::O1, SEG::O2, s0, s1, s2), dot3(SEG::O3, SEG::O4, SEG::O5, s0, s1, s2),
+                                       dot3(SEG::O6, SEG::O7, SEG::O8, s0, s1, s2));
                 dE += en - eo;
             }
             accepted = dE < 0.0 || u3 < exp(-dE * a.beta[grep_override >= 0 ? grep_override : rep]);
@@ -161,6 +170,13 @@ __device__ __forceinline__ bool site_finish(Site<SEG> &d, double *spins, int rep
         }
     }
     return accepted;
+}
+
+template <int UPD, class SEG, bool NC = true, int PART = -1>
+__device__ __forceinline__ bool site_finish(Site<SEG> &d, double *spins, int rep, const SweepArgs &a, int grep_override = -1,
+                                            unsigned long long ctr_extra = 0ULL, double x0 = 0.0, double x1 = 0.0, double x2 = 0.0) {
+    double *sx = spins + (size_t)rep * (3ull * NPAD), *sy = sx + NPAD, *sz = sy + NPAD;
+    return site_finish_ptr<UPD, SEG, NC, PART>(d, sx, sy, sz, grep_override >= 0 ? grep_override : rep, a, ctr_extra, x0, x1, x2);
 }
 
 // a non-zero part: evaluate its slots' contribution to the neighbour field of the site

@@ -96,6 +96,12 @@ typedef struct csmc_opts {
 #define CSMC_FLAG_NO_RESIDENT 32  /* never use the resident (one CTA per replica) kernel           */
 #define CSMC_FLAG_NO_AUTOTUNE 64  /* skip the launch-mode autotune at csmc_create (eager path):      \
                                      programmatic dependent launch is then off unless CSMC_FLAG_PDL */
+#define CSMC_FLAG_FUSED 128       /* experimental, off by default: run pairs of consecutive sweeps on   \
+                                     the fused full-sweep kernels (one launch per sweep: tile + halo  \
+                                     in shared memory, both colours, ping-pong spin buffers;          \
+                                     two-colour periodic 1-D/2-D models).  Measured slower than the   \
+                                     per-colour passes on B200 (shared-memory wavefront bound, see    \
+                                     DESIGN.md section 5), kept for that comparison                   */
 /* Default: models whose colouring is a periodic pattern get kernels specialised for that model
  * (unrolled terms, literal coefficients, constant geometry; compiled for sm_100a with NVRTC at
  * csmc_create) when n_sites * n_replicas >= 32768; smaller problems are launch-latency bound and

@@ -9,8 +9,8 @@ import numpy as np
 import pytest
 
 from classicalspinmc.jl_b200 import _lib
-from classicalspinmc.jl_b200._abi import (FLAG_FORCE_GENERIC, FLAG_JIT, FLAG_NO_GRAPH, FLAG_NO_JIT, FLAG_NO_RESIDENT,
-                                          ModelData)
+from classicalspinmc.jl_b200._abi import (FLAG_FORCE_GENERIC, FLAG_FUSED, FLAG_JIT, FLAG_NO_GRAPH, FLAG_NO_JIT,
+                                          FLAG_NO_RESIDENT, ModelData)
 from oracle import oracle as orc
 from tests import models
 
@@ -236,6 +236,66 @@ def test_graph_and_plain_launch_agree():
     # 25 sweeps of chaotic dynamics amplify 1e-16 rounding differences (FMA contraction, sincospi)
     # exponentially; the accept decisions above are the sharp check, this one only bounds the drift
     assert np.abs(outs[0][0] - s).max() <= 1e-4
+
+
+FUSED_CASES = [
+    ("square-16x16-one-tile", lambda: models.square_heisenberg(), (16, 16), 1.0),
+    ("square-96x80-tiles", lambda: models.square_heisenberg(), (96, 80), 1.0),
+    ("square-J2-field-64x128", lambda: models.square_heisenberg(h=(0.1, -0.2, 0.3)), (64, 128), 1.0),
+    ("honeycomb-J3-48x40", lambda: models.kitaev_honeycomb(J3=0.25), (48, 40), 1.0),
+    ("chain-periodic-4096", lambda: models.chain_heisenberg(), (4096,), 1.0),
+]
+
+
+@pytest.mark.parametrize("graph", [0, FLAG_NO_GRAPH], ids=["graph", "plain"])
+@pytest.mark.parametrize("name,builder,shape,S", FUSED_CASES, ids=[c[0] for c in FUSED_CASES])
+def test_fused_full_sweep_kernels_match_pass_kernels(name, builder, shape, S, graph):
+    """CSMC_FLAG_FUSED (experimental): the fused full-sweep kernels (tile + halo in shared memory, colour 0
+    recomputed on the ring, ping-pong buffers) against the per-colour pass kernels from the same state.
+    Metropolis sweeps are bit-identical (same accept decisions); overrelaxation differs by FMA contraction
+    only (<= 1e-12 after one pair of sweeps)."""
+    md = ModelData(builder(), shape, S)
+    if not _lib.plan(md)[2] or _lib.plan(md)[1] != 2:
+        pytest.skip("fused kernels need a two-colour periodic pattern")
+    R = 3
+    T = np.array([0.3, 1.0, 2.5])
+    fused = _lib.Engine(md, n_replicas=R, seed=77, flags=FLAG_JIT | FLAG_NO_RESIDENT | FLAG_FUSED | graph)
+    plain = _lib.Engine(md, n_replicas=R, seed=77, flags=FLAG_JIT | FLAG_NO_RESIDENT | graph)
+    for eng in (fused, plain):
+        eng.randomize(11)
+        eng.set_temperatures(T)
+
+    def spins(eng):
+        return np.stack([eng.get_spins(r) for r in range(R)])
+
+    def step(orc, mc, n=1):
+        counts = []
+        for eng in (fused, plain):
+            l0 = eng.launches
+            eng.cycles_async(n, orc, mc)
+            eng.sync()
+            counts.append(eng.launches - l0)
+        return counts
+
+    bump = 0 if graph else 1                       # device sweep-counter increment inside the graphs
+    assert step(2, 0) == [2, 4]                    # one launch per sweep instead of one per colour
+    assert np.abs(spins(fused) - spins(plain)).max() <= TOL
+    for r in range(R):
+        plain.set_spins(spins(fused)[r], r)
+    assert step(0, 2) == [2 + bump, 4 + bump]
+    assert np.array_equal(spins(fused), spins(plain))
+    assert np.array_equal(fused.accepted(), plain.accepted()) and fused.accepted().min() > 0
+    # odd number of sweeps: the first one runs on the pass kernels, the (OR, Metropolis) pair fused
+    assert step(2, 1) == [2 + 2 + bump, 6 + bump]
+    assert np.abs(spins(fused) - spins(plain)).max() <= 1e-10
+    assert np.abs(fused.accepted() - plain.accepted()).max() <= 2
+    # cone moves with adaptation through csmc_anneal_temperature_cone (OR blocks on the fused kernels)
+    for r in range(R):
+        plain.set_spins(spins(fused)[r], r)
+    out = [eng.anneal_temperature_cone(T, np.array([40.0, 25.0, 60.0]), adapt=True, t_thermalization=4, overrelaxation_rate=2)
+           for eng in (fused, plain)]
+    assert np.abs(out[0][0] - out[1][0]).max() <= 2 and np.abs(out[0][1] - out[1][1]).max() <= 1e-6
+    assert np.abs(spins(fused) - spins(plain)).max() <= 1e-9
 
 
 def test_anneal_temperature_schedule_matches_reference_loop():
