@@ -1,11 +1,11 @@
 """Output files — mirror of src/hdf5.jl's writers/readers (layout in SURVEY.md section 5).
 
-h5py is not available in the build image, so two backends are provided with the same group /
-dataset / attribute names: real HDF5 through ``h5py`` when it can be imported, and otherwise a
-``.npz`` container whose keys are the HDF5 paths (``unit_cell/bilinear/(1,2),(0, -1)`` ...) and whose
-attributes live under ``@attrs/<name>``.  File names keep the reference's ``.h5`` / ``.h5.params``
-suffixes either way (src/monte_carlo.jl:96-99).  The Julia package (julia/ClassicalSpinMC) writes real
-HDF5 through HDF5.jl.
+The files are real HDF5 with the reference's group / dataset / attribute names.  Backend: ``h5py`` when it
+can be imported; otherwise ``minih5`` (this package), a pure-Python writer/reader of the HDF5 1.8-compatible
+subset the reference's files need (superblock v0, old-style groups, contiguous datasets, root attributes) —
+the build image has no HDF5 library at all, see minih5.py for what that implies for validation.  File names
+keep the reference's ``.h5`` / ``.h5.params`` suffixes (src/monte_carlo.jl:96-99).  The Julia package
+(julia/ClassicalSpinMC) writes the same layout through HDF5.jl.
 """
 from __future__ import annotations
 
@@ -14,6 +14,8 @@ import os
 
 import numpy as np
 
+from . import minih5
+
 try:  # pragma: no cover - not installed in the build image
     import h5py
 except Exception:  # noqa: BLE001
@@ -21,32 +23,18 @@ except Exception:  # noqa: BLE001
 
 
 # ---- tiny container abstraction ---------------------------------------------------------------------
-class _NpzFile:
-    """dict-of-arrays stand-in for an HDF5 file: keys are paths, attributes are '@attrs/<name>'."""
-
-    def __init__(self, filename, mode):
-        self.filename, self.mode = filename, mode
-        self.data = {}
-        if mode in ("r", "r+") and os.path.exists(filename):
-            with np.load(filename, allow_pickle=False) as z:
-                self.data = {k: z[k] for k in z.files}
-        elif mode in ("r", "r+"):
-            raise FileNotFoundError(filename)
-
-    def close(self):
-        if self.mode != "r":
-            with open(self.filename, "wb") as f:
-                np.savez(f, **self.data)
+def _is_mini(f):
+    return isinstance(f, minih5.File)
 
 
 def _open(filename, mode):
     if h5py is not None:
         return h5py.File(filename, mode)
-    return _NpzFile(filename, mode)
+    return minih5.File(filename, mode)
 
 
 def _set(f, path, value):
-    if h5py is not None and not isinstance(f, _NpzFile):
+    if not _is_mini(f):
         if path in f:
             del f[path]
         f[path] = value
@@ -55,27 +43,36 @@ def _set(f, path, value):
 
 
 def _get(f, path):
-    if h5py is not None and not isinstance(f, _NpzFile):
+    if not _is_mini(f):
         return f[path][()]
     return f.data[path]
 
 
+def _mkgroup(f, path):
+    """create_group(...): the reference creates its groups even when they stay empty (src/hdf5.jl:37-71)
+    and its reader iterates over them unconditionally (:92-116)."""
+    if not _is_mini(f):
+        f.require_group(path)
+    else:
+        f.groups.add(path.strip("/"))
+
+
 def _set_attr(f, name, value):
-    if h5py is not None and not isinstance(f, _NpzFile):
+    if not _is_mini(f):
         f.attrs[name] = value
     else:
-        f.data["@attrs/" + name] = np.asarray(value)
+        f.data["@attrs/" + name] = value if isinstance(value, (str, bytes)) else np.asarray(value)
 
 
 def _get_attr(f, name):
-    if h5py is not None and not isinstance(f, _NpzFile):
+    if not _is_mini(f):
         return f.attrs[name]
     v = f.data["@attrs/" + name]
-    return v.item() if v.shape == () else v
+    return v.item() if isinstance(v, np.ndarray) and v.shape == () else v
 
 
 def _keys(f, group):
-    if h5py is not None and not isinstance(f, _NpzFile):
+    if not _is_mini(f):
         return list(f[group].keys()) if group in f else []
     pre = group.rstrip("/") + "/"
     return sorted({k[len(pre):].split("/")[0] for k in f.data if k.startswith(pre)})
@@ -90,6 +87,8 @@ def _julia_tuple(t):
 # ---- params file (src/hdf5.jl:36-147) -------------------------------------------------------------------
 def dump_unit_cell(f, uc):
     """src/hdf5.jl:36-76"""
+    for g in ("field", "onsite", "bilinear", "cubic", "quartic"):
+        _mkgroup(f, "unit_cell/" + g)
     _set(f, "unit_cell/lattice_vectors", np.stack(uc.lattice_vectors, axis=1))   # columns = a_i
     _set(f, "unit_cell/basis", np.stack(uc.basis, axis=0))                        # n_basis x D
     for b, vec in uc.field:
