@@ -26,6 +26,9 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     std::string err;
 };
@@ -46,7 +49,11 @@ bool load_nccl() {
     g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(g_nccl.lib, "ncclCommDestroy");
     g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(g_nccl.lib, "ncclAllGather");
     g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(g_nccl.lib, "ncclGetErrorString");
-    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllGather) {
+    g_nccl.Broadcast = (decltype(g_nccl.Broadcast))dlsym(g_nccl.lib, "ncclBroadcast");
+    g_nccl.GroupStart = (decltype(g_nccl.GroupStart))dlsym(g_nccl.lib, "ncclGroupStart");
+    g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))dlsym(g_nccl.lib, "ncclGroupEnd");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllGather || !g_nccl.Broadcast ||
+        !g_nccl.GroupStart || !g_nccl.GroupEnd) {
         g_nccl.err = "libnccl lacks required symbols";
         dlclose(g_nccl.lib); g_nccl.lib = nullptr;
         return false;
@@ -115,6 +122,9 @@ struct csmc_handle {
     // CUDA graphs of n consecutive overrelaxation sweeps (parallel-tempering loop)
     std::map<int, cudaGraphExec_t> or_graphs;
     std::map<int, long long> or_graph_launches;
+    // multi-GPU: replica block of every rank (gathered at csmc_comm_init)
+    std::vector<long long> rank_base, rank_count;
+    bool even_partition = true;
 
     std::string err;
     long long launches = 0;
@@ -460,16 +470,46 @@ void free_pt(csmc_handle *h) {
     cudaFree(h->d_ssf_sum); h->d_ssf_sum = nullptr; h->ssf_probes = 0;
 }
 
-// measurement + gather across ranks into d_meas_all (in place)
-int enqueue_measure_all(csmc_handle *h, bool write_energy) {
-    double *mine = h->d_meas_all + (size_t)h->replica_base * 8;
-    enqueue_measure(h, mine, write_energy);
-    if (h->comm) {
-        if (h->n_slots != h->R * h->n_ranks || h->replica_base != h->rank * h->R)
-            return fail(h, CSMC_ERR_INVALID, "NCCL gather needs equal replica counts per rank and replica_base == rank * n_replicas");
-        CKN(g_nccl.AllGather(mine, h->d_meas_all, (size_t)h->R * 8, ncclFloat64, h->comm, h->stream));
+// the ranks' replica blocks must tile [0, n_slots) in rank order (csmc_comm_init gathered them)
+int check_partition(csmc_handle *h) {
+    if (!h->comm) return CSMC_OK;
+    long long next = 0;
+    for (int g = 0; g < h->n_ranks; ++g) {
+        if (h->rank_base[g] != next)
+            return fail(h, CSMC_ERR_INVALID, "multi-GPU parallel tempering: replica_base of rank " + std::to_string(g) +
+                                                 " must be the sum of the replica counts of the ranks before it");
+        next += h->rank_count[g];
+    }
+    if (next != h->n_slots)
+        return fail(h, CSMC_ERR_INVALID, "multi-GPU parallel tempering: the ranks hold " + std::to_string(next) +
+                                             " replicas but csmc_pt_init was given " + std::to_string(h->n_slots) + " temperatures");
+    return CSMC_OK;
+}
+
+// every rank's 8-double records into d_meas_all on every rank, in place (the per-replica energies of the
+// exchange test, src/monte_carlo.jl:321-343): one ncclAllGather when the ranks hold equally many replicas,
+// otherwise one grouped ncclBroadcast per rank
+int enqueue_gather_meas(csmc_handle *h) {
+    if (!h->comm) return CSMC_OK;
+    if (h->even_partition) {
+        CKN(g_nccl.AllGather(h->d_meas_all + (size_t)h->replica_base * 8, h->d_meas_all, (size_t)h->R * 8, ncclFloat64, h->comm, h->stream));
+    } else {
+        CKN(g_nccl.GroupStart());
+        for (int g = 0; g < h->n_ranks; ++g) {
+            double *blk = h->d_meas_all + (size_t)h->rank_base[g] * 8;
+            ncclResult_t r = g_nccl.Broadcast(blk, blk, (size_t)h->rank_count[g] * 8, ncclFloat64, g, h->comm, h->stream);
+            if (r != 0) { g_nccl.GroupEnd(); CKN(r); }
+        }
+        CKN(g_nccl.GroupEnd());
     }
     return CSMC_OK;
+}
+
+// measurement + gather across ranks into d_meas_all (in place)
+int enqueue_measure_all(csmc_handle *h, bool write_energy) {
+    int rc = check_partition(h); if (rc) return rc;
+    enqueue_measure(h, h->d_meas_all + (size_t)h->replica_base * 8, write_energy);
+    return enqueue_gather_meas(h);
 }
 
 }  // namespace
@@ -1234,6 +1274,25 @@ int32_t csmc_comm_init(csmc_handle *h, int32_t n_ranks, int32_t rank, const uint
     std::memcpy(u.internal, id, 128);
     CKN(g_nccl.CommInitRank(&h->comm, n_ranks, u, rank));
     h->n_ranks = n_ranks; h->rank = rank;
+    // every rank learns every rank's replica block (replica_base, n_replicas)
+    double *d_part = nullptr;
+    CK(dalloc(&d_part, (size_t)2 * n_ranks));
+    const double mine[2] = {(double)h->replica_base, (double)h->R};
+    std::vector<double> part((size_t)2 * n_ranks);
+    cudaError_t ce = cudaMemcpyAsync(d_part + 2 * rank, mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream);
+    ncclResult_t nr = 0;
+    if (ce == cudaSuccess) nr = g_nccl.AllGather(d_part + 2 * rank, d_part, 2, ncclFloat64, h->comm, h->stream);
+    if (ce == cudaSuccess && nr == 0) ce = cudaMemcpyAsync(part.data(), d_part, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, h->stream);
+    if (ce == cudaSuccess && nr == 0) ce = cudaStreamSynchronize(h->stream);
+    cudaFree(d_part);
+    CK(ce);
+    CKN(nr);
+    h->rank_base.resize(n_ranks); h->rank_count.resize(n_ranks);
+    h->even_partition = true;
+    for (int g = 0; g < n_ranks; ++g) {
+        h->rank_base[g] = (long long)part[2 * g]; h->rank_count[g] = (long long)part[2 * g + 1];
+        if (h->rank_count[g] != h->R || h->rank_base[g] != (long long)g * h->R) h->even_partition = false;
+    }
     return CSMC_OK;
 }
 
@@ -1278,13 +1337,9 @@ int32_t csmc_pt_run(csmc_handle *h, const csmc_pt_params *p, int64_t sweep_begin
     PtState st = pt_state(h);
     const int nb = (h->n_slots + 127) / 128;
     const bool resident = use_resident(h, sweep_end - sweep_begin);
-    if (h->comm && (h->n_slots != h->R * h->n_ranks || h->replica_base != h->rank * h->R))
-        return fail(h, CSMC_ERR_INVALID, "NCCL gather needs equal replica counts per rank and replica_base == rank * n_replicas");
+    rc = check_partition(h); if (rc) return rc;
     double *mine = h->d_meas_all + (size_t)h->replica_base * 8;
-    auto gather = [&]() -> int {
-        if (h->comm) CKN(g_nccl.AllGather(mine, h->d_meas_all, (size_t)h->R * 8, ncclFloat64, h->comm, h->stream));
-        return CSMC_OK;
-    };
+    auto gather = [&]() -> int { return enqueue_gather_meas(h); };
     int pending_or = 0;   // overrelaxation sweeps not yet enqueued (flushed as one graph replay)
     // The energies are consumed only by an exchange (same sweep) or by probes before the next Metropolis
     // sweep, so total_energy (src/monte_carlo.jl:305) is evaluated -- and gathered across GPUs -- only at

@@ -237,8 +237,6 @@ def parallel_tempering(mc: MonteCarlo, saveIC=(), alg=None):
     n_slots, R = len(T_all), len(mc.temperatures)
     if n_slots == 1:
         warnings.warn("a single temperature slot; no replica exchanges will occur!")  # :258
-    if comm_size > 1 and len(set(counts)) != 1:
-        raise ValueError("every rank must hold the same number of temperatures")
 
     from . import _lib
     mc._device(n_replicas=R, replica_base=base)

@@ -238,7 +238,10 @@ int32_t csmc_get_accepted(csmc_handle *h, double *accepted, int32_t reset);
  * configurations never move. */
 int32_t csmc_pt_init(csmc_handle *h, int32_t n_slots, const double *T_all);
 /* Multi-GPU: rank 0 calls csmc_comm_unique_id, the host broadcasts the 128 bytes (e.g. with
- * torch.distributed / MPI), every rank calls csmc_comm_init.  Single-GPU jobs skip both. */
+ * torch.distributed / MPI), every rank calls csmc_comm_init.  Single-GPU jobs skip both.
+ * The ranks' replica blocks [replica_base, replica_base + n_replicas) must tile the slots in rank
+ * order; they need not be equally long (equal blocks are gathered with one ncclAllGather, unequal
+ * ones with one grouped ncclBroadcast per rank). */
 int32_t csmc_comm_unique_id(uint8_t id[128]);
 int32_t csmc_comm_init(csmc_handle *h, int32_t n_ranks, int32_t rank, const uint8_t id[128]);
 

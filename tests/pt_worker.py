@@ -25,11 +25,13 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     md = ModelData(models.kitaev_honeycomb(), (8, 8), 1.0)
     lat = orc.OracleLattice(md)
-    R_total = 4 * world
+    # "uneven": the ranks hold different numbers of temperature slots (grouped ncclBroadcast instead of ncclAllGather)
+    per_rank = [3 + 2 * (g % 2) for g in range(world)] if "uneven" in sys.argv[1:] else [4] * world
+    R_total, R = sum(per_rank), per_rank[rank]
     T_all_expected = np.geomspace(0.1, 1.5, R_total)
-    R = R_total // world
-    T_all, base, counts = parallel.gather_temperatures(T_all_expected[rank * R:(rank + 1) * R])
-    assert np.allclose(T_all, T_all_expected) and base == rank * R
+    first = sum(per_rank[:rank])
+    T_all, base, counts = parallel.gather_temperatures(T_all_expected[first:first + R])
+    assert np.allclose(T_all, T_all_expected) and base == first and counts == per_rank
     p = dict(t_thermalization=200, t_measurement=600, probe_rate=20, swap_rate=10, overrelaxation_rate=5)
     seed = 2718
     eng = _lib.Engine(md, n_replicas=R, seed=seed, device=local, replica_base=base)

@@ -19,12 +19,13 @@ def _n_gpus():
         return 0
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_sharded_parallel_tempering_is_bit_identical_to_single_gpu(world):
+@pytest.mark.parametrize("world,split", [(2, "even"), (2, "uneven"), (4, "even"), (8, "even"), (8, "uneven")])
+def test_sharded_parallel_tempering_is_bit_identical_to_single_gpu(world, split):
     if _n_gpus() < world:
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", str(29500 + world), os.path.join(ROOT, "tests", "pt_worker.py")]
+           "--master-addr", "127.0.0.1", "--master-port", str(29500 + world + (20 if split == "uneven" else 0)),
+           os.path.join(ROOT, "tests", "pt_worker.py"), split]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
