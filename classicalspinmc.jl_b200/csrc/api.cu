@@ -277,16 +277,28 @@ void enqueue_measure(csmc_handle *h, double *meas, bool write_energy) {
     h->launches++;
 }
 
-void enqueue_eval(csmc_handle *h, int rep, int what, double *out) {
-    for (int c = 0; c < h->hm.n_colours; ++c) {
+// what == 0: local fields, 1: site energies, into out (reference order).  only_site >= 0 (0-based reference
+// index): evaluate just the block holding that site (single-site queries stay O(1) in the lattice size).
+void enqueue_eval(csmc_handle *h, int rep, int what, double *out, long long only_site = -1) {
+    int c_lo = 0, c_hi = h->hm.n_colours, seg_off = 0, block_off = 0;
+    if (only_site >= 0) {
+        const int pos = h->hm.pos_of_ref[only_site];
+        int s = 0;
+        while (s + 1 < (int)h->hm.segs.size() && !(pos >= h->hm.segs[s].start && pos < h->hm.segs[s].start + h->hm.segs[s].count)) ++s;
+        c_lo = h->hm.segs[s].colour; c_hi = c_lo + 1;
+        seg_off = s - h->hm.colour_seg_begin[c_lo];
+        block_off = (pos - h->hm.segs[s].start) / TPB;
+    }
+    for (int c = c_lo; c < c_hi; ++c) {
         const int nseg = h->hm.colour_seg_begin[c + 1] - h->hm.colour_seg_begin[c];
         dim3 grid(h->pass_blocks[c], nseg, 1), block(TPB);
+        if (only_site >= 0) grid = dim3(1, 1, 1);
         if (h->large) {
-            if (h->hm.structured) k_eval<PassLarge, true><<<grid, block, 0, h->stream>>>(h->pl[c], rep, what, out);
-            else k_eval<PassLarge, false><<<grid, block, 0, h->stream>>>(h->pl[c], rep, what, out);
+            if (h->hm.structured) k_eval<PassLarge, true><<<grid, block, 0, h->stream>>>(h->pl[c], rep, what, out, seg_off, block_off);
+            else k_eval<PassLarge, false><<<grid, block, 0, h->stream>>>(h->pl[c], rep, what, out, seg_off, block_off);
         } else {
-            if (h->hm.structured) k_eval<PassSmall, true><<<grid, block, 0, h->stream>>>(h->ps[c], rep, what, out);
-            else k_eval<PassSmall, false><<<grid, block, 0, h->stream>>>(h->ps[c], rep, what, out);
+            if (h->hm.structured) k_eval<PassSmall, true><<<grid, block, 0, h->stream>>>(h->ps[c], rep, what, out, seg_off, block_off);
+            else k_eval<PassSmall, false><<<grid, block, 0, h->stream>>>(h->ps[c], rep, what, out, seg_off, block_off);
         }
         h->launches++;
     }
@@ -833,7 +845,7 @@ int32_t csmc_local_field(csmc_handle *h, int32_t replica, int64_t site, double o
     if (replica < 0 || replica >= h->R) return fail(h, CSMC_ERR_INVALID, "replica out of range");
     if (site < 1 || site > h->hm.N) return fail(h, CSMC_ERR_INVALID, "site out of range (1-based)");
     CK(cudaSetDevice(h->device));
-    enqueue_eval(h, replica, 0, h->d_out);
+    enqueue_eval(h, replica, 0, h->d_out, site - 1);
     CK(cudaMemcpyAsync(out, h->d_out + 3 * (site - 1), sizeof(double) * 3, cudaMemcpyDeviceToHost, h->stream));
     return finish(h);
 }

@@ -331,10 +331,12 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const double *__restric
 // what == 0: local field H - h (src/hamiltonian.jl:3-67) -> out[N x 3];  what == 1: site energy
 // (src/hamiltonian.jl:139-196) -> out[N]
 template <class P, bool STRUCT>
-__global__ void __launch_bounds__(TPB) k_eval(const __grid_constant__ P p, int rep, int what, double *__restrict__ out) {
-    const DevSeg &seg = p.segs[blockIdx.y];
+__global__ void __launch_bounds__(TPB) k_eval(const __grid_constant__ P p, int rep, int what, double *__restrict__ out,
+                                              int seg_off, int block_off) {
+    // (seg_off, block_off) != 0: single-site queries launch only the block that holds the site
+    const DevSeg &seg = p.segs[blockIdx.y + seg_off];
     int pos, m[MAXD];
-    if (!locate<P, STRUCT>(p, seg, blockIdx.x * TPB + threadIdx.x, pos, m)) return;
+    if (!locate<P, STRUCT>(p, seg, (blockIdx.x + block_off) * TPB + threadIdx.x, pos, m)) return;
     const double *sx = p.spins + (size_t)rep * p.rep_stride, *sy = sx + p.npad, *sz = sy + p.npad;
     const double s0 = sx[pos], s1 = sy[pos], s2 = sz[pos];
     const int ref = __ldg(p.ref_of_pos + pos);

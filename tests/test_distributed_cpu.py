@@ -36,6 +36,13 @@ def _worker(rank, world, port, out_dir):
         T_full = np.geomspace(0.1, 2.0, 3 * world)
         T_all, base, counts = parallel.gather_temperatures(T_full[3 * rank:3 * rank + 3])
         assert np.allclose(T_all, T_full) and base == 3 * rank and counts == [3] * world
+        # unequal blocks (rank g holds 2 + g slots): bases are the running sums
+        per = [2 + g for g in range(world)]
+        T_un = np.geomspace(0.1, 2.0, sum(per))
+        lo = sum(per[:rank])
+        Tu, bu, cu = parallel.gather_temperatures(T_un[lo:lo + per[rank]])
+        assert np.allclose(Tu, T_un) and bu == lo and cu == per
+        assert [parallel.owner_of_replica(r, cu) for r in range(sum(per))] == [g for g in range(world) for _ in range(per[g])]
         # NCCL unique-id bootstrap: rank 0 creates, everyone receives the same 128 bytes
         uid = parallel.broadcast_unique_id(lambda: bytes(range(128)))
         assert uid == bytes(range(128))
