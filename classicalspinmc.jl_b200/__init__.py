@@ -15,7 +15,9 @@ from .metropolis import (Metropolis, MetropolisAdaptive, MetropolisConstraint,
                          MetropolisConstraintAdaptive, MetropolisFixedCone)
 from .monte_carlo import (MonteCarlo, MCParamsBuffer, SimulationParameters, deterministic_updates,
                           parallel_tempering, simulated_annealing)
-from .spin_correlations import compute_equal_time_correlations
+from .reciprocal import get_allowed_wavevectors, get_k_path, get_k_plane, reciprocal
+from .spin_correlations import (compute_equal_time_correlations, compute_equal_time_structure_factor,
+                                runEqualTimeStructureFactor)
 from .hdf5 import (create_params_file, overwrite_keys, read_lattice, read_spin_configuration,
                    write_MC_checkpoint)
 
@@ -27,5 +29,6 @@ __all__ = [
     "MonteCarlo", "simulated_annealing", "deterministic_updates", "parallel_tempering",
     "total_energy", "energy_density", "get_local_field",
     "Triangular", "Square", "Honeycomb", "FCC", "Pyrochlore", "BreathingPyrochlore",
-    "compute_equal_time_correlations",
+    "compute_equal_time_correlations", "runEqualTimeStructureFactor", "compute_equal_time_structure_factor",
+    "reciprocal", "get_allowed_wavevectors", "get_k_path", "get_k_plane",
 ]

@@ -57,6 +57,13 @@ def _mkgroup(f, path):
         f.groups.add(path.strip("/"))
 
 
+def _has_group(f, path):
+    if not _is_mini(f):
+        return path in f
+    p = path.strip("/")
+    return p in f.groups or any(k.startswith(p + "/") for k in f.data)
+
+
 def _set_attr(f, name, value):
     if not _is_mini(f):
         f.attrs[name] = value

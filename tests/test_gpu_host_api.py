@@ -161,6 +161,47 @@ def test_parallel_tempering_accumulates_structure_factor(tmp_path):
     f.close()
 
 
+def test_structure_factor_batch_runner_over_configuration_files(tmp_path):
+    """runEqualTimeStructureFactor! + compute_equal_time_structure_factor (src/spin_correlations.jl:48-145):
+    IC_<n>.h5 files in, per-file spin_correlations group, then the average into a destination file; momenta
+    from get_allowed_wavevectors (src/reciprocal.jl:23-29)."""
+    uc = models.kitaev_honeycomb()
+    lat = csm.Lattice((6, 4), uc, 1.0, rng=np.random.default_rng(1))
+    ks = csm.get_allowed_wavevectors(uc, (6, 4))
+    mc = csm.MonteCarlo(0.5, lat, {"t_thermalization": 10}, outpath=str(tmp_path) + "/")
+    ic_dir = str(tmp_path / "IC_0") + "/"
+    os.makedirs(ic_dir)
+    rng = np.random.default_rng(2)
+    expected = []
+    for n in range(3):
+        spins = rng.normal(size=(3, lat.size))
+        spins /= np.linalg.norm(spins, axis=0)
+        h5.write_initial_configuration(ic_dir + f"IC_{n}.h5", mc, spins=spins)
+        lat.spins[:, :] = spins
+        expected.append(csm.compute_equal_time_correlations(lat, ks))
+    csm.runEqualTimeStructureFactor(ic_dir, lat, ks)
+    for n in range(3):
+        f = h5._open(ic_dir + f"IC_{n}.h5", "r")
+        assert np.array_equal(h5._get(f, "spin_correlations/SSF"), expected[n])
+        assert np.array_equal(h5._get(f, "spin_correlations/SSF_momentum"), ks)
+        assert np.array_equal(np.asarray(h5._get(f, "spins")).T, lat.spins) == (n == 2)
+        f.close()
+    # already processed files are skipped unless override is set
+    f = h5._open(ic_dir + "IC_1.h5", "r+")
+    h5.overwrite_keys(f, {"spin_correlations/SSF": np.zeros_like(expected[1])})
+    f.close()
+    csm.runEqualTimeStructureFactor(ic_dir, lat, ks)
+    f = h5._open(ic_dir + "IC_1.h5", "r")
+    assert not np.any(h5._get(f, "spin_correlations/SSF"))
+    f.close()
+    csm.runEqualTimeStructureFactor(ic_dir, lat, ks, True)
+    mean = csm.compute_equal_time_structure_factor(ic_dir, mc.outpath)
+    assert np.allclose(mean, np.mean(expected, axis=0), rtol=1e-13, atol=1e-13)
+    f = h5._open(mc.outpath, "r")
+    assert np.allclose(h5._get(f, "spin_correlations/SSF"), mean) and np.array_equal(h5._get(f, "spin_correlations/SSF_momentum"), ks)
+    f.close()
+
+
 def test_errors_cross_the_abi_as_status_codes():
     L = _lib.lib()
     md = ModelData(models.square_heisenberg(), (4, 4), 1.0)

@@ -189,3 +189,30 @@ def test_unsupported_variants_are_loud():
     mc = csm.MonteCarlo(1.0, lat, {})
     with pytest.raises(NotImplementedError):
         csm.parallel_tempering(mc, alg=csm.MetropolisConstraintAdaptive())
+
+
+def test_reciprocal_space_helpers():
+    """src/reciprocal.jl: b_i . a_j = 2 pi delta_ij; commensurate wavevectors in Iterators.product order
+    (first dimension fastest); k-paths made of allowed wavevectors between high-symmetry points."""
+    for uc in (csm.Triangular(), csm.Honeycomb(), csm.Pyrochlore(), csm.FCC()):
+        b = csm.reciprocal(*uc.lattice_vectors)
+        assert np.allclose(np.stack(b) @ np.stack(uc.lattice_vectors).T, 2 * np.pi * np.eye(uc.D), atol=1e-12)
+    uc = csm.Triangular()
+    b1, b2 = csm.reciprocal(*uc.lattice_vectors)
+    ks = csm.get_allowed_wavevectors(uc, (4, 6))
+    assert ks.shape == (2, 5 * 7)
+    assert np.allclose(ks[:, 1], b1 / 4) and np.allclose(ks[:, 5], b2 / 6) and np.allclose(ks[:, -1], b1 + b2)
+    ks2 = csm.get_allowed_wavevectors(uc, (4, 6), min=-1, max=1)
+    assert ks2.shape == (2, 9 * 13) and np.allclose(ks2[:, 0], -b1 - b2)
+    # every allowed wavevector is a Bloch vector of the 4 x 6 torus: exp(i k . (L_d a_d)) == 1
+    a1, a2 = uc.lattice_vectors
+    assert np.allclose(np.exp(1j * (ks.T @ (4 * a1))), 1.0) and np.allclose(np.exp(1j * (ks.T @ (6 * a2))), 1.0)
+    plane = csm.get_k_plane(uc, (4, 4), min=-1, max=1)
+    assert plane.shape[0] == 2 and np.all(np.abs(plane) <= 2 * np.pi + 1e-6) and plane.shape[1] < 9 * 9
+    hsp = {"G": np.zeros(2), "M": 0.5 * b1, "K": (2 * b1 + b2) / 3}
+    count, kpath = csm.get_k_path(uc, hsp, ["G", "M", "K", "G"], (12, 12))
+    assert count.tolist() == [0, 6, 8, 12] and kpath.shape == (2, 13)
+    assert np.allclose(kpath[:, 0], 0) and np.allclose(kpath[:, 6], hsp["M"]) and np.allclose(kpath[:, 8], hsp["K"])
+    assert np.allclose(kpath[:, 12], 0)
+    line = csm.get_k_path(uc, np.array([1.0, 0.0]), (6, 6))
+    assert line.shape[0] == 2 and line.shape[1] > 0 and np.allclose(line[1], 0.0, atol=1e-9)
