@@ -22,7 +22,7 @@ EXPORTS = [
     "csmc_version", "csmc_last_error", "csmc_create", "csmc_destroy", "csmc_plan", "csmc_reference_tables",
     "csmc_n_sites",
     "csmc_n_replicas", "csmc_n_colours", "csmc_get_colouring", "csmc_is_structured",
-    "csmc_kernel_mode", "csmc_autotune_report", "csmc_jit_check", "csmc_launch_count", "csmc_get_tables", "csmc_set_spins", "csmc_get_spins",
+    "csmc_kernel_mode", "csmc_autotune_report", "csmc_sweep_groups", "csmc_jit_check", "csmc_launch_count", "csmc_get_tables", "csmc_set_spins", "csmc_get_spins",
     "csmc_randomize_spins", "csmc_local_field", "csmc_local_field_all", "csmc_site_energy_all",
     "csmc_total_energy", "csmc_magnetization", "csmc_structure_factor", "csmc_overrelax", "csmc_deterministic",
     "csmc_metropolis", "csmc_metropolis_cone", "csmc_anneal_temperature", "csmc_anneal_temperature_cone", "csmc_set_temperatures",
@@ -73,6 +73,7 @@ def lib():
     L.csmc_launch_count.argtypes = [vp, P(i64)]
     L.csmc_kernel_mode.argtypes = [vp, P(i32)]
     L.csmc_autotune_report.argtypes = [vp, vp, P(i32)]
+    L.csmc_sweep_groups.argtypes = [vp, P(i32), vp]
     L.csmc_jit_check.argtypes = [P(CsmcModel), i32, vp, i64, P(i64), vp, i64]
     L.csmc_get_tables.argtypes = [vp, vp, vp, vp]
     L.csmc_set_spins.argtypes = [vp, i32, vp]
@@ -237,6 +238,13 @@ class Engine:
         sel = C.c_int32()
         self._ck(self._L.csmc_autotune_report(self._h, ms, C.byref(sel)))
         return float(ms[0]), float(ms[1]), bool(sel.value)
+
+    def sweep_groups(self):
+        """(replica groups in use, (ms with 1, 2, 4 groups) of the create-time probe; zeros if not measured)."""
+        ms = (C.c_float * 3)()
+        g = C.c_int32()
+        self._ck(self._L.csmc_sweep_groups(self._h, C.byref(g), ms))
+        return int(g.value), tuple(float(v) for v in ms)
 
     @property
     def launches(self):

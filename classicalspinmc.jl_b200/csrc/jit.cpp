@@ -428,7 +428,7 @@ struct Gen {
         for (int u = 0; u < 4; ++u) {
             o << "extern \"C\" __global__ void __launch_bounds__(" << tpb << ") csmc_fused_u" << u << "(const double *__restrict__ in, double *__restrict__ out, const SweepArgs a) {\n";
             o << "    extern __shared__ double sh[];\n    double *shx = sh, *shy = sh + SH_TOTAL, *shz = sh + 2 * SH_TOTAL;\n";
-            o << "    const int rep = blockIdx.z;\n    int t = blockIdx.x;\n";
+            o << "    const int rep = blockIdx.z + a.rep0;\n    int t = blockIdx.x;\n";
             o << "    const int t2 = t % " << NT[2] << "; t /= " << NT[2] << "; const int t1 = t % " << NT[1] << "; const int t0 = t / " << NT[1] << ";\n";
             o << "    const int o0 = t0 * " << W[0] << ", o1 = t1 * " << W[1] << ", o2 = t2 * " << W[2] << ";\n";
             o << "    const double *gx = in + (size_t)rep * (3ull * NPAD), *gy = gx + NPAD, *gz = gy + NPAD;\n";
@@ -557,7 +557,7 @@ struct Gen {
                     o << "extern \"C\" __global__ void __launch_bounds__(" << sw_tpb << ", " << (u >= 2 ? mb_mc : mb_or) << ") csmc_sweep_c" << c << "_u" << u << "(double *spins, const SweepArgs a) {\n";
                     o << "#ifdef CSMC_PDL\n#if CSMC_PDL == 1\n    pdl_launch_dependents();\n#endif\n    pdl_wait();\n#endif\n";
                     o << "    __shared__ double part_g[" << (SPc - 1) << "][3][" << TS << "];\n";
-                    o << "    const int rep = blockIdx.z;\n    int t = blockIdx.x;\n";
+                    o << "    const int rep = blockIdx.z + a.rep0;\n    int t = blockIdx.x;\n";
                     o << "    const int warp = threadIdx.x >> 5, part = warp % " << SPc << ", ls = (warp / " << SPc << ") * 32 + (threadIdx.x & 31);\n";
                     o << "    const int t2 = t % " << NTs[2] << "; t /= " << NTs[2] << "; const int t1 = t % " << NTs[1] << "; const int t0 = t / " << NTs[1] << ";\n";
                     o << "    const int l2 = ls & " << (Ts[2] - 1) << ", l1 = (ls >> " << ilog2(Ts[2]) << ") & " << (Ts[1] - 1) << ", l0 = ls >> " << (ilog2(Ts[2]) + ilog2(Ts[1])) << ";\n";
@@ -591,7 +591,7 @@ struct Gen {
                 if (u == 2) plan.groups_metro.resize(hm.n_colours), plan.groups_metro[c] = ngroups;
                 o << "extern \"C\" __global__ void __launch_bounds__(" << sw_tpb << ", " << (u >= 2 ? mb_mc : mb_or) << ") csmc_sweep_c" << c << "_u" << u << "(double *spins, const SweepArgs a) {\n";
                 o << "#ifdef CSMC_PDL\n#if CSMC_PDL == 1\n    pdl_launch_dependents();\n#endif\n    pdl_wait();\n#endif\n";
-                o << "    const int rep = blockIdx.z;\n    int t = blockIdx.x;\n";
+                o << "    const int rep = blockIdx.z + a.rep0;\n    int t = blockIdx.x;\n";
                 o << "    const int t2 = t % " << NT[2] << "; t /= " << NT[2] << "; const int t1 = t % " << NT[1] << "; const int t0 = t / " << NT[1] << ";\n";
                 o << "    const int l2 = threadIdx.x & " << (T[2] - 1) << ", l1 = (threadIdx.x >> " << ilog2(T[2]) << ") & " << (T[1] - 1)
                   << ", l0 = threadIdx.x >> " << (ilog2(T[2]) + ilog2(T[1])) << ";\n";

@@ -28,6 +28,7 @@ struct SweepArgs {
     unsigned long long ctr_off;
     unsigned long long seed;
     int replica_base;
+    int rep0;
 };
 
 struct u4 { uint32_t x, y, z, w; };

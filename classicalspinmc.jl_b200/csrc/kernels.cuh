@@ -29,6 +29,7 @@ struct SweepArgs {
     unsigned long long ctr_off;          // + by-value offset
     unsigned long long seed;
     int replica_base;                    // global index of local replica 0
+    int rep0;                            // first local replica of this launch (replica groups on separate streams)
 };
 
 // ---- Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11) --------------------------------------------
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(TPB) k_sweep(const __grid_constant__ P p, cons
     const DevSeg &seg = p.segs[blockIdx.y];
     int pos, m[MAXD];
     const bool active = locate<P, STRUCT>(p, seg, blockIdx.x * TPB + threadIdx.x, pos, m);
-    const int rep = blockIdx.z;
+    const int rep = blockIdx.z + a.rep0;
     double *sx = p.spins + (size_t)rep * p.rep_stride, *sy = sx + p.npad, *sz = sy + p.npad;
     bool accepted = false;
     if (active) {

@@ -148,6 +148,13 @@ int32_t csmc_kernel_mode(const csmc_handle *h, int32_t *mode);
 /* Result of the launch-mode autotune of csmc_create: ms[0] / ms[1] = time of the probe run without /
  * with programmatic dependent launch (0 when the autotune did not run), *pdl_selected = mode in use. */
 int32_t csmc_autotune_report(const csmc_handle *h, float ms[2], int32_t *pdl_selected);
+/* Replica groups: with several replicas in a handle, sequences of >= 2 sweeps run as `groups`
+ * independent chains (n_replicas / groups replicas each) on separate streams -- parallel branches of
+ * the replayed CUDA graph -- so that the fixed latencies of the single-wave colour passes overlap.
+ * csmc_create times 1, 2 and 4 groups on the model (same probe run as above) and keeps the fastest;
+ * ms[0..2] are those times (0 when not measured).  The environment variable CSMC_SWEEP_GROUPS
+ * overrides.  Results do not depend on the group count (replicas are independent chains). */
+int32_t csmc_sweep_groups(const csmc_handle *h, int32_t *groups, float ms[3]);
 /* Host-only (no GPU needed): generate the specialised kernel source for `model` and, if
  * compile != 0, compile it with NVRTC for sm_100a.  source/log may be NULL; *_cap are buffer sizes;
  * *source_len receives the full source length.  Used by build checks and tests. */

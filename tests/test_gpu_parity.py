@@ -298,6 +298,36 @@ def test_fused_full_sweep_kernels_match_pass_kernels(name, builder, shape, S, gr
     assert np.abs(spins(fused) - spins(plain)).max() <= 1e-9
 
 
+def test_replica_groups_do_not_change_results(monkeypatch):
+    """Sequences of sweeps run as 1, 2 or 4 concurrent chains of replicas on separate streams (parallel graph
+    branches, csmc_sweep_groups); replicas are independent, so spins, acceptance counts and PT series are
+    bit-identical for every group count."""
+    md = ModelData(models.kitaev_honeycomb(J3=0.25), (16, 12), 1.0)
+    R = 6
+    T = np.geomspace(0.2, 2.0, R)
+    p = dict(t_thermalization=60, t_measurement=120, probe_rate=10, swap_rate=5, overrelaxation_rate=5)
+    outs = []
+    for groups in ("1", "2", "4", "3"):
+        monkeypatch.setenv("CSMC_SWEEP_GROUPS", groups)
+        eng = _lib.Engine(md, n_replicas=R, seed=31, flags=FLAG_JIT | FLAG_NO_RESIDENT)
+        assert eng.sweep_groups()[0] in (1, int(groups))
+        eng.randomize(3)
+        eng.set_temperatures(T)
+        eng.cycles_async(4, 5, 1)
+        eng.cycles_async(1, 0, 3)
+        eng.sync()
+        assert eng.sweep_groups()[0] == int(groups)
+        acc = eng.accepted().copy()
+        eng.pt_init(T)
+        eng.pt_run(p, 0, 180)
+        E, M = eng.pt_series()
+        outs.append((np.stack([eng.get_spins(r) for r in range(R)]), acc, E, M, eng.pt_slots()))
+    for o in outs[1:]:
+        for a, b in zip(o, outs[0]):
+            assert np.array_equal(a, b)
+    assert outs[0][1].min() > 0 and outs[0][2].shape[0] > 0
+
+
 def test_anneal_temperature_schedule_matches_reference_loop():
     """csmc_anneal_temperature == the `while t < t_thermalization` loop of src/monte_carlo.jl:169-182."""
     md = ModelData(models.kitaev_honeycomb(), (4, 4), 1.0)

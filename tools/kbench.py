@@ -58,7 +58,7 @@ def main():
         eng.set_temperatures(np.geomspace(0.5, 2.0, R))
         N, C = eng.N, eng.n_colours
         balg = B_ALG.get(C, 24.0 * (C + 1))
-        out = {"workload": spec, "N": N, "R": R, "colours": C, "mode": eng.kernel_mode}
+        out = {"workload": spec, "N": N, "R": R, "colours": C, "mode": eng.kernel_mode, "groups": eng.sweep_groups()}
         for label, orc, mc in (("or", 1, 0), ("or2", 2, 0), ("metro", 0, 1), ("metro2", 0, 2), ("cycle10+1", 10, 1)):
             n = args.n if label != "cycle10+1" else max(args.n // 10, 5)
             dt = time_cycles(eng, stream, n, orc, mc)
