@@ -116,9 +116,8 @@ struct csmc_handle {
     long long ssf_probes = 0;
 
     // CUDA graph of one bench cycle
-    cudaGraphExec_t cycle_graph = nullptr;
-    int cycle_or = -1, cycle_metro = -1;
-    long long cycle_launches = 0;
+    struct CycleGraph { cudaGraphExec_t exec; long long launches; };
+    std::map<std::pair<int, int>, CycleGraph> cycle_graphs;   // keyed by (OR sweeps, Metropolis sweeps) per cycle
     // CUDA graphs of n consecutive overrelaxation sweeps (parallel-tempering loop)
     std::map<int, cudaGraphExec_t> or_graphs;
     std::map<int, long long> or_graph_launches;
@@ -431,7 +430,8 @@ std::string load_jit_module(const HostModel &hm, bool pdl, JitModule &m, bool wa
 }
 
 void drop_graphs(csmc_handle *h) {
-    if (h->cycle_graph) { cudaGraphExecDestroy(h->cycle_graph); h->cycle_graph = nullptr; h->cycle_or = h->cycle_metro = -1; }
+    for (auto &kv : h->cycle_graphs) cudaGraphExecDestroy(kv.second.exec);
+    h->cycle_graphs.clear();
     for (auto &kv : h->or_graphs) cudaGraphExecDestroy(kv.second);
     h->or_graphs.clear();
 }
@@ -584,6 +584,7 @@ int32_t csmc_version(void) { return CSMC_VERSION; }
 const char *csmc_last_error(const csmc_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 static int autotune_pdl(csmc_handle *h);
+static int enqueue_or_block(csmc_handle *h, int n);
 
 int32_t csmc_create(const csmc_model *model, const csmc_opts *opts, csmc_handle **out) {
     csmc_handle *h = nullptr;
@@ -797,7 +798,7 @@ int32_t csmc_destroy(csmc_handle *h) {
     if (!h) return CSMC_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    if (h->cycle_graph) cudaGraphExecDestroy(h->cycle_graph);
+    for (auto &kv : h->cycle_graphs) cudaGraphExecDestroy(kv.second.exec);
     for (auto &kv : h->or_graphs) cudaGraphExecDestroy(kv.second);
     for (auto st : h->aux_streams) cudaStreamDestroy(st);
     for (auto ev : h->aux_done) cudaEventDestroy(ev);
@@ -971,7 +972,14 @@ int32_t csmc_overrelax(csmc_handle *h, int32_t n_sweeps) {
     NEED(h);
     CK(cudaSetDevice(h->device));
     if (n_sweeps > 0 && use_resident(h, n_sweeps)) enqueue_resident(h, 1, n_sweeps, 0, 0, 0, nullptr, 0);
-    else for (int s = 0; s < n_sweeps; ++s) enqueue_sweep<UPD_OR>(h);
+    else {
+        // blocks of up to 64 sweeps: one graph replay each (replica groups on concurrent streams included)
+        for (int left = n_sweeps; left > 0;) {
+            const int k = std::min(left, 64);
+            int rc = enqueue_or_block(h, k); if (rc) return rc;
+            left -= k;
+        }
+    }
     return finish(h);
 }
 
@@ -1022,8 +1030,7 @@ int32_t csmc_metropolis(csmc_handle *h, const double *T, int32_t n_sweeps, doubl
     rc = upload_T(h, T); if (rc) return rc;
     std::vector<double> before(h->R), after(h->R);
     if (accepted) { rc = csmc_get_accepted(h, before.data(), 0); if (rc) return rc; }
-    if (n_sweeps > 0 && use_resident(h, n_sweeps)) enqueue_resident(h, 1, 0, n_sweeps, 0, 0, nullptr, 0);
-    else for (int s = 0; s < n_sweeps; ++s) enqueue_metropolis(h, false);
+    if (n_sweeps > 0) { rc = csmc_cycles_async(h, n_sweeps, 0, 1); if (rc) return rc; }   // resident kernel or graph replay
     rc = finish(h); if (rc) return rc;
     if (accepted) {
         rc = csmc_get_accepted(h, after.data(), 0); if (rc) return rc;
@@ -1062,12 +1069,14 @@ int32_t csmc_metropolis_cone(csmc_handle *h, const double *T, double *sigma, int
 }
 
 // ---- cycles: CUDA-graph replay of (or_per_cycle OR sweeps + metro_per_cycle Metropolis sweeps) --------
-static int build_cycle_graph(csmc_handle *h, int orc, int mc) {
-    if (h->cycle_graph && h->cycle_or == orc && h->cycle_metro == mc) return CSMC_OK;
-    if (h->cycle_graph) { cudaGraphExecDestroy(h->cycle_graph); h->cycle_graph = nullptr; }
+static int build_cycle_graph(csmc_handle *h, int orc, int mc, const csmc_handle::CycleGraph **out) {
+    const auto key = std::make_pair(orc, mc);
+    auto it = h->cycle_graphs.find(key);
+    if (it != h->cycle_graphs.end()) { *out = &it->second; return CSMC_OK; }
     cudaGraph_t graph = nullptr;
     const long long before = h->launches;
     const bool fused = fused_ready(h);
+    sweep_groups(h, 2);   // streams / events of the replica groups exist before the capture starts
     std::vector<SweepOp> seq;
     for (int s = 0; s < orc; ++s) seq.push_back({UPD_OR, 0ULL, false});
     for (int s = 0; s < mc; ++s) seq.push_back({UPD_METRO, (unsigned long long)s, true});
@@ -1075,12 +1084,18 @@ static int build_cycle_graph(csmc_handle *h, int orc, int mc) {
     enqueue_sweep_seq(h, seq.data(), (int)seq.size(), fused);
     if (mc > 0) { k_add_u64<<<1, 1, 0, h->stream>>>(h->d_ctr, (unsigned long long)mc); h->launches++; }
     CK(cudaStreamEndCapture(h->stream, &graph));
-    h->cycle_launches = h->launches - before;
+    const long long launches = h->launches - before;
     h->launches = before;  // capture enqueues nothing
-    cudaError_t e = cudaGraphInstantiate(&h->cycle_graph, graph, 0);
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) return fail(h, CSMC_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
-    h->cycle_or = orc; h->cycle_metro = mc;
+    if (h->cycle_graphs.size() >= 16) {
+        CK(cudaStreamSynchronize(h->stream));   // replays in flight keep their executable graphs until here
+        for (auto &kv : h->cycle_graphs) cudaGraphExecDestroy(kv.second.exec);
+        h->cycle_graphs.clear();
+    }
+    *out = &h->cycle_graphs.emplace(key, csmc_handle::CycleGraph{exec, launches}).first->second;
     return CSMC_OK;
 }
 
@@ -1113,10 +1128,11 @@ int32_t csmc_cycles_async(csmc_handle *h, int64_t n_cycles, int32_t orc, int32_t
     }
     // the graph reads the sweep counter from device memory: bring it up to date first
     CK(cudaMemcpyAsync(h->d_ctr, &h->metro_ctr, sizeof(unsigned long long), cudaMemcpyHostToDevice, h->stream));
-    int rc = build_cycle_graph(h, orc, mc); if (rc) return rc;
-    for (int64_t c = 0; c < n_cycles; ++c) CK(cudaGraphLaunch(h->cycle_graph, h->stream));
+    const csmc_handle::CycleGraph *cg = nullptr;
+    int rc = build_cycle_graph(h, orc, mc, &cg); if (rc) return rc;
+    for (int64_t c = 0; c < n_cycles; ++c) CK(cudaGraphLaunch(cg->exec, h->stream));
     h->metro_ctr += (unsigned long long)n_cycles * mc;
-    h->launches += n_cycles * h->cycle_launches;
+    h->launches += n_cycles * cg->launches;
     CK(cudaGetLastError());
     return CSMC_OK;
 }
@@ -1134,6 +1150,7 @@ static int enqueue_or_block(csmc_handle *h, int n) {
     if (it == h->or_graphs.end()) {
         cudaGraph_t graph = nullptr;
         const long long before = h->launches;
+        sweep_groups(h, 2);   // streams / events of the replica groups exist before the capture starts
         CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
         enqueue_sweep_seq(h, seq.data(), n, fused);
         CK(cudaStreamEndCapture(h->stream, &graph));
@@ -1143,7 +1160,11 @@ static int enqueue_or_block(csmc_handle *h, int n) {
         cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
         cudaGraphDestroy(graph);
         if (e != cudaSuccess) return fail(h, CSMC_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
-        if (h->or_graphs.size() > 64) { for (auto &kv : h->or_graphs) cudaGraphExecDestroy(kv.second); h->or_graphs.clear(); }
+        if (h->or_graphs.size() > 64) {
+            CK(cudaStreamSynchronize(h->stream));   // replays in flight keep their executable graphs until here
+            for (auto &kv : h->or_graphs) cudaGraphExecDestroy(kv.second);
+            h->or_graphs.clear();
+        }
         it = h->or_graphs.emplace(n, exec).first;
     }
     CK(cudaGraphLaunch(it->second, h->stream));
