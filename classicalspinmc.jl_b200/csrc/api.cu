@@ -1456,6 +1456,14 @@ int32_t csmc_pt_run(csmc_handle *h, const csmc_pt_params *p, int64_t sweep_begin
     double *mine = h->d_meas_all + (size_t)h->replica_base * 8;
     auto gather = [&]() -> int { return enqueue_gather_meas(h); };
     int pending_or = 0;   // overrelaxation sweeps not yet enqueued (flushed as one graph replay)
+    // plain Metropolis on the pass kernels: the pending OR sweeps and the Metropolis sweep are one graph (the
+    // same cycle graphs csmc_cycles_async replays), so the replica groups run OR block + Metropolis as
+    // uninterrupted concurrent chains; the sweep counter then lives on the device
+    const bool fold = !resident && !cone && rate != 0 && !(h->flags & CSMC_FLAG_NO_GRAPH);
+    if (fold) {
+        CK(cudaMemcpyAsync(h->d_ctr, &h->metro_ctr, sizeof(unsigned long long), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
     // The energies are consumed only by an exchange (same sweep) or by probes before the next Metropolis
     // sweep, so total_energy (src/monte_carlo.jl:305) is evaluated -- and gathered across GPUs -- only at
     // Metropolis sweeps where one of the two follows; the values that are consumed are unchanged.
@@ -1474,6 +1482,13 @@ int32_t csmc_pt_run(csmc_handle *h, const csmc_pt_params *p, int64_t sweep_begin
             // one launch: the pending OR sweeps, the Metropolis sweep and (if consumed) E/M of every local replica
             enqueue_resident(h, 1, pending_or, 1, cone, 0, meas ? mine : nullptr, 1, adapt);
             pending_or = 0;
+        } else if (fold && metro) {
+            const csmc_handle::CycleGraph *cg = nullptr;
+            rc = build_cycle_graph(h, pending_or, 1, &cg); if (rc) return rc;
+            CK(cudaGraphLaunch(cg->exec, h->stream));
+            h->launches += cg->launches;
+            h->metro_ctr++;
+            pending_or = 0;
         } else if (metro || probe || sweep + 1 == sweep_end) {
             if (resident) { if (pending_or) enqueue_resident(h, 1, pending_or, 0, 0, 0, nullptr, 0); }
             else { rc = enqueue_or_block(h, pending_or); if (rc) return rc; }
@@ -1481,7 +1496,7 @@ int32_t csmc_pt_run(csmc_handle *h, const csmc_pt_params *p, int64_t sweep_begin
         }
         if (metro) {                                                            // :302-305
             if (!resident) {
-                enqueue_metropolis(h, cone != 0);
+                if (!fold) enqueue_metropolis(h, cone != 0);
                 if (adapt) { k_adapt_sigma<<<(h->R + 127) / 128, 128, 0, h->stream>>>(h->d_sigma, h->d_acc, h->d_acc_prev, (double)h->hm.N, h->R); h->launches++; }
                 if (meas) enqueue_measure(h, mine, true);
             }
