@@ -83,6 +83,13 @@ class MonteCarlo:
         # slots per process the files are named by global slot (== rank when there is one slot per process)
         if comm_size > 1:
             _, self.slot_base, _ = parallel.gather_temperatures(self.temperatures)
+            # the exchange decisions are drawn redundantly on every rank from the shared Philox stream: all
+            # processes of a job must use one seed (rank 0's when none was given)
+            seeds = parallel.allgather_objects(self.seed)
+            if seed is None:
+                self.seed = int(seeds[0])
+            elif len(set(seeds)) != 1:
+                raise ValueError("every process of a parallel-tempering job must be given the same seed")
         else:
             self.slot_base = 0
         if len(outpath) > 0:                                            # :95-113

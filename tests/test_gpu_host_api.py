@@ -202,6 +202,40 @@ def test_structure_factor_batch_runner_over_configuration_files(tmp_path):
     f.close()
 
 
+def test_example_runners(tmp_path):
+    """examples/: the reference's two example scripts (simulated annealing of the Kitaev honeycomb model,
+    parallel tempering of the pyrochlore model) on the GPU engine, at reduced sizes."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out1 = str(tmp_path / "sa") + "/"
+    r = subprocess.run([sys.executable, os.path.join(root, "examples", "simulated_annealing", "runner.py"), out1,
+                        "--t-thermalization", "300", "--t-deterministic", "4000"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
+    e = float([l for l in r.stdout.splitlines() if l.startswith("energy per site:")][-1].split(":")[1])
+    assert -0.9 < e < -0.5                       # Kitaev ferromagnet in a weak field: E/N close to -0.6
+    f = h5._open(out1 + "configuration.h5.params", "r")
+    assert h5._get_attr(f, "K") == -1.0 and h5._get_attr(f, "t_thermalization") == 300
+    assert len(h5._keys(f, "unit_cell/bilinear")) == 3 and h5._has_group(f, "unit_cell/cubic")
+    f.close()
+    g = h5._open(out1 + "configuration_0.h5", "r")
+    spins = np.asarray(h5._get(g, "spins"))
+    g.close()
+    assert spins.shape == (32, 3) and np.allclose(np.linalg.norm(spins, axis=1), 1.0)
+    out2 = str(tmp_path / "pt") + "/"
+    r = subprocess.run([sys.executable, os.path.join(root, "examples", "parallel_tempering", "runner.py"), out2,
+                        "--temperatures", "6", "--L", "2", "--t-thermalization", "400", "--t-measurement", "2000", "--B", "1.0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
+    energies = []
+    for slot in range(6):
+        obs = h5.read_observables(out2 + f"configuration_{slot}.h5")
+        assert {"energy", "energy_err", "specific_heat", "magnetization", "susceptibility"} <= set(obs)
+        energies.append(obs["energy"])
+    assert energies[0] < energies[-1]            # colder slots sit lower in energy
+    assert os.path.isdir(out2 + "IC_0") and len(os.listdir(out2 + "IC_0")) == 2      # checkpoints at sweeps 1000, 2000
+
+
 def test_errors_cross_the_abi_as_status_codes():
     L = _lib.lib()
     md = ModelData(models.square_heisenberg(), (4, 4), 1.0)
