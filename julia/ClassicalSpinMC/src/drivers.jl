@@ -201,6 +201,14 @@ function parallel_tempering!(mc::MonteCarlo, saveIC::Vector{Int64}=Int64[]; alg:
     n_slots == 1 && @warn "a single temperature slot; no replica exchanges will occur!"
     base = rank * R
     out = length(mc.outdir) > 0
+    if nranks > 1
+        # exchange decisions are drawn redundantly on every rank from the shared Philox stream: one seed per job
+        seed0 = reinterpret(UInt64, bcast_bytes(collect(reinterpret(UInt8, [mc.seed]))))[1]
+        if seed0 != mc.seed
+            mc.seed = seed0
+            mc.engine = nothing
+        end
+    end
     e = upload!(mc; replica_base=base)
     if nranks > 1
         id = rank == 0 ? comm_unique_id() : zeros(UInt8, 128)
