@@ -413,6 +413,48 @@ def test_full_size_properties_square_1024():
     assert E2 < -1.5    # ferromagnet: aligning to the local field drives E/N towards -2.1
 
 
+def _golden_cases():
+    import importlib.util
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_vectors", os.path.join(here, "make_vectors.py"))
+    mv = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mv)
+    return mv, os.path.join(here, "oracle_vectors.npz")
+
+
+@pytest.mark.parametrize("flags", MODES, ids=MODE_IDS)
+@pytest.mark.parametrize("name", ["square-8x8", "honeycomb-J3-6x4", "pyrochlore-3x2x4", "triangular-multispin-onsite-8x4",
+                                  "mixed-basis-open-5x3", "chain-open-17"])
+def test_cuda_path_against_committed_golden_vectors(name, flags):
+    """tests/golden/oracle_vectors.npz: the CUDA path against the committed fixtures alone (no oracle call at
+    run time): fields, site energies, total energy, magnetisation <= 1e-12; overrelaxation, deterministic and
+    same-stream Metropolis sweeps in colour order <= 1e-12 per component with identical accept counts."""
+    mv, path = _golden_cases()
+    z = np.load(path)
+    g = {k.split("/", 1)[1]: z[k] for k in z.files if k.startswith(name + "/")}
+    builder, shape, bc, S = mv.CASES[name]
+    md = ModelData(builder(), shape, S, bc)
+    if flags & FLAG_JIT and not _lib.plan(md)[2]:
+        pytest.skip("no periodic colouring pattern: explicit-table kernels only")
+    eng = _lib.Engine(md, seed=mv.SEED, flags=flags)
+    assert np.array_equal(eng.colour_order(), g["order"])
+    eng.set_spins(g["spins0"])
+    fscale = max(1.0, np.abs(g["field"]).max())
+    assert np.abs(eng.local_field_all() - g["field"]).max() <= TOL * fscale
+    assert np.abs(eng.site_energy_all() - g["site_energy"]).max() <= TOL * max(1.0, np.abs(g["site_energy"]).max())
+    assert abs(eng.total_energy()[0] - g["energy"][0]) <= TOL * g["energy"][1]
+    assert np.abs(eng.magnetization_vector()[0] - g["magnetization"]).max() <= TOL * md.n_sites * S
+    eng.overrelax(3)
+    assert np.abs(eng.get_spins() - g["or3"]).max() <= TOL * S
+    eng.set_spins(g["spins0"])
+    eng.deterministic(2)
+    assert np.abs(eng.get_spins() - g["det2"]).max() <= TOL * S
+    eng.set_spins(g["spins0"])
+    assert eng.metropolis(mv.T, 2)[0] == g["metro2_accepted"][0]
+    assert np.abs(eng.get_spins() - g["metro2"]).max() <= TOL * S
+
+
 FULL_SIZE = [
     ("C3-honeycomb-256", lambda: models.kitaev_honeycomb(), (256, 256), 1.0, 2),
     ("C4-pyrochlore-32", lambda: models.pyrochlore_local(), (32, 32, 32), 0.5, 4),

@@ -133,3 +133,37 @@ def test_multispin_perspectives_sum_rule():
             direct += np.einsum("abc,a,b,c->", C3, s0, s1, s2)
             direct += np.einsum("abcd,a,b,c,d->", R4, s0, s1, s2, s3)
     assert abs(lat.total_energy(s) - direct) < 1e-12
+
+
+# ---- committed fixtures (tests/golden/, generated by tests/golden/make_vectors.py) -----------------------------
+def _golden():
+    import importlib.util
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_vectors", os.path.join(here, "make_vectors.py"))
+    mv = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mv)
+    return mv, np.load(os.path.join(here, "oracle_vectors.npz")), os.path.join(here, "reference_known_answers.json")
+
+
+def test_known_answers_file_lists_what_this_module_pins():
+    import json
+    _, _, path = _golden()
+    answers = json.load(open(path))["answers"]
+    cites = " ".join(a["cite"] for a in answers)
+    for needle in ("latticetests.jl:3-7", "latticetests.jl:10-17", "latticetests.jl:18", "latticetests.jl:21-30", "mctests.jl:36-49", "mctests.jl:52-58"):
+        assert needle in cites
+    assert [a["value"] for a in answers if "mctests" in a["cite"]] == [-0.6444, -0.6444]
+
+
+def test_oracle_reproduces_the_committed_vectors():
+    """The fixtures the GPU parity tests read were produced by this oracle: regenerating them gives the same
+    numbers (<= 1e-13: the library may be rebuilt by another compiler version)."""
+    mv, z, _ = _golden()
+    assert {k.split("/")[0] for k in z.files} == set(mv.CASES)
+    for name in mv.CASES:
+        fresh = mv.build(name)
+        for k, v in fresh.items():
+            ref = z[f"{name}/{k}"]
+            assert ref.shape == np.asarray(v).shape, (name, k)
+            assert np.abs(ref - v).max() <= 1e-13 * max(1.0, np.abs(ref).max()), (name, k)
