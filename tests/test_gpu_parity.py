@@ -298,7 +298,8 @@ def test_fused_full_sweep_kernels_match_pass_kernels(name, builder, shape, S, gr
     assert np.abs(spins(fused) - spins(plain)).max() <= 1e-9
 
 
-def test_replica_groups_do_not_change_results(monkeypatch):
+@pytest.mark.parametrize("graph", [0, FLAG_NO_GRAPH], ids=["graph", "plain"])
+def test_replica_groups_do_not_change_results(monkeypatch, graph):
     """Sequences of sweeps run as 1, 2 or 4 concurrent chains of replicas on separate streams (parallel graph
     branches, csmc_sweep_groups); replicas are independent, so spins, acceptance counts and PT series are
     bit-identical for every group count."""
@@ -309,7 +310,7 @@ def test_replica_groups_do_not_change_results(monkeypatch):
     outs = []
     for groups in ("1", "2", "4", "3"):
         monkeypatch.setenv("CSMC_SWEEP_GROUPS", groups)
-        eng = _lib.Engine(md, n_replicas=R, seed=31, flags=FLAG_JIT | FLAG_NO_RESIDENT)
+        eng = _lib.Engine(md, n_replicas=R, seed=31, flags=FLAG_JIT | FLAG_NO_RESIDENT | graph)
         assert eng.sweep_groups()[0] in (1, int(groups))
         eng.randomize(3)
         eng.set_temperatures(T)
