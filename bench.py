@@ -137,7 +137,24 @@ def cpu_baseline(md, T, or_per_cycle, metro_per_cycle, n_cycles, threads):
     return updates / dt, updates, dt
 
 
+def cpu_pt_baseline(md, T_all, sweeps, threads, swap_rate=50, rate=10, seed=3):
+    """The oracle's restatement of the reference parallel-tempering loop (src/monte_carlo.jl:289-349: OR every
+    sweep, random-site Metropolis + total_energy every `rate`-th, configuration-swapping exchange every
+    `swap_rate`-th), one temperature per host thread as examples/parallel_tempering/README.txt:17."""
+    from oracle import oracle as orc
+    lat = orc.OracleLattice(md)
+    R = len(T_all)
+    spins = np.concatenate([lat.randomize(seed=12345, replica=r) for r in range(R)])
+    t0 = time.perf_counter()
+    lat.parallel_tempering(spins, T_all, sweeps, 0, 2000, swap_rate, rate, seed=seed, n_threads=threads)
+    dt = time.perf_counter() - t0
+    updates = float(sweeps + (sweeps + rate - 1) // rate) * lat.N * R
+    return updates / dt, updates, dt
+
+
 def run_reference(args):
+    """Reference arm: the reference's CPU algorithm for the workload (C restatement under oracle/, the
+    reference itself is Julia and cannot run here) on all host threads; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -145,22 +162,40 @@ def run_reference(args):
     md, cfg = workload_model(args.workload, args.L)
     threads = args.cpu_threads or (os.cpu_count() or 1)
     orc.lib()
-    cycles = args.ref_cycles
-    for _ in range(args.warmup):
-        cpu_baseline(md, 1.0, args.or_per_cycle, args.metro_per_cycle, 1, threads) if args.ref_warm else None
+    pt = args.workload in PT_DEFAULTS
+    if pt:
+        d = PT_DEFAULTS[args.workload]
+        R = args.replicas or d["R"]
+        T_all = np.geomspace(d["Tmin"], d["Tmax"], R)
+        sweeps = args.ref_sweeps
+
+        def step(n):
+            return cpu_pt_baseline(md, T_all, n, threads)
+        one, warm = sweeps, 10
+        sample = (f"reference parallel-tempering loop, {R} temperatures on {threads} host threads, {sweeps} sweeps per "
+                  f"step (swap 50, OR 10, total_energy after every Metropolis sweep, configurations swapped); "
+                  f"C restatement, not Julia")
+        cfg.update(replicas=R, swap_rate=50, overrelaxation_rate=10, sweeps_per_step=sweeps, l2="n/a (host)")
+    else:
+        def step(n):
+            return cpu_baseline(md, 1.0, args.or_per_cycle, args.metro_per_cycle, n, threads)
+        one, warm = args.ref_cycles, 1
+        sample = (f"{threads} independent replicas (one per host thread, as one MPI rank per temperature) x "
+                  f"{one} cycle(s) of the {cfg['workload']} lattice per step; reference algorithm unchanged "
+                  f"(C restatement, not Julia)")
+        cfg.update(cycle=f"{args.or_per_cycle} OR + {args.metro_per_cycle} Metropolis", l2="n/a (host)")
+    for _ in range(args.warmup):          # untimed: a short pass (pages in the lattice and the thread pool)
+        step(warm)
     tot_u, tot_t = 0.0, 0.0
     for _ in range(args.steps):
-        v, u, dt = cpu_baseline(md, 1.0, args.or_per_cycle, args.metro_per_cycle, cycles, threads)
+        v, u, dt = step(one)
         tot_u += u
         tot_t += dt
-    value = tot_u / tot_t
-    cfg.update(cycle=f"{args.or_per_cycle} OR + {args.metro_per_cycle} Metropolis", l2="n/a (host)")
-    sample = (f"{threads} independent replicas (one per host thread, as one MPI rank per temperature) x "
-              f"{cycles} cycle(s) of the {cfg['workload']} lattice per step; reference algorithm unchanged "
-              f"(C restatement, not Julia)")
-    line = {"impl": "reference", "metric": "single-spin updates/sec (Metropolis+overrelax)", "value": value,
+    value = tot_u / max(tot_t, 1e-30)
+    line = {"impl": "reference", "metric": "single-spin updates/sec (Metropolis+overrelax)" + (", parallel tempering" if pt else ""),
+            "value": value,
             "unit": "updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True, "scaling": "strong" if pt else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": value, "unit": "updates/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -392,7 +427,7 @@ def main():
     ap.add_argument("--or-per-cycle", type=int, default=10)
     ap.add_argument("--metro-per-cycle", type=int, default=1)
     ap.add_argument("--ref-cycles", type=int, default=4, help="cycles per host thread per step in the CPU legs")
-    ap.add_argument("--ref-warm", action="store_true")
+    ap.add_argument("--ref-sweeps", type=int, default=55, help="PT workloads: sweeps per step in the reference arm")
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pt", action="store_true", help="N > 1: skip the extra parallel-tempering measurement")

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Small-lattice regime (the sizes the reference's examples actually run): parallel tempering on the
 pyrochlore L=8 example (N=2048, 128 temperatures, swap every 50, 10 OR : 1 Metropolis) and annealing of
-the L=4 README lattice.  Compares the resident kernel, the per-colour pass kernels and the CPU oracle."""
+the L=4 README lattice.  Compares the resident kernel and the per-colour pass kernels; the CPU figure next to
+them is bench.py's reference-arm leg (bench.cpu_pt_baseline), the one place outside tests/ that runs oracle/."""
 import json
 import os
 import sys
@@ -13,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from classicalspinmc.jl_b200 import _lib  # noqa: E402
 from classicalspinmc.jl_b200._abi import FLAG_JIT, FLAG_NO_RESIDENT, ModelData  # noqa: E402
-from oracle import oracle as orc  # noqa: E402
+import bench  # noqa: E402
 from tests import models  # noqa: E402
 
 
@@ -37,13 +38,9 @@ def main():
     out = {"workload": "pyrochlore L=8 (N=2048), PT 128 temperatures"}
     out["resident"] = pt_case(md, R, 5000, FLAG_JIT)
     out["pass_kernels"] = pt_case(md, R, 1000, FLAG_JIT | FLAG_NO_RESIDENT)
-    lat = orc.OracleLattice(md)
     threads = os.cpu_count() or 1
-    spins = np.concatenate([lat.randomize(seed=5, replica=r) for r in range(R)])
-    t0 = time.perf_counter()
-    lat.parallel_tempering(spins, np.geomspace(0.09 / 11.6, 14 / 11.6, R), 200, 0, 2000, 50, 10, seed=3, n_threads=threads)
-    dt = time.perf_counter() - t0
-    out["cpu_oracle"] = {"threads": threads, "sweeps_per_s": 200 / dt, "Gupd_s": 200 * 1.1 * 2048 * R / dt / 1e9}
+    v, _, _ = bench.cpu_pt_baseline(md, np.geomspace(0.09 / 11.6, 14 / 11.6, R), 200, threads)
+    out["cpu_reference_arm"] = {"threads": threads, "sweeps_per_s": v / (1.1 * 2048 * R), "Gupd_s": v / 1e9}
     print(json.dumps(out))
 
 
