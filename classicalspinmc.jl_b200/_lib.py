@@ -28,7 +28,7 @@ EXPORTS = [
     "csmc_metropolis", "csmc_metropolis_cone", "csmc_anneal_temperature", "csmc_anneal_temperature_cone", "csmc_set_temperatures",
     "csmc_set_sigma", "csmc_get_sigma",
     "csmc_cycles_async", "csmc_sync", "csmc_get_accepted", "csmc_pt_init", "csmc_comm_unique_id",
-    "csmc_comm_init", "csmc_pt_run", "csmc_pt_exchange", "csmc_pt_get_slots", "csmc_pt_get_series",
+    "csmc_comm_init", "csmc_comm_mode", "csmc_pt_run", "csmc_pt_exchange", "csmc_pt_get_slots", "csmc_pt_get_series",
     "csmc_pt_get_stats", "csmc_pt_set_momenta", "csmc_pt_get_ssf",
 ]
 
@@ -100,6 +100,7 @@ def lib():
     L.csmc_pt_init.argtypes = [vp, i32, vp]
     L.csmc_comm_unique_id.argtypes = [vp]
     L.csmc_comm_init.argtypes = [vp, i32, i32, vp]
+    L.csmc_comm_mode.argtypes = [vp, P(i32)]
     L.csmc_pt_run.argtypes = [vp, P(CsmcPtParams), i64, i64]
     L.csmc_pt_exchange.argtypes = [vp, i32, vp]
     L.csmc_pt_get_slots.argtypes = [vp, vp]
@@ -379,6 +380,12 @@ class Engine:
     def comm_init(self, n_ranks, rank, unique_id: bytes):
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         self._ck(self._L.csmc_comm_init(self._h, n_ranks, rank, buf))
+
+    def comm_mode(self) -> int:
+        """0 no communicator, 1 NCCL collectives, 2 / 3 stores into peer memory (CSMC_PEER_GATHER=1 / 2)."""
+        m = C.c_int32()
+        self._ck(self._L.csmc_comm_mode(self._h, C.byref(m)))
+        return m.value
 
     def pt_init(self, T_all):
         T_all = _f64(T_all)

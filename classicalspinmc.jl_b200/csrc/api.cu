@@ -19,7 +19,7 @@ namespace {
 typedef struct ncclComm *ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
-enum { ncclFloat64 = 8 };
+enum { ncclUint8 = 1, ncclFloat64 = 8 };
 struct NcclApi {
     void *lib = nullptr;
     ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
@@ -130,6 +130,17 @@ struct csmc_handle {
     // multi-GPU: replica block of every rank (gathered at csmc_comm_init)
     std::vector<long long> rank_base, rank_count;
     bool even_partition = true;
+    // measurement records gathered by stores into peer memory instead of NCCL (opt-in, CSMC_PEER_GATHER)
+    struct PeerGather {
+        int mode = 0;                          // 0 off, 1 push + wait kernels, 2 push folded into the energy reduction
+        unsigned char *base = nullptr;         // local allocation: [flags 128 B][arrival counter 128 B][mailbox 2 x cap8 doubles]
+        void *peer[PEER_MAX_RANKS] = {};       // the other ranks' allocations (cudaIpcOpenMemHandle)
+        PeerPorts ports{};
+        unsigned long long seq = 0;            // gathers issued so far (same on every rank)
+        bool pushed = false;                   // the measurement just enqueued already pushed its records (mode 2)
+        int *err = nullptr;                    // mapped host memory: set by k_peer_wait on timeout
+        unsigned long long timeout_ns = 30000000000ULL;
+    } peer;
 
     std::string err;
     long long launches = 0;
@@ -305,6 +316,11 @@ void enqueue_metropolis(csmc_handle *h, bool cone) {
     h->metro_ctr++;
 }
 
+// peer-memory gather usable for the current parallel-tempering state (all ranks decide alike: n_slots is global)
+bool peer_gather_active(const csmc_handle *h) {
+    return h->peer.mode != 0 && h->comm && h->n_slots > 0 && (long long)h->n_slots * 8 <= h->peer.ports.cap8;
+}
+
 // energy + magnetisation of every local replica into meas[(R) x 8]
 void enqueue_measure(csmc_handle *h, double *meas, bool write_energy) {
     for (int c = 0; c < h->hm.n_colours; ++c) {
@@ -322,7 +338,15 @@ void enqueue_measure(csmc_handle *h, double *meas, bool write_energy) {
         }
         h->launches++;
     }
-    k_reduce_partials<<<h->R, 256, 0, h->stream>>>(h->d_partials, h->n_partials, h->d_acc, h->d_sigma, meas, write_energy ? 1 : 0);
+    if (peer_gather_active(h) && h->peer.mode == 2 && h->d_meas_all && meas == h->d_meas_all + (size_t)h->replica_base * 8) {
+        // the records go straight from the reduction into every rank's mailbox (enqueue_gather_meas then only waits)
+        unsigned int *arrive = (unsigned int *)(h->peer.base + 128);
+        k_reduce_partials_push<<<h->R, 256, 0, h->stream>>>(h->d_partials, h->n_partials, h->d_acc, h->d_sigma, meas, write_energy ? 1 : 0,
+                                                            h->peer.ports, (long long)h->replica_base * 8, ++h->peer.seq, arrive);
+        h->peer.pushed = true;
+    } else {
+        k_reduce_partials<<<h->R, 256, 0, h->stream>>>(h->d_partials, h->n_partials, h->d_acc, h->d_sigma, meas, write_energy ? 1 : 0);
+    }
     h->launches++;
 }
 
@@ -490,6 +514,11 @@ void enqueue_resident(csmc_handle *h, int n_cycles, int orc, int mc, int cone, i
 int finish(csmc_handle *h) {
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
+    if (h->peer.err && *h->peer.err) {
+        const int who = *h->peer.err - 1;
+        *h->peer.err = 0;
+        return fail(h, CSMC_ERR_NCCL, "peer-memory gather: rank " + std::to_string(who) + " did not deliver its measurement records in time");
+    }
     return CSMC_OK;
 }
 
@@ -532,6 +561,81 @@ void free_pt(csmc_handle *h) {
     cudaFree(h->d_ssf_sum); h->d_ssf_sum = nullptr; h->ssf_probes = 0;
 }
 
+void peer_gather_release(csmc_handle *h) {
+    auto &pg = h->peer;
+    for (int g = 0; g < PEER_MAX_RANKS; ++g) if (pg.peer[g]) { cudaIpcCloseMemHandle(pg.peer[g]); pg.peer[g] = nullptr; }
+    if (pg.base) { cudaFree(pg.base); pg.base = nullptr; }
+    if (pg.err) { cudaFreeHost(pg.err); pg.err = nullptr; }
+    pg.mode = 0; pg.seq = 0; pg.pushed = false; pg.ports = PeerPorts{};
+}
+
+// CSMC_PEER_GATHER=1|2 at csmc_comm_init (set it for every rank of the job or for none): every rank allocates
+// its mailbox, the CUDA IPC handles travel through the communicator, every rank maps every other rank's mailbox.
+// The outcome of the mapping is gathered too: unless every rank mapped every mailbox the NCCL collectives stay
+// in use (csmc_comm_mode tells).  Needs all ranks on one node with peer access (NVLink / NVSwitch on a B200 box).
+int peer_gather_setup(csmc_handle *h, int mode) {
+    peer_gather_release(h);
+    if (mode == 0 || h->n_ranks > PEER_MAX_RANKS) return CSMC_OK;   // default: nothing changes, no extra collective
+    auto &pg = h->peer;
+    constexpr size_t BYTES = 2u << 20, HEADER = 256;
+    struct Card { cudaIpcMemHandle_t handle; int32_t mode, ok; };   // what a rank tells the others
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    Card mine{};
+    mine.mode = mode; mine.ok = 0;
+    if (mode) {
+        bool ok = cudaMalloc((void **)&pg.base, BYTES) == cudaSuccess && cudaMemsetAsync(pg.base, 0, BYTES, h->stream) == cudaSuccess &&
+                  cudaIpcGetMemHandle(&mine.handle, pg.base) == cudaSuccess &&
+                  cudaHostAlloc((void **)&pg.err, sizeof(int), cudaHostAllocMapped) == cudaSuccess;
+        if (ok) *pg.err = 0;
+        else cudaGetLastError();
+        mine.ok = ok ? 1 : 0;
+    }
+    // exchange the cards (every rank takes part, whatever its own setting)
+    const int n = h->n_ranks;
+    std::vector<Card> cards(n);
+    unsigned char *d_cards = nullptr;
+    CK(dalloc(&d_cards, sizeof(Card) * n));
+    auto exchange = [&]() -> int {
+        cudaError_t ce = cudaMemcpyAsync(d_cards + sizeof(Card) * h->rank, &mine, sizeof(Card), cudaMemcpyHostToDevice, h->stream);
+        ncclResult_t nr = 0;
+        if (ce == cudaSuccess) nr = g_nccl.AllGather(d_cards + sizeof(Card) * h->rank, d_cards, sizeof(Card), ncclUint8, h->comm, h->stream);
+        if (ce == cudaSuccess && nr == 0) ce = cudaMemcpyAsync(cards.data(), d_cards, sizeof(Card) * n, cudaMemcpyDeviceToHost, h->stream);
+        if (ce == cudaSuccess && nr == 0) ce = cudaStreamSynchronize(h->stream);
+        if (ce != cudaSuccess) return fail(h, CSMC_ERR_CUDA, std::string("peer gather setup: ") + cudaGetErrorString(ce));
+        if (nr != 0) return fail(h, CSMC_ERR_NCCL, "peer gather setup: ncclAllGather failed");
+        return CSMC_OK;
+    };
+    int rc = exchange();
+    bool all = rc == CSMC_OK;
+    for (int g = 0; all && g < n; ++g) all = cards[g].mode == mode && cards[g].ok == 1;
+    if (all) {
+        for (int g = 0; g < n && mine.ok; ++g) {
+            if (g == h->rank) continue;
+            if (cudaIpcOpenMemHandle(&pg.peer[g], cards[g].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                pg.peer[g] = nullptr;
+                mine.ok = 0;
+            }
+        }
+    }
+    // second round: did every rank map every mailbox?  (also orders every rank's memset before any push)
+    if (rc == CSMC_OK) rc = exchange();
+    cudaFree(d_cards);
+    if (rc != CSMC_OK) { peer_gather_release(h); return rc; }
+    for (int g = 0; all && g < n; ++g) all = cards[g].ok == 1;
+    if (!all || mode == 0) { peer_gather_release(h); return CSMC_OK; }
+    pg.mode = mode;
+    pg.ports.n_ranks = n; pg.ports.rank = h->rank;
+    pg.ports.cap8 = (long long)((BYTES - HEADER) / 2 / sizeof(double));
+    for (int g = 0; g < n; ++g) {
+        unsigned char *b = g == h->rank ? pg.base : (unsigned char *)pg.peer[g];
+        pg.ports.flag[g] = (unsigned long long *)b;
+        pg.ports.mail[g] = (double *)(b + HEADER);
+    }
+    if (const char *e = std::getenv("CSMC_PEER_TIMEOUT_MS")) pg.timeout_ns = (unsigned long long)std::max(1L, std::atol(e)) * 1000000ULL;
+    return CSMC_OK;
+}
+
 // the ranks' replica blocks must tile [0, n_slots) in rank order (csmc_comm_init gathered them)
 int check_partition(csmc_handle *h) {
     if (!h->comm) return CSMC_OK;
@@ -553,6 +657,19 @@ int check_partition(csmc_handle *h) {
 // otherwise one grouped ncclBroadcast per rank
 int enqueue_gather_meas(csmc_handle *h) {
     if (!h->comm) return CSMC_OK;
+    if (peer_gather_active(h)) {
+        auto &pg = h->peer;
+        if (!pg.pushed) {
+            k_peer_push<<<h->n_ranks, 256, 0, h->stream>>>(pg.ports, h->d_meas_all + (size_t)h->replica_base * 8, h->R * 8,
+                                                           (long long)h->replica_base * 8, ++pg.seq);
+            h->launches++;
+        }
+        pg.pushed = false;
+        const double *mail = pg.ports.mail[h->rank] + (pg.seq & 1ULL) * pg.ports.cap8;
+        k_peer_wait<<<1, 256, 0, h->stream>>>(pg.ports.flag[h->rank], h->n_ranks, pg.seq, mail, h->d_meas_all, h->n_slots * 8, pg.err, pg.timeout_ns);
+        h->launches++;
+        return CSMC_OK;
+    }
     if (h->even_partition) {
         CKN(g_nccl.AllGather(h->d_meas_all + (size_t)h->replica_base * 8, h->d_meas_all, (size_t)h->R * 8, ncclFloat64, h->comm, h->stream));
     } else {
@@ -804,6 +921,7 @@ int32_t csmc_destroy(csmc_handle *h) {
     for (auto ev : h->aux_done) cudaEventDestroy(ev);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->jit_lib) cudaLibraryUnload(h->jit_lib);
+    peer_gather_release(h);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     free_pt(h);
     cudaFree(h->d_spins); cudaFree(h->d_spins_alt); cudaFree(h->d_stage); cudaFree(h->d_out); cudaFree(h->d_nbr); cudaFree(h->d_ref_of_pos);
@@ -1384,6 +1502,7 @@ int32_t csmc_comm_init(csmc_handle *h, int32_t n_ranks, int32_t rank, const uint
     if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(h, CSMC_ERR_INVALID, "bad rank / n_ranks");
     if (!load_nccl()) return fail(h, CSMC_ERR_NCCL, g_nccl.err);
     CK(cudaSetDevice(h->device));
+    peer_gather_release(h);
     if (h->comm) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
     ncclUniqueId u;
     std::memcpy(u.internal, id, 128);
@@ -1408,6 +1527,14 @@ int32_t csmc_comm_init(csmc_handle *h, int32_t n_ranks, int32_t rank, const uint
         h->rank_base[g] = (long long)part[2 * g]; h->rank_count[g] = (long long)part[2 * g + 1];
         if (h->rank_count[g] != h->R || h->rank_base[g] != (long long)g * h->R) h->even_partition = false;
     }
+    int peer_mode = 0;
+    if (const char *e = std::getenv("CSMC_PEER_GATHER")) peer_mode = std::max(0, std::min(2, std::atoi(e)));
+    return peer_gather_setup(h, peer_mode);
+}
+
+int32_t csmc_comm_mode(const csmc_handle *h, int32_t *mode) {
+    NEED(h); NEEDARG(h, mode);
+    *mode = !h->comm ? 0 : (h->peer.mode == 0 ? 1 : 1 + h->peer.mode);
     return CSMC_OK;
 }
 

@@ -297,10 +297,9 @@ __global__ void __launch_bounds__(TPB) k_energy(const __grid_constant__ P p, dou
 
 // second stage: one block per replica sums its partials in a fixed order (deterministic) and writes
 // the 8-double measurement record {E, Mx, My, Mz, accepted, 0, 0, 0}.
-__global__ void __launch_bounds__(256) k_reduce_partials(const double *__restrict__ partials, int n_partials,
-                                                         const unsigned long long *__restrict__ accepted,
-                                                         const double *__restrict__ sigma,
-                                                         double *__restrict__ meas, int write_energy) {
+__device__ __forceinline__ void reduce_record(const double *__restrict__ partials, int n_partials,
+                                              const unsigned long long *__restrict__ accepted,
+                                              const double *__restrict__ sigma, double *meas, int write_energy) {
     const int rep = blockIdx.x;
     double v[4] = {0, 0, 0, 0};
     for (int i = threadIdx.x; i < n_partials; i += 256) {
@@ -326,6 +325,13 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const double *__restric
         meas[(size_t)rep * 8 + 4] = (double)acc;
         meas[(size_t)rep * 8 + 5] = sigma[rep];   // cone width travels with the temperature slot
     }
+}
+
+__global__ void __launch_bounds__(256) k_reduce_partials(const double *__restrict__ partials, int n_partials,
+                                                         const unsigned long long *__restrict__ accepted,
+                                                         const double *__restrict__ sigma,
+                                                         double *__restrict__ meas, int write_energy) {
+    reduce_record(partials, n_partials, accepted, sigma, meas, write_energy);
 }
 
 // ---- evaluation kernels (API / parity tests): outputs in reference site order -------------------------
@@ -571,6 +577,87 @@ __global__ void k_pt_probe(PtState st, double *series_E, double *series_M, long 
     const double *mrec = st.meas_all + (size_t)rep * 8;
     series_E[index * st.n_slots + slot] = st.E_last[rep];
     series_M[index * st.n_slots + slot] = sqrt(mrec[1] * mrec[1] + mrec[2] * mrec[2] + mrec[3] * mrec[3]);
+}
+
+// ---- measurement records gathered by stores into peer memory (NVLink / NVSwitch) --------------------------
+// Opt-in alternative (CSMC_PEER_GATHER) to the ncclAllGather of the per-replica energies before an exchange
+// (src/monte_carlo.jl:321-343 sends them with MPI.Sendrecv!).  Every rank owns a mailbox
+// [2 parities][cap8 doubles] and one arrival flag per rank, mapped into every other process with CUDA IPC.
+// A gather with sequence number q: each rank stores its block of records into mailbox parity q & 1 of EVERY
+// rank, fences at system scope and publishes q in its flag there; each rank then waits until all of its own
+// flags reached q and copies the mailbox into meas_all.  A rank can be at most one gather ahead of another
+// (its next push comes after its own wait), so two parities suffice and flags only grow.
+constexpr int PEER_MAX_RANKS = 16;
+struct PeerPorts {
+    double *mail[PEER_MAX_RANKS];              // mailbox of every rank (own rank: the local pointer)
+    unsigned long long *flag[PEER_MAX_RANKS];  // arrival flags of every rank, [n_ranks] sequence numbers
+    int n_ranks, rank;
+    long long cap8;                            // doubles per mailbox parity
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// block g stores this rank's records mine[n_mine] at offset base8 of rank g's mailbox, then raises the flag
+__global__ void __launch_bounds__(256) k_peer_push(PeerPorts pp, const double *mine, int n_mine, long long base8, unsigned long long seq) {
+    const int g = blockIdx.x;
+    double *dst = pp.mail[g] + (seq & 1ULL) * pp.cap8 + base8;
+    for (int i = threadIdx.x; i < n_mine; i += blockDim.x) dst[i] = mine[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_sys(pp.flag[g] + pp.rank, seq);
+}
+
+// k_reduce_partials with the push folded in: block `rep` stores its 8-double record into every rank's mailbox;
+// the block that arrives last (counter *arrive, reset for the next launch) raises this rank's flag everywhere.
+__global__ void __launch_bounds__(256) k_reduce_partials_push(const double *__restrict__ partials, int n_partials,
+                                                              const unsigned long long *__restrict__ accepted,
+                                                              const double *__restrict__ sigma, double *meas, int write_energy,
+                                                              PeerPorts pp, long long base8, unsigned long long seq, unsigned int *arrive) {
+    reduce_record(partials, n_partials, accepted, sigma, meas, write_energy);
+    __syncthreads();
+    const int rep = blockIdx.x;
+    if ((int)threadIdx.x < pp.n_ranks * 8) {
+        const int g = threadIdx.x >> 3, c = threadIdx.x & 7;
+        pp.mail[g][(seq & 1ULL) * pp.cap8 + base8 + (long long)rep * 8 + c] = meas[(size_t)rep * 8 + c];
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ int sh_last;
+    if (threadIdx.x == 0) sh_last = (atomicAdd(arrive, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (sh_last) {
+        __threadfence_system();
+        if (threadIdx.x == 0) *arrive = 0u;
+        if ((int)threadIdx.x < pp.n_ranks) st_release_sys(pp.flag[threadIdx.x] + pp.rank, seq);
+    }
+}
+
+// waits until every rank's flag reached seq, then copies the local mailbox parity into meas_all[n8].  A peer
+// that never arrives (dead process) sets *err after timeout_ns instead of hanging the GPU.
+__global__ void __launch_bounds__(256) k_peer_wait(const unsigned long long *flags, int n_ranks, unsigned long long seq,
+                                                   const double *mail, double *__restrict__ meas_all, int n8,
+                                                   volatile int *err, unsigned long long timeout_ns) {
+    if ((int)threadIdx.x < n_ranks) {
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(flags + threadIdx.x) < seq) {
+            if (global_timer_ns() - t0 > timeout_ns) { *err = 1 + (int)threadIdx.x; break; }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n8; i += blockDim.x) meas_all[i] = __ldcv(mail + i);
 }
 
 }  // namespace csmc

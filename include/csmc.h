@@ -251,6 +251,15 @@ int32_t csmc_pt_init(csmc_handle *h, int32_t n_slots, const double *T_all);
  * ones with one grouped ncclBroadcast per rank). */
 int32_t csmc_comm_unique_id(uint8_t id[128]);
 int32_t csmc_comm_init(csmc_handle *h, int32_t n_ranks, int32_t rank, const uint8_t id[128]);
+/* How the per-replica measurement records (the energies of the exchange test, which the reference sends
+ * with MPI.Sendrecv!, src/monte_carlo.jl:321-343) travel between the ranks' GPUs:
+ * 0 no communicator, 1 NCCL collectives (default), 2 stores into peer memory (one push kernel + one wait
+ * kernel instead of the collective), 3 the same with the push folded into the energy reduction kernel.
+ * 2 / 3 are selected with the environment variable CSMC_PEER_GATHER=1 / 2, set identically for every rank
+ * before csmc_comm_init: each rank's mailbox is mapped into the other processes with CUDA IPC (one node,
+ * NVLink / NVSwitch peer access); if any rank cannot map a peer the job stays on 1.  Results do not depend
+ * on the mode. */
+int32_t csmc_comm_mode(const csmc_handle *h, int32_t *mode);
 
 typedef struct csmc_pt_params {
     int64_t t_thermalization;

@@ -145,6 +145,11 @@ function comm_unique_id()
 end
 comm_init!(e::Engine, n_ranks, rank, id::Vector{UInt8}) =
     check(e, ccall((:csmc_comm_init, libcsmc), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{UInt8}), e.ptr, n_ranks, rank, id))
+function comm_mode(e::Engine)
+    m = Ref{Int32}(0)
+    check(e, ccall((:csmc_comm_mode, libcsmc), Int32, (Ptr{Cvoid}, Ref{Int32}), e.ptr, m))
+    return Int(m[])
+end
 pt_init!(e::Engine, T_all::Vector{Float64}) =
     check(e, ccall((:csmc_pt_init, libcsmc), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}), e.ptr, length(T_all), T_all))
 pt_run!(e::Engine, p::CsmcPtParams, sweep_begin, sweep_end) =

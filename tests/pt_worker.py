@@ -15,7 +15,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from classicalspinmc.jl_b200 import _lib, parallel
+    from classicalspinmc.jl_b200 import _abi, _lib, parallel
     from classicalspinmc.jl_b200._abi import ModelData
     from oracle import oracle as orc
     from tests import models
@@ -34,11 +34,14 @@ def main():
     assert np.allclose(T_all, T_all_expected) and base == first and counts == per_rank
     p = dict(t_thermalization=200, t_measurement=600, probe_rate=20, swap_rate=10, overrelaxation_rate=5)
     seed = 2718
-    eng = _lib.Engine(md, n_replicas=R, seed=seed, device=local, replica_base=base)
+    # "passes": per-colour pass kernels instead of the resident kernel (the energy reduction then feeds the gather)
+    flags = (_abi.FLAG_JIT | _abi.FLAG_NO_RESIDENT) if "passes" in sys.argv[1:] else 0
+    eng = _lib.Engine(md, n_replicas=R, seed=seed, device=local, replica_base=base, flags=flags)
     for r in range(R):
         eng.set_spins(lat.randomize(seed=500 + base + r), replica=r)
     uid = parallel.broadcast_unique_id(_lib.comm_unique_id)
     eng.comm_init(world, rank, uid)
+    comm_mode = eng.comm_mode()      # 1 NCCL collectives, 2 / 3 stores into peer memory (CSMC_PEER_GATHER=1 / 2)
     eng.pt_init(T_all)
     eng.pt_run(p, 0, 400)
     eng.pt_run(p, 400, 800)
@@ -52,7 +55,7 @@ def main():
     all_spins = parallel.allgather_objects(spins)
     ok = True
     if rank == 0:
-        ref = _lib.Engine(md, n_replicas=R_total, seed=seed, device=local, replica_base=0)
+        ref = _lib.Engine(md, n_replicas=R_total, seed=seed, device=local, replica_base=0, flags=flags)
         for r in range(R_total):
             ref.set_spins(lat.randomize(seed=500 + r), replica=r)
         ref.pt_init(T_all)
@@ -66,7 +69,8 @@ def main():
         for r in range(R_total):
             assert np.array_equal(ref.get_spins(r), flat[r])
         assert ex.sum() > 0
-        print(json.dumps({"ok": True, "world": world, "exchanges": float(ex.sum()), "probes": int(E.shape[0])}))
+        print(json.dumps({"ok": True, "world": world, "exchanges": float(ex.sum()), "probes": int(E.shape[0]),
+                          "comm_mode": comm_mode, "kernel_mode": eng.kernel_mode}))
     dist.barrier()
     dist.destroy_process_group()
 

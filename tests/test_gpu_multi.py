@@ -32,6 +32,26 @@ def test_sharded_parallel_tempering_is_bit_identical_to_single_gpu(world, split)
     assert line["ok"] and line["world"] == world and line["exchanges"] > 0
 
 
+@pytest.mark.parametrize("world,split,kernels,peer", [(2, "even", "resident", 1), (2, "uneven", "passes", 1), (2, "even", "passes", 2),
+                                                      (8, "even", "passes", 2), (8, "uneven", "resident", 1)])
+def test_peer_memory_gather_is_bit_identical_to_single_gpu(world, split, kernels, peer):
+    """CSMC_PEER_GATHER=1 / 2: the measurement records travel by stores into CUDA-IPC-mapped peer memory instead of
+    ncclAllGather (csmc_comm_mode 2 / 3).  Opt-in path written in round 1 without multi-GPU time left to run it:
+    set CSMC_TEST_PEER_GATHER=1 to include it."""
+    if os.environ.get("CSMC_TEST_PEER_GATHER") != "1":
+        pytest.skip("peer-memory gather tests are opt-in (CSMC_TEST_PEER_GATHER=1)")
+    if _n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29540 + world + peer + (20 if split == "uneven" else 0)),
+           os.path.join(ROOT, "tests", "pt_worker.py"), split, kernels]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, CSMC_PEER_GATHER=str(peer)))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["ok"] and line["world"] == world and line["exchanges"] > 0
+    assert line["comm_mode"] == 1 + peer, "peers could not be mapped: the job fell back to the NCCL collectives"
+
+
 def test_parallel_tempering_driver_across_processes(tmp_path):
     """examples/parallel_tempering/runner.jl through the host mirror on 2 GPUs: slots block-partitioned over
     processes, files per temperature slot written by whichever process holds the slot's replica."""
