@@ -28,7 +28,7 @@ EXPORTS = [
     "csmc_metropolis", "csmc_metropolis_cone", "csmc_anneal_temperature", "csmc_anneal_temperature_cone", "csmc_set_temperatures",
     "csmc_set_sigma", "csmc_get_sigma",
     "csmc_cycles_async", "csmc_sync", "csmc_get_accepted", "csmc_pt_init", "csmc_comm_unique_id",
-    "csmc_comm_init", "csmc_comm_mode", "csmc_pt_run", "csmc_pt_exchange", "csmc_pt_get_slots", "csmc_pt_get_series",
+    "csmc_comm_init", "csmc_comm_mode", "csmc_replica_blocks", "csmc_pt_run", "csmc_pt_exchange", "csmc_pt_get_slots", "csmc_pt_get_series",
     "csmc_pt_get_stats", "csmc_pt_set_momenta", "csmc_pt_get_ssf",
 ]
 
@@ -74,6 +74,7 @@ def lib():
     L.csmc_kernel_mode.argtypes = [vp, P(i32)]
     L.csmc_autotune_report.argtypes = [vp, vp, P(i32)]
     L.csmc_sweep_groups.argtypes = [vp, P(i32), vp]
+    L.csmc_replica_blocks.argtypes = [vp, P(i32), vp]
     L.csmc_jit_check.argtypes = [P(CsmcModel), i32, vp, i64, P(i64), vp, i64]
     L.csmc_get_tables.argtypes = [vp, vp, vp, vp]
     L.csmc_set_spins.argtypes = [vp, i32, vp]
@@ -246,6 +247,13 @@ class Engine:
         g = C.c_int32()
         self._ck(self._L.csmc_sweep_groups(self._h, C.byref(g), ms))
         return int(g.value), tuple(float(v) for v in ms)
+
+    def replica_blocks(self):
+        """(replica blocks in use, (ms unblocked, ms blocked) of the create-time probe; zeros if not measured)."""
+        ms = (C.c_float * 2)()
+        b = C.c_int32()
+        self._ck(self._L.csmc_replica_blocks(self._h, C.byref(b), ms))
+        return int(b.value), tuple(float(v) for v in ms)
 
     @property
     def launches(self):

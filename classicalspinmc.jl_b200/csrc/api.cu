@@ -122,6 +122,8 @@ struct csmc_handle {
     std::map<int, cudaGraphExec_t> or_graphs;
     std::map<int, long long> or_graph_launches;
     // replica groups on separate streams (sweep_groups)
+    int n_blocks = 1;                  // replica blocks run one after the other (L2 residency), see enqueue_sweep_seq
+    float tune_blocks_ms[2] = {0.f, 0.f};   // autotune: ms per probe run unblocked / with n_blocks_wanted blocks
     int n_groups = 0;                  // 0: not decided yet
     float tune_groups_ms[3] = {0.f, 0.f, 0.f};   // autotune: ms per probe run with 1 / 2 / 4 groups
     std::vector<cudaStream_t> aux_streams;
@@ -285,13 +287,29 @@ int sweep_groups(csmc_handle *h, int n) {
     return n >= 2 ? h->n_groups : 1;
 }
 
-void enqueue_sweep_seq(csmc_handle *h, const SweepOp *seq, int n, bool fused) {
-    int i = 0;
-    const int G = (fused || n < 1) ? 1 : sweep_groups(h, n);
+// Replica blocks: when the spins of all R replicas do not fit in L2 but a sequence of n sweeps is enqueued at once
+// (a cycle graph: the OR block + the Metropolis sweep between two exchanges), the sequence runs block by block --
+// all n sweeps for the first R/B replicas, then for the next -- so that a block's spins are read from HBM once
+// and stay L2-resident for the 2n..4n colour passes of the sequence instead of streaming every replica through
+// L2 once per pass.  Replicas are independent between exchanges, so results do not change.  The count is chosen
+// at csmc_create (autotune: blocked vs unblocked timing; CSMC_REPLICA_BLOCKS overrides, CSMC_L2_BLOCK_MB sets
+// the per-block budget, default 64 MiB of the 126 MB L2).
+int replica_blocks_wanted(const csmc_handle *h) {
+    if (const char *e = std::getenv("CSMC_REPLICA_BLOCKS")) return std::max(1, std::min(std::atoi(e), h->R));
+    long budget_mb = 64;
+    if (const char *e = std::getenv("CSMC_L2_BLOCK_MB")) budget_mb = std::max(1L, std::atol(e));
+    const double bytes = (double)h->R * 3.0 * h->hm.npad * sizeof(double);
+    const int nb = (int)std::ceil(bytes / ((double)budget_mb * 1048576.0));
+    return std::max(1, std::min(nb, h->R));
+}
+
+// a sequence of n sweeps over the local replicas [rb, rb + rn), as G concurrent chains when replica groups are on
+void enqueue_sweep_seq_range(csmc_handle *h, const SweepOp *seq, int n, int rb, int rn) {
+    const int G = std::min(n < 1 ? 1 : sweep_groups(h, n), rn);
     if (G > 1) {
         cudaEventRecord(h->ev_fork, h->stream);
         for (int g = 0; g < G; ++g) {
-            const int r0 = (int)((long long)h->R * g / G), r1 = (int)((long long)h->R * (g + 1) / G);
+            const int r0 = rb + (int)((long long)rn * g / G), r1 = rb + (int)((long long)rn * (g + 1) / G);
             cudaStream_t st = g == 0 ? h->stream : h->aux_streams[g - 1];
             if (g > 0) cudaStreamWaitEvent(st, h->ev_fork, 0);
             for (int k = 0; k < n; ++k) enqueue_pass_sweep(h, seq[k], st, r0, r1 - r0);
@@ -299,14 +317,23 @@ void enqueue_sweep_seq(csmc_handle *h, const SweepOp *seq, int n, bool fused) {
         }
         return;
     }
+    for (int i = 0; i < n; ++i) enqueue_pass_sweep(h, seq[i], nullptr, rb, rn);
+}
+
+void enqueue_sweep_seq(csmc_handle *h, const SweepOp *seq, int n, bool fused) {
     if (fused && n >= 2) {
+        int i = 0;
         if (n & 1) enqueue_pass_sweep(h, seq[i++]);
         for (; i < n; i += 2) {
             launch_fused(h, seq[i].upd, h->d_spins, h->d_spins_alt, sweep_args(h, seq[i].ctr_off, seq[i].device_ctr));
             launch_fused(h, seq[i + 1].upd, h->d_spins_alt, h->d_spins, sweep_args(h, seq[i + 1].ctr_off, seq[i + 1].device_ctr));
         }
-    } else {
-        for (; i < n; ++i) enqueue_pass_sweep(h, seq[i]);
+        return;
+    }
+    const int B = n >= 2 ? std::max(1, std::min(h->n_blocks, h->R)) : 1;
+    for (int b = 0; b < B; ++b) {
+        const int r0 = (int)((long long)h->R * b / B), r1 = (int)((long long)h->R * (b + 1) / B);
+        enqueue_sweep_seq_range(h, seq, n, r0, r1 - r0);
     }
 }
 
@@ -769,6 +796,7 @@ int32_t csmc_create(const csmc_model *model, const csmc_opts *opts, csmc_handle 
         CKC(cudaStreamSynchronize(h->stream));
     }
     h->acc_base.assign(h->R, 0ULL);
+    if (std::getenv("CSMC_REPLICA_BLOCKS")) h->n_blocks = replica_blocks_wanted(h);   // otherwise 1 until the autotune decides
 
     // per-colour launch geometry and parameter blocks
     h->pass_blocks.assign(hm.n_colours, 1);
@@ -870,9 +898,20 @@ static int autotune_pdl(csmc_handle *h) {
     const int keep = h->tune_ms[1] < 0.97f * h->tune_ms[0] ? 1 : 0;
     install_jit_module(h, *mods[keep]);
     cudaLibraryUnload(mods[1 - keep]->lib);
+    float best_so_far = h->tune_ms[keep];
+    // replica blocks (enqueue_sweep_seq): all replicas per pass, or block by block so that a block stays in L2
+    if (!std::getenv("CSMC_REPLICA_BLOCKS") && replica_blocks_wanted(h) > 1) {
+        h->tune_blocks_ms[0] = best_so_far;
+        h->n_blocks = replica_blocks_wanted(h);
+        drop_graphs(h);
+        int rc = probe(h->tune_blocks_ms[1]); if (rc) return rc;
+        if (h->tune_blocks_ms[1] < 0.97f * best_so_far) best_so_far = h->tune_blocks_ms[1];
+        else h->n_blocks = 1;
+        drop_graphs(h);
+    }
     // replica groups on separate streams (enqueue_sweep_seq): 1, 2 or 4 concurrent chains
     if (!groups_from_env && h->R >= 2) {
-        h->tune_groups_ms[0] = h->tune_ms[keep];
+        h->tune_groups_ms[0] = best_so_far;
         int best_g = 1;
         float best_ms = h->tune_groups_ms[0];
         for (int gi = 1; gi <= 2; ++gi) {
@@ -958,6 +997,13 @@ int32_t csmc_sweep_groups(const csmc_handle *h, int32_t *groups, float ms[3]) {
     NEED(h);
     if (groups) *groups = std::max(1, h->n_groups);
     if (ms) for (int i = 0; i < 3; ++i) ms[i] = h->tune_groups_ms[i];
+    return CSMC_OK;
+}
+
+int32_t csmc_replica_blocks(const csmc_handle *h, int32_t *blocks, float ms[2]) {
+    NEED(h); NEEDARG(h, blocks);
+    *blocks = std::max(1, std::min(h->n_blocks, h->R));
+    if (ms) { ms[0] = h->tune_blocks_ms[0]; ms[1] = h->tune_blocks_ms[1]; }
     return CSMC_OK;
 }
 

@@ -155,6 +155,13 @@ int32_t csmc_autotune_report(const csmc_handle *h, float ms[2], int32_t *pdl_sel
  * ms[0..2] are those times (0 when not measured).  The environment variable CSMC_SWEEP_GROUPS
  * overrides.  Results do not depend on the group count (replicas are independent chains). */
 int32_t csmc_sweep_groups(const csmc_handle *h, int32_t *groups, float ms[3]);
+/* Replica blocks: when the spins of all replicas of the handle exceed the L2 budget (64 MiB; CSMC_L2_BLOCK_MB),
+ * a sequence of sweeps enqueued at once (the OR block + Metropolis sweep between two exchanges) can run block
+ * by block -- all sweeps for the first replicas, then for the next -- so that each block is read from HBM once
+ * and stays L2-resident for every colour pass of the sequence.  csmc_create times both and keeps the faster
+ * (ms[0] all replicas per pass, ms[1] blocked; 0 when not probed); CSMC_REPLICA_BLOCKS=n forces n blocks.
+ * Results do not depend on it (replicas are independent between exchanges). */
+int32_t csmc_replica_blocks(const csmc_handle *h, int32_t *blocks, float ms[2]);
 /* Host-only (no GPU needed): generate the specialised kernel source for `model` and, if
  * compile != 0, compile it with NVRTC for sm_100a.  source/log may be NULL; *_cap are buffer sizes;
  * *source_len receives the full source length.  Used by build checks and tests. */

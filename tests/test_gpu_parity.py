@@ -329,6 +329,49 @@ def test_replica_groups_do_not_change_results(monkeypatch, graph):
     assert outs[0][1].min() > 0 and outs[0][2].shape[0] > 0
 
 
+@pytest.mark.parametrize("graph", [0, FLAG_NO_GRAPH], ids=["graph", "plain"])
+def test_replica_blocks_do_not_change_results(monkeypatch, graph):
+    """Sequences of sweeps run over all replicas per pass, or block by block for L2 residency (csmc_replica_blocks),
+    alone or combined with concurrent replica groups inside a block; replicas are independent between exchanges,
+    so spins, acceptance counts and PT series are bit-identical."""
+    md = ModelData(models.kitaev_honeycomb(J3=0.25), (16, 12), 1.0)
+    R = 7
+    T = np.geomspace(0.2, 2.0, R)
+    p = dict(t_thermalization=60, t_measurement=120, probe_rate=10, swap_rate=5, overrelaxation_rate=5)
+    outs = []
+    for blocks, groups in (("1", "1"), ("2", "1"), ("3", "2"), ("7", "1"), ("99", "4")):
+        monkeypatch.setenv("CSMC_REPLICA_BLOCKS", blocks)
+        monkeypatch.setenv("CSMC_SWEEP_GROUPS", groups)
+        eng = _lib.Engine(md, n_replicas=R, seed=31, flags=FLAG_JIT | FLAG_NO_RESIDENT | graph)
+        assert eng.replica_blocks()[0] == min(int(blocks), R)
+        eng.randomize(3)
+        eng.set_temperatures(T)
+        eng.cycles_async(4, 5, 1)
+        eng.cycles_async(1, 0, 3)
+        eng.sync()
+        acc = eng.accepted().copy()
+        eng.pt_init(T)
+        eng.pt_run(p, 0, 180)
+        E, M = eng.pt_series()
+        outs.append((np.stack([eng.get_spins(r) for r in range(R)]), acc, E, M, eng.pt_slots()))
+    for o in outs[1:]:
+        for a, b in zip(o, outs[0]):
+            assert np.array_equal(a, b)
+    assert outs[0][1].min() > 0 and outs[0][2].shape[0] > 0
+
+
+def test_replica_blocks_autotune_reports_both_timings(monkeypatch):
+    """With more spins than the per-block L2 budget csmc_create times the blocked and the unblocked schedule and
+    keeps the faster; the choice is visible through csmc_replica_blocks."""
+    monkeypatch.delenv("CSMC_REPLICA_BLOCKS", raising=False)
+    monkeypatch.setenv("CSMC_L2_BLOCK_MB", "1")      # 8 replicas x 0.75 MiB -> 6 blocks wanted
+    md = ModelData(models.kitaev_honeycomb(), (128, 128), 1.0)
+    eng = _lib.Engine(md, n_replicas=8, seed=5, flags=FLAG_JIT | FLAG_NO_RESIDENT)
+    blocks, ms = eng.replica_blocks()
+    assert ms[0] > 0 and ms[1] > 0 and blocks in (1, 6)
+    assert (blocks == 6) == (ms[1] < 0.97 * ms[0])
+
+
 def test_anneal_temperature_schedule_matches_reference_loop():
     """csmc_anneal_temperature == the `while t < t_thermalization` loop of src/monte_carlo.jl:169-182."""
     md = ModelData(models.kitaev_honeycomb(), (4, 4), 1.0)
