@@ -138,6 +138,11 @@ def main():
             out(check="replica_blocks_identical_all", ok=bool(check_blocks_identical()), t=round(time.perf_counter() - t0, 1))
         elif item == "peer":
             out(check="peer_gather_all", ok=bool(check_peer()), t=round(time.perf_counter() - t0, 1))
+        elif item.startswith("sweep-"):       # throughput against the number of replica blocks
+            for name, builder, shape, S, R in cases["timing-" + item[6:]]:
+                for blocks in (1, 2, 3, 4, 6, 8, 12, 16, 32):
+                    if blocks <= R:
+                        time_workload(name, builder, shape, S, R, blocks)
         else:
             for name, builder, shape, S, R in cases[item]:
                 for blocks in (1, None):
