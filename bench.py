@@ -256,9 +256,10 @@ def run_pt(workload, L, world, rank, local_rank, stream, steps, warmup, sweeps_p
     value = updates / (ms * 1e-3)
     cfg.update(replicas=R_total, replicas_per_gpu=R, swap_rate=50, overrelaxation_rate=10, sweeps_per_step=sweeps_per_step,
                colours=n_col, kernel_mode=eng.kernel_mode, sweep_groups=eng.sweep_groups()[0],
-               exchange="temperatures swapped; energies via "
-                        + {0: "single GPU", 1: "ncclAllGather", 2: "peer-memory stores (push + wait kernels)",
-                           3: "peer-memory stores from the energy reduction kernel"}[eng.comm_mode()])
+               replica_blocks=eng.replica_blocks()[0],
+               exchange="temperatures swapped; "
+                        + {0: "single GPU", 1: "energies via ncclAllGather", 2: "energies via peer-memory stores (push + wait kernels)",
+                           3: "energies via peer-memory stores from the energy reduction kernel"}[eng.comm_mode()])
     return {"metric": "single-spin updates/sec (Metropolis+overrelax), parallel tempering", "value": value, "unit": "updates/s",
             "n_gpus": world, "steps": steps, "ms_per_step": ms / steps, "config": cfg,
             "exchanges_accepted": float(ex.sum()), "gpu_launches": int(eng.launches - l0),
