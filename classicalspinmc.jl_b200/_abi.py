@@ -66,6 +66,7 @@ FLAG_PDL = 16
 FLAG_NO_RESIDENT = 32
 FLAG_NO_AUTOTUNE = 64
 FLAG_FUSED = 128
+FLAG_SKEW = 256
 
 
 def resolve_field_onsite(uc):

@@ -28,7 +28,7 @@ EXPORTS = [
     "csmc_metropolis", "csmc_metropolis_cone", "csmc_anneal_temperature", "csmc_anneal_temperature_cone", "csmc_set_temperatures",
     "csmc_set_sigma", "csmc_get_sigma",
     "csmc_cycles_async", "csmc_sync", "csmc_get_accepted", "csmc_pt_init", "csmc_comm_unique_id",
-    "csmc_comm_init", "csmc_comm_mode", "csmc_replica_blocks", "csmc_pt_run", "csmc_pt_exchange", "csmc_pt_get_slots", "csmc_pt_get_series",
+    "csmc_comm_init", "csmc_comm_mode", "csmc_replica_blocks", "csmc_skew_schedule", "csmc_skew_info", "csmc_skew_geometry", "csmc_pt_run", "csmc_pt_exchange", "csmc_pt_get_slots", "csmc_pt_get_series",
     "csmc_pt_get_stats", "csmc_pt_set_momenta", "csmc_pt_get_ssf",
 ]
 
@@ -75,6 +75,9 @@ def lib():
     L.csmc_autotune_report.argtypes = [vp, vp, P(i32)]
     L.csmc_sweep_groups.argtypes = [vp, P(i32), vp]
     L.csmc_replica_blocks.argtypes = [vp, P(i32), vp]
+    L.csmc_skew_schedule.argtypes = [i32, i32, i32, i32, vp, i64, P(i64)]
+    L.csmc_skew_info.argtypes = [vp, P(i32), P(i32), P(i32), P(i32)]
+    L.csmc_skew_geometry.argtypes = [P(CsmcModel), P(i32), P(i32), P(i32), P(i32)]
     L.csmc_jit_check.argtypes = [P(CsmcModel), i32, vp, i64, P(i64), vp, i64]
     L.csmc_get_tables.argtypes = [vp, vp, vp, vp]
     L.csmc_set_spins.argtypes = [vp, i32, vp]
@@ -159,6 +162,29 @@ def jit_check(model: ModelData, compile: bool = True):
     if rc:
         raise CsmcError(f"csmc_jit_check failed ({rc}): {L.csmc_last_error(None).decode()}")
     return src.value.decode(), log.value.decode()
+
+
+def skew_schedule(n_rows: int, n_passes: int, reach: int, budget_rows: int):
+    """Host-only launch plan of the time-skewed strips (csmc_skew_schedule): int32 array (n, 3) of
+    (pass, first tile row, tile rows); empty when not applicable."""
+    L = lib()
+    n = C.c_int64(0)
+    rc = L.csmc_skew_schedule(n_rows, n_passes, reach, budget_rows, None, 0, C.byref(n))
+    if rc:
+        raise CsmcError(f"csmc_skew_schedule failed ({rc}): {L.csmc_last_error(None).decode()}")
+    out = np.zeros((n.value, 3), np.int32)
+    if n.value:
+        L.csmc_skew_schedule(n_rows, n_passes, reach, budget_rows, _p(out), n.value, C.byref(n))
+    return out
+
+
+def skew_geometry(model: ModelData):
+    """Host-only: (usable, CTA-tile rows along dimension 0, reach in rows, CTA tiles per row) of the time-skewed strips."""
+    v = [C.c_int32() for _ in range(4)]
+    rc = lib().csmc_skew_geometry(C.byref(model.struct), *[C.byref(x) for x in v])
+    if rc:
+        raise CsmcError(f"csmc_skew_geometry failed ({rc}): {lib().csmc_last_error(None).decode()}")
+    return bool(v[0].value), v[1].value, v[2].value, v[3].value
 
 
 def reference_tables(model: ModelData):
@@ -247,6 +273,12 @@ class Engine:
         g = C.c_int32()
         self._ck(self._L.csmc_sweep_groups(self._h, C.byref(g), ms))
         return int(g.value), tuple(float(v) for v in ms)
+
+    def skew_info(self):
+        """(usable, tile rows, reach in tile rows, L2 budget in tile rows) of the time-skewed strips (CSMC_FLAG_SKEW)."""
+        v = [C.c_int32() for _ in range(4)]
+        self._ck(self._L.csmc_skew_info(self._h, *[C.byref(x) for x in v]))
+        return bool(v[0].value), v[1].value, v[2].value, v[3].value
 
     def replica_blocks(self):
         """(replica blocks in use, (ms unblocked, ms blocked) of the create-time probe; zeros if not measured)."""

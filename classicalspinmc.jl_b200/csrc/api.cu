@@ -122,6 +122,7 @@ struct csmc_handle {
     std::map<int, cudaGraphExec_t> or_graphs;
     std::map<int, long long> or_graph_launches;
     // replica groups on separate streams (sweep_groups)
+    std::map<int, std::vector<SkewLaunch>> skew_cache;   // time-skewed launch plans by number of passes
     int n_blocks = 1;                  // replica blocks run one after the other (L2 residency), see enqueue_sweep_seq
     float tune_blocks_ms[2] = {0.f, 0.f};   // autotune: ms per probe run unblocked / with n_blocks_wanted blocks
     int n_groups = 0;                  // 0: not decided yet
@@ -172,14 +173,15 @@ template <class T> cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((void
 
 // one colour pass over the local replicas [a.rep0, a.rep0 + nrep) on `stream`
 template <int UPD>
-void launch_sweep_pass(csmc_handle *h, int colour, const SweepArgs &a, cudaStream_t stream, int nrep) {
+void launch_sweep_pass(csmc_handle *h, int colour, const SweepArgs &a, cudaStream_t stream, int nrep, int n_tiles = -1) {
     const int nseg = h->hm.colour_seg_begin[colour + 1] - h->hm.colour_seg_begin[colour];
     dim3 grid(h->pass_blocks[colour], nseg, nrep), block(TPB);
     if (h->jit) {
         // multi-dimensional CTA tiles over supercell coordinates, classes fused per thread (jit.cpp)
         void *args[] = {(void *)&h->d_spins, (void *)&a};
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(h->jit_plan.tiles[colour], (UPD >= UPD_METRO ? h->jit_plan.groups_metro : h->jit_plan.groups)[colour], nrep);
+        // n_tiles >= 0: only the CTA tiles [a.tile_off, a.tile_off + n_tiles) (time-skewed strips, kernels built with CSMC_SKEW)
+        cfg.gridDim = dim3(n_tiles >= 0 ? n_tiles : h->jit_plan.tiles[colour], (UPD >= UPD_METRO ? h->jit_plan.groups_metro : h->jit_plan.groups)[colour], nrep);
         cfg.blockDim = dim3(h->jit_plan.sweep_tpb);
         cfg.stream = stream;
         cudaLaunchAttribute attr[1];
@@ -287,6 +289,62 @@ int sweep_groups(csmc_handle *h, int n) {
     return n >= 2 ? h->n_groups : 1;
 }
 
+// Time-skewed strips (jit.cpp, skew_schedule): a lattice whose spins exceed L2 runs a sequence of n sweeps strip by
+// strip instead of pass by pass, each strip of CTA-tile rows staying L2-resident for all n * colours passes.
+// Opt-in (CSMC_FLAG_SKEW / CSMC_SKEW=1); results are bit-identical to the pass-by-pass order.
+long skew_budget_rows(const csmc_handle *h) {
+    double budget_mb = 64.0;
+    if (const char *e = std::getenv("CSMC_L2_BLOCK_MB")) budget_mb = std::max(0.001, std::atof(e));
+    const double row_bytes = 3.0 * sizeof(double) * (double)h->hm.N / std::max(1, h->jit_plan.skew_rows);
+    return (long)std::min(1e9, budget_mb * 1048576.0 / row_bytes);
+}
+
+// launch plan for a sequence of n sweeps (cached), or nullptr when the strips would vanish before the last pass
+const std::vector<SkewLaunch> *skew_plan_for(csmc_handle *h, int n, long budget) {
+    if (n < 2) return nullptr;
+    const int P = n * h->hm.n_colours;
+    auto it = h->skew_cache.find(P);
+    if (it == h->skew_cache.end())
+        it = h->skew_cache.emplace(P, skew_schedule(h->jit_plan.skew_rows, P, h->jit_plan.skew_reach, (int)budget)).first;
+    return it->second.empty() ? nullptr : &it->second;
+}
+
+void enqueue_skewed(csmc_handle *h, const SweepOp *seq, const std::vector<SkewLaunch> &plan) {
+    const int C = h->hm.n_colours, tpr = h->jit_plan.skew_tiles_per_row;
+    for (int rep = 0; rep < h->R; ++rep)
+        for (const SkewLaunch &L : plan) {
+            const SweepOp &op = seq[L.pass / C];
+            const int colour = L.pass % C;
+            SweepArgs a = sweep_args(h, op.ctr_off, op.device_ctr);
+            a.rep0 = rep;
+            a.tile_off = L.row0 * tpr;
+            switch (op.upd) {
+            case UPD_OR: launch_sweep_pass<UPD_OR>(h, colour, a, h->stream, 1, L.nrows * tpr); break;
+            case UPD_DET: launch_sweep_pass<UPD_DET>(h, colour, a, h->stream, 1, L.nrows * tpr); break;
+            case UPD_METRO: launch_sweep_pass<UPD_METRO>(h, colour, a, h->stream, 1, L.nrows * tpr); break;
+            default: launch_sweep_pass<UPD_CONE>(h, colour, a, h->stream, 1, L.nrows * tpr); break;
+            }
+        }
+}
+
+// A sequence of n sweeps as time-skewed strips, in chunks short enough that a strip boundary moves over at most a
+// quarter of the L2 budget (longer chunks leave too little of the first strip).  false: not applicable, nothing enqueued.
+bool enqueue_skewed_seq(csmc_handle *h, const SweepOp *seq, int n) {
+    if (!h->jit || !h->jit_plan.skew || n < 2) return false;
+    const long budget = skew_budget_rows(h);
+    if (budget >= h->jit_plan.skew_rows) return false;            // the whole lattice fits in the budget: nothing to gain
+    const int C = h->hm.n_colours, reach = std::max(1, h->jit_plan.skew_reach);
+    int chunk = std::min<long>(n, std::max<long>(2, (budget / (4L * reach) + 1) / C));
+    while (chunk >= 2 && !skew_plan_for(h, chunk, budget)) --chunk;
+    if (chunk < 2) return false;
+    for (int i = 0; i < n; i += chunk) {
+        const int len = std::min(chunk, n - i);
+        if (const std::vector<SkewLaunch> *plan = skew_plan_for(h, len, budget)) enqueue_skewed(h, seq + i, *plan);
+        else for (int k = 0; k < len; ++k) enqueue_pass_sweep(h, seq[i + k]);
+    }
+    return true;
+}
+
 // Replica blocks: when the spins of all R replicas do not fit in L2 but a sequence of n sweeps is enqueued at once
 // (a cycle graph: the OR block + the Metropolis sweep between two exchanges), the sequence runs block by block --
 // all n sweeps for the first R/B replicas, then for the next -- so that a block's spins are read from HBM once
@@ -296,10 +354,10 @@ int sweep_groups(csmc_handle *h, int n) {
 // the per-block budget, default 64 MiB of the 126 MB L2).
 int replica_blocks_wanted(const csmc_handle *h) {
     if (const char *e = std::getenv("CSMC_REPLICA_BLOCKS")) return std::max(1, std::min(std::atoi(e), h->R));
-    long budget_mb = 64;
-    if (const char *e = std::getenv("CSMC_L2_BLOCK_MB")) budget_mb = std::max(1L, std::atol(e));
+    double budget_mb = 64.0;
+    if (const char *e = std::getenv("CSMC_L2_BLOCK_MB")) budget_mb = std::max(0.001, std::atof(e));
     const double bytes = (double)h->R * 3.0 * h->hm.npad * sizeof(double);
-    const int nb = (int)std::ceil(bytes / ((double)budget_mb * 1048576.0));
+    const int nb = (int)std::ceil(bytes / (budget_mb * 1048576.0));
     return std::max(1, std::min(nb, h->R));
 }
 
@@ -330,6 +388,7 @@ void enqueue_sweep_seq(csmc_handle *h, const SweepOp *seq, int n, bool fused) {
         }
         return;
     }
+    if (enqueue_skewed_seq(h, seq, n)) return;
     const int B = n >= 2 ? std::max(1, std::min(h->n_blocks, h->R)) : 1;
     for (int b = 0; b < B; ++b) {
         const int r0 = (int)((long long)h->R * b / B), r1 = (int)((long long)h->R * (b + 1) / B);
@@ -420,8 +479,9 @@ struct JitModule {
 };
 
 // generate + compile (or fetch from the per-process cache) + load the kernels specialised for hm
-std::string load_jit_module(const HostModel &hm, bool pdl, JitModule &m, bool want_fused = false) {
+std::string load_jit_module(const HostModel &hm, bool pdl, JitModule &m, bool want_fused = false, bool want_skew = false) {
     m.plan.want_fused = want_fused;
+    m.plan.want_skew = want_skew;
     std::string err, log;
     std::vector<char> cubin;
     try {
@@ -480,6 +540,11 @@ std::string load_jit_module(const HostModel &hm, bool pdl, JitModule &m, bool wa
     return "";
 }
 
+bool want_skew(const csmc_handle *h) {
+    const char *e = std::getenv("CSMC_SKEW");
+    return (h->flags & CSMC_FLAG_SKEW) != 0 || (e && e[0] == '1');
+}
+
 void drop_graphs(csmc_handle *h) {
     for (auto &kv : h->cycle_graphs) cudaGraphExecDestroy(kv.second.exec);
     h->cycle_graphs.clear();
@@ -511,7 +576,7 @@ std::string build_jit(csmc_handle *h) {
         return h->jit_note;
     }
     JitModule m;
-    const std::string err = load_jit_module(hm, (h->flags & CSMC_FLAG_PDL) != 0, m, (h->flags & CSMC_FLAG_FUSED) != 0);
+    const std::string err = load_jit_module(hm, (h->flags & CSMC_FLAG_PDL) != 0, m, (h->flags & CSMC_FLAG_FUSED) != 0, want_skew(h));
     if (err.empty()) install_jit_module(h, m);
     else {
         if (m.lib) cudaLibraryUnload(m.lib);
@@ -863,7 +928,7 @@ static int autotune_pdl(csmc_handle *h) {
     if (!h->jit || (h->flags & (CSMC_FLAG_PDL | CSMC_FLAG_NO_AUTOTUNE | CSMC_FLAG_NO_GRAPH)) || h->hm.self_loop) return CSMC_OK;
     if (h->jit_resident && h->hm.N <= 4096 && !(h->flags & CSMC_FLAG_NO_RESIDENT)) return CSMC_OK;   // sweeps run on the resident kernel
     JitModule other;
-    if (!load_jit_module(h->hm, true, other, (h->flags & CSMC_FLAG_FUSED) != 0).empty()) { if (other.lib) cudaLibraryUnload(other.lib); cudaGetLastError(); return CSMC_OK; }
+    if (!load_jit_module(h->hm, true, other, (h->flags & CSMC_FLAG_FUSED) != 0, want_skew(h)).empty()) { if (other.lib) cudaLibraryUnload(other.lib); cudaGetLastError(); return CSMC_OK; }
     JitModule base;
     base.lib = h->jit_lib; for (int u = 0; u < 4; ++u) base.sweep[u] = h->jit_sweep[u];
     base.energy = h->jit_energy; base.resident = h->jit_resident; base.plan = h->jit_plan; base.pdl = false;
@@ -1000,6 +1065,51 @@ int32_t csmc_sweep_groups(const csmc_handle *h, int32_t *groups, float ms[3]) {
     return CSMC_OK;
 }
 
+int32_t csmc_skew_schedule(int32_t n_rows, int32_t n_passes, int32_t reach, int32_t budget_rows, int32_t *launches, int64_t cap, int64_t *n) {
+    if (!n) return fail(nullptr, CSMC_ERR_INVALID, "csmc_skew_schedule: NULL argument");
+    std::vector<SkewLaunch> plan;
+    try {
+        plan = skew_schedule(n_rows, n_passes, reach, budget_rows);
+    } catch (const std::exception &ex) {
+        return fail(nullptr, CSMC_ERR_NOMEM, ex.what());
+    }
+    *n = (int64_t)plan.size();
+    if (launches)
+        for (int64_t i = 0; i < std::min<int64_t>(cap, *n); ++i) {
+            launches[3 * i] = plan[i].pass; launches[3 * i + 1] = plan[i].row0; launches[3 * i + 2] = plan[i].nrows;
+        }
+    return CSMC_OK;
+}
+
+int32_t csmc_skew_geometry(const csmc_model *model, int32_t *usable, int32_t *tile_rows, int32_t *reach, int32_t *tiles_per_row) {
+    if (!model || !usable) return fail(nullptr, CSMC_ERR_INVALID, "csmc_skew_geometry: NULL argument");
+    HostModel hm;
+    std::string e;
+    JitPlan plan;
+    plan.want_skew = true;
+    try {
+        e = build_host_model(model, 0, hm);
+        if (e.empty() && hm.structured && !hm.self_loop) jit_generate_source(hm, false, &plan);
+    } catch (const std::exception &ex) {
+        e = std::string("csmc_skew_geometry: ") + ex.what();
+    }
+    if (!e.empty()) return fail(nullptr, CSMC_ERR_INVALID, e);
+    *usable = plan.skew ? 1 : 0;
+    if (tile_rows) *tile_rows = plan.skew_rows;
+    if (reach) *reach = plan.skew_reach;
+    if (tiles_per_row) *tiles_per_row = plan.skew_tiles_per_row;
+    return CSMC_OK;
+}
+
+int32_t csmc_skew_info(const csmc_handle *h, int32_t *usable, int32_t *tile_rows, int32_t *reach, int32_t *budget_rows) {
+    NEED(h); NEEDARG(h, usable);
+    *usable = (h->jit && h->jit_plan.skew) ? 1 : 0;
+    if (tile_rows) *tile_rows = h->jit_plan.skew_rows;
+    if (reach) *reach = h->jit_plan.skew_reach;
+    if (budget_rows) *budget_rows = *usable ? (int32_t)std::min<long>(skew_budget_rows(h), 1L << 30) : 0;
+    return CSMC_OK;
+}
+
 int32_t csmc_replica_blocks(const csmc_handle *h, int32_t *blocks, float ms[2]) {
     NEED(h); NEEDARG(h, blocks);
     *blocks = std::max(1, std::min(h->n_blocks, h->R));
@@ -1017,6 +1127,7 @@ int32_t csmc_jit_check(const csmc_model *model, int32_t compile, char *source, i
         if (e.empty() && !hm.structured) e = "model has no periodic colouring pattern: explicit-table kernels only";
         JitPlan plan;
         plan.want_fused = true;   // the build check covers the experimental fused kernels too
+        { const char *sk = std::getenv("CSMC_SKEW"); plan.want_skew = sk && sk[0] == '1'; }   // and, on request, the tile-offset variant
         if (e.empty()) src = jit_generate_source(hm, false, &plan);
         if (e.empty() && compile) {
             std::vector<char> cubin;

@@ -118,7 +118,17 @@ struct JitPlan {
     bool want_fused = false;     // in: also generate the fused full-sweep kernels (CSMC_FLAG_FUSED)
     bool fused = false;          // full-sweep kernel with shared-memory tiles (two-colour periodic models)
     int fused_tiles = 0, fused_smem = 0, fused_tpb = 256;
+    // time-skewed strips (api.cu, enqueue_skewed): launches over a range of CTA-tile rows along lattice dimension 0
+    bool want_skew = false;      // in: emit the sweep kernels with a tile offset (CSMC_SKEW)
+    bool skew = false;           // out: usable -- every colour has the same tiling, whole tile rows, no split sites
+    int skew_rows = 0;           // CTA-tile rows along dimension 0
+    int skew_tiles_per_row = 0;  // CTA tiles per tile row (grid.x = rows * tiles_per_row)
+    int skew_reach = 0;          // tile rows a site's neighbours can be away (>= 1)
 };   // per colour: grid.x (CTA tiles), grid.y (class groups)
+// launches (pass, first tile row, tile rows) that run P colour passes strip by strip without changing any result;
+// empty when the lattice is too small for the budget to matter (csmc_skew_schedule exports it for the tests)
+struct SkewLaunch { int pass, row0, nrows; };
+std::vector<SkewLaunch> skew_schedule(int n_rows, int n_passes, int reach, int budget_rows);
 std::string jit_generate_source(const HostModel &hm, bool pdl = false, JitPlan *plan = nullptr);
 std::string jit_compile(const std::string &src, std::vector<char> &cubin, std::string &log);
 

@@ -60,6 +60,9 @@ struct Gen {
         else idx = it->second;
         return "CSMC_K[" + std::to_string(idx) + "]";
     }
+    int max_delta0 = 0;                       // largest neighbour shift along dimension 0, in supercells
+    bool skew_ok = false;                     // see JitPlan::skew
+    int skew_T0 = 0, skew_NT0 = 0, skew_row = 0;
     std::map<std::tuple<int, int, int, int>, int> seg_of_class;
     explicit Gen(const HostModel &h) : hm(h) {
         for (size_t s = 0; s < hm.segs.size(); ++s)
@@ -76,6 +79,7 @@ struct Gen {
         }
         auto it = seg_of_class.find(std::make_tuple(t.nb_basis[k], r2[0], r2[1], r2[2]));
         if (it == seg_of_class.end()) return false;
+        max_delta0 = std::max(max_delta0, std::abs(delta[0]));
         const HostSeg &ns = hm.segs[it->second];
         o << "          int j" << k << ";\n          {\n";
         for (int d = 0; d < MAXD; ++d) {
@@ -529,6 +533,14 @@ struct Gen {
             if (hm.D == 1) T[0] = sw_tpb;
             for (int d = 0; d < MAXD; ++d) NT[d] = (M[d] + T[d] - 1) / T[d];
             plan.tiles[c] = NT[0] * NT[1] * NT[2];
+            // time-skewed strips need one tiling for all colours, whole tile rows along dimension 0 and every
+            // class of the colour spanning the full extent (so that a tile row means the same sites everywhere)
+            {
+                bool ok = hm.D >= 2 && M[0] % T[0] == 0 && NT[0] >= 2;
+                for (int s = s0; s < s1; ++s) ok = ok && hm.segs[s].M[0] == M[0];
+                if (c == 0) { skew_ok = ok; skew_T0 = T[0]; skew_NT0 = NT[0]; skew_row = NT[1] * NT[2]; }
+                else skew_ok = skew_ok && ok && skew_T0 == T[0] && skew_NT0 == NT[0] && skew_row == NT[1] * NT[2];
+            }
             // classes of the colour are fused in pairs into one thread (shared neighbour loads, ILP);
             // tuning knobs (environment, for A/B runs): CSMC_JIT_FUSE / CSMC_JIT_FUSE_METRO (classes per
             // thread), CSMC_JIT_MB / CSMC_JIT_MB_METRO (min resident CTAs per SM in __launch_bounds__)
@@ -537,6 +549,7 @@ struct Gen {
             const int mb_or = std::max(1, env_int("CSMC_JIT_MB", 1)), mb_mc = std::max(1, env_int("CSMC_JIT_MB_METRO", mb_or));
             int SPc = 1;
             for (int sg = s0; sg < s1; ++sg) SPc = std::max(SPc, seg_split[sg]);
+            if (SPc > 1) skew_ok = false;
             if (SPc > 1) {
                 // ---- heavy sites: SPc warps share one site (see segment()); tile = sw_tpb / SPc sites ----
                 const int TS = sw_tpb / SPc;
@@ -557,7 +570,7 @@ struct Gen {
                     o << "extern \"C\" __global__ void __launch_bounds__(" << sw_tpb << ", " << (u >= 2 ? mb_mc : mb_or) << ") csmc_sweep_c" << c << "_u" << u << "(double *spins, const SweepArgs a) {\n";
                     o << "#ifdef CSMC_PDL\n#if CSMC_PDL == 1\n    pdl_launch_dependents();\n#endif\n    pdl_wait();\n#endif\n";
                     o << "    __shared__ double part_g[" << (SPc - 1) << "][3][" << TS << "];\n";
-                    o << "    const int rep = blockIdx.z + a.rep0;\n    int t = blockIdx.x;\n";
+                    o << "    const int rep = blockIdx.z + a.rep0;\n    int t = blockIdx.x + CSMC_TILE_OFF(a);\n";
                     o << "    const int warp = threadIdx.x >> 5, part = warp % " << SPc << ", ls = (warp / " << SPc << ") * 32 + (threadIdx.x & 31);\n";
                     o << "    const int t2 = t % " << NTs[2] << "; t /= " << NTs[2] << "; const int t1 = t % " << NTs[1] << "; const int t0 = t / " << NTs[1] << ";\n";
                     o << "    const int l2 = ls & " << (Ts[2] - 1) << ", l1 = (ls >> " << ilog2(Ts[2]) << ") & " << (Ts[1] - 1) << ", l0 = ls >> " << (ilog2(Ts[2]) + ilog2(Ts[1])) << ";\n";
@@ -591,7 +604,7 @@ struct Gen {
                 if (u == 2) plan.groups_metro.resize(hm.n_colours), plan.groups_metro[c] = ngroups;
                 o << "extern \"C\" __global__ void __launch_bounds__(" << sw_tpb << ", " << (u >= 2 ? mb_mc : mb_or) << ") csmc_sweep_c" << c << "_u" << u << "(double *spins, const SweepArgs a) {\n";
                 o << "#ifdef CSMC_PDL\n#if CSMC_PDL == 1\n    pdl_launch_dependents();\n#endif\n    pdl_wait();\n#endif\n";
-                o << "    const int rep = blockIdx.z + a.rep0;\n    int t = blockIdx.x;\n";
+                o << "    const int rep = blockIdx.z + a.rep0;\n    int t = blockIdx.x + CSMC_TILE_OFF(a);\n";
                 o << "    const int t2 = t % " << NT[2] << "; t /= " << NT[2] << "; const int t1 = t % " << NT[1] << "; const int t0 = t / " << NT[1] << ";\n";
                 o << "    const int l2 = threadIdx.x & " << (T[2] - 1) << ", l1 = (threadIdx.x >> " << ilog2(T[2]) << ") & " << (T[1] - 1)
                   << ", l0 = threadIdx.x >> " << (ilog2(T[2]) + ilog2(T[1])) << ";\n";
@@ -613,6 +626,9 @@ struct Gen {
             for (int s = s0; s < s1; ++s) o << "    case " << (s - s0) << ": energy_site<Seg" << s << ">(spins, v); break;\n";
             o << "    default: break;\n    }\n    energy_block_reduce(v, partials, n_partials, partial_base);\n}\n";
         }
+        plan.skew = plan.want_skew && skew_ok;
+        plan.skew_rows = skew_NT0; plan.skew_tiles_per_row = skew_row;
+        plan.skew_reach = std::max(1, (max_delta0 + std::max(1, skew_T0) - 1) / std::max(1, skew_T0));
         emit_fused(plan);
         // ---- resident kernel: one CTA per replica keeps the whole lattice in shared memory and runs
         // whole sweep schedules (n_cycles x (or_per_cycle OR + metro_per_cycle Metropolis), then det_sweeps
@@ -712,7 +728,39 @@ std::string jit_generate_source(const HostModel &hm, bool pdl, JitPlan *plan) {
     JitPlan local;
     std::string src = g.run(plan ? *plan : local);
     const char *mode = std::getenv("CSMC_JIT_PDL_MODE");   // 1: trigger dependents at kernel start, 2: at kernel end
+    if (plan && plan->skew) src = "#define CSMC_SKEW 1\n" + src;
     return pdl ? std::string("#define CSMC_PDL ") + (mode && mode[0] == '2' ? "2" : "1") + "\n" + src : src;
+}
+
+// Time-skewed strips.  P colour passes over a lattice whose spins exceed L2 normally stream the whole lattice
+// through L2 P times.  Dependencies only reach `reach` tile rows, so the passes can instead be run strip by
+// strip -- all P passes on one strip of tile rows while it is L2-resident -- if the strip moves up by `reach`
+// rows per pass: a row then sees its neighbours exactly as the pass-by-pass order would show them (each
+// neighbour row has finished the previous pass and has not started the next one), so every site update reads
+// the same values and the result is bit-identical.  With periodic wrap the first strip shrinks from both sides
+// (nothing outside it has been updated yet), the following strips are parallelograms, and the last one grows
+// on both sides across the wrap.  Rows are CTA-tile rows along lattice dimension 0.
+std::vector<SkewLaunch> skew_schedule(int n_rows, int n_passes, int reach, int budget_rows) {
+    std::vector<SkewLaunch> out;
+    const int P = n_passes, d = std::max(1, reach);
+    const int shift = (P - 1) * d;                       // total movement of a strip boundary
+    // first strip W0 rows (shrinks to W0 - 2 shift), last strip Wc rows (grows to Wc + 2 shift = W0); on a lattice
+    // only slightly larger than the budget the two share it
+    const int W0 = std::min(budget_rows, (n_rows + 2 * shift) / 2), Wc = W0 - 2 * shift;
+    if (P < 2 || n_rows < 2 || budget_rows < 1 || Wc < 1) return out;
+    const int middle = n_rows - W0 - Wc;
+    const int n_mid = (middle + budget_rows - 1) / budget_rows;
+    std::vector<int> B;                                  // boundaries of the parallelogram strips at pass 0
+    for (int s = 0; s <= n_mid; ++s) B.push_back(W0 + (int)((long long)middle * s / std::max(1, n_mid)));
+    for (int p = 0; p < P; ++p) out.push_back({p, p * d, W0 - 2 * p * d});                 // shrinking first strip
+    for (int s = 0; s < n_mid; ++s)
+        for (int p = 0; p < P; ++p) out.push_back({p, B[s] - p * d, B[s + 1] - B[s]});    // parallelograms
+    const int BS = B.back();
+    for (int p = 0; p < P; ++p) {                                                          // growing last strip, wraps
+        out.push_back({p, BS - p * d, n_rows - (BS - p * d)});
+        if (p > 0) out.push_back({p, 0, p * d});
+    }
+    return out;
 }
 
 // returns "" on success

@@ -29,7 +29,16 @@ struct SweepArgs {
     unsigned long long seed;
     int replica_base;
     int rep0;
+#ifdef CSMC_SKEW
+    int tile_off;   // first CTA tile of this launch (time-skewed strips, api.cu); the host struct always carries it
+    int pad_;
+#endif
 };
+#ifdef CSMC_SKEW
+#define CSMC_TILE_OFF(a) ((a).tile_off)
+#else
+#define CSMC_TILE_OFF(a) 0
+#endif
 
 struct u4 { uint32_t x, y, z, w; };
 __device__ __forceinline__ u4 philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {

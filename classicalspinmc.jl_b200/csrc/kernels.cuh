@@ -30,7 +30,10 @@ struct SweepArgs {
     unsigned long long seed;
     int replica_base;                    // global index of local replica 0
     int rep0;                            // first local replica of this launch (replica groups on separate streams)
+    int tile_off;                        // first CTA tile of this launch: read only by runtime-specialised kernels built
+    int pad_;                            // with CSMC_SKEW (time-skewed strips); every other kernel's SweepArgs ends at rep0
 };
+static_assert(sizeof(SweepArgs) == 64, "SweepArgs layout (jit_prelude.h mirrors it)");
 
 // ---- Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11) --------------------------------------------
 struct u4 { uint32_t x, y, z, w; };

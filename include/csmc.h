@@ -102,6 +102,12 @@ typedef struct csmc_opts {
                                      two-colour periodic 1-D/2-D models).  Measured slower than the   \
                                      per-colour passes on B200 (shared-memory wavefront bound, see    \
                                      DESIGN.md section 5), kept for that comparison                   */
+#define CSMC_FLAG_SKEW 256        /* experimental, off by default (also CSMC_SKEW=1): a single lattice whose      \
+                                     spins exceed the L2 budget (64 MiB; CSMC_L2_BLOCK_MB) runs sequences of sweeps  \
+                                     as time-skewed strips of CTA-tile rows -- all colour passes of the sequence on   \
+                                     one strip while it is L2-resident, the strip moving one dependency reach per     \
+                                     pass -- instead of streaming the lattice through L2 once per pass.  Results are  \
+                                     bit-identical (csmc_skew_schedule, csmc_skew_info)                               */
 /* Default: models whose colouring is a periodic pattern get kernels specialised for that model
  * (unrolled terms, literal coefficients, constant geometry; compiled for sm_100a with NVRTC at
  * csmc_create) when n_sites * n_replicas >= 32768; smaller problems are launch-latency bound and
@@ -162,6 +168,20 @@ int32_t csmc_sweep_groups(const csmc_handle *h, int32_t *groups, float ms[3]);
  * (ms[0] all replicas per pass, ms[1] blocked; 0 when not probed); CSMC_REPLICA_BLOCKS=n forces n blocks.
  * Results do not depend on it (replicas are independent between exchanges). */
 int32_t csmc_replica_blocks(const csmc_handle *h, int32_t *blocks, float ms[2]);
+/* Time-skewed strips (CSMC_FLAG_SKEW).  csmc_skew_schedule is host-only: the launch plan for n_passes colour passes
+ * over n_rows CTA-tile rows when a site's neighbours are at most `reach` rows away and budget_rows rows fit in L2:
+ * launches[3 * i] = {pass, first row, rows}; *n = number of launches (0: not applicable, run pass by pass);
+ * at most cap triples are written.  Executed in that order every site update reads exactly the values the
+ * pass-by-pass order would give it (tests/test_host_plan.py checks this for the plan itself, the GPU tests for the
+ * spins).  csmc_skew_info: whether the handle's kernels can run such plans, and the geometry they would use. */
+int32_t csmc_skew_schedule(int32_t n_rows, int32_t n_passes, int32_t reach, int32_t budget_rows,
+                           int32_t *launches, int64_t cap, int64_t *n);
+int32_t csmc_skew_info(const csmc_handle *h, int32_t *usable, int32_t *tile_rows, int32_t *reach,
+                       int32_t *budget_rows);
+/* host-only: the strip geometry the specialised kernels of `model` would use (CTA-tile rows along lattice
+ * dimension 0, dependency reach in rows, CTA tiles per row); *usable = 0 when the model cannot be strip-mined */
+int32_t csmc_skew_geometry(const csmc_model *model, int32_t *usable, int32_t *tile_rows, int32_t *reach,
+                           int32_t *tiles_per_row);
 /* Host-only (no GPU needed): generate the specialised kernel source for `model` and, if
  * compile != 0, compile it with NVRTC for sm_100a.  source/log may be NULL; *_cap are buffer sizes;
  * *source_len receives the full source length.  Used by build checks and tests. */

@@ -372,6 +372,50 @@ def test_replica_blocks_autotune_reports_both_timings(monkeypatch):
     assert (blocks == 6) == (ms[1] < 0.97 * ms[0])
 
 
+SKEW_CASES = [("square-256", models.square_heisenberg, (256, 256), 1.0),
+              ("honeycomb-J3-512x64", lambda: models.kitaev_honeycomb(J3=0.25), (512, 64), 1.0),
+              ("triangular-multispin-1024x64", models.triangular_multispin, (1024, 64), 1.0),
+              ("square-open-512x128", models.square_heisenberg, (512, 128), 1.0)]
+
+
+@pytest.mark.parametrize("graph", [0, FLAG_NO_GRAPH], ids=["graph", "plain"])
+@pytest.mark.parametrize("name,builder,shape,S", SKEW_CASES, ids=[c[0] for c in SKEW_CASES])
+def test_time_skewed_strips_match_pass_by_pass_order(monkeypatch, name, builder, shape, S, graph):
+    """CSMC_FLAG_SKEW: sequences of sweeps run strip by strip (all colour passes on one strip of CTA-tile rows while
+    it is L2-resident, the strip moving one dependency reach per pass).  Every site update must read exactly what
+    the pass-by-pass order gives it: spins and acceptance counts are bit-identical, and the launch count shows
+    that the strips were actually used."""
+    from classicalspinmc.jl_b200._abi import FLAG_SKEW
+    monkeypatch.setenv("CSMC_L2_BLOCK_MB", "1")
+    monkeypatch.setenv("CSMC_SWEEP_GROUPS", "1")
+    md = ModelData(builder(), shape, S, bc="open" if "open" in name else "periodic")
+    R = 2
+    T = np.array([0.7, 1.3])
+    res = []
+    for flags in (FLAG_JIT | FLAG_NO_RESIDENT | graph, FLAG_JIT | FLAG_NO_RESIDENT | FLAG_SKEW | graph):
+        eng = _lib.Engine(md, n_replicas=R, seed=77, flags=flags)
+        usable, rows, reach, budget = eng.skew_info()
+        eng.randomize(5)
+        eng.set_temperatures(T)
+        l0 = eng.launches
+        eng.cycles_async(2, 2, 1)          # 2 x (2 OR + 1 Metropolis): sequences of 3 sweeps
+        eng.sync()
+        cyc_launches = eng.launches - l0
+        eng.overrelax(4)
+        eng.deterministic(2)
+        acc = eng.accepted().copy()
+        res.append((np.stack([eng.get_spins(r) for r in range(R)]), acc))
+        if flags & FLAG_SKEW:
+            assert usable and rows >= 8 and reach >= 1
+            plan = _lib.skew_schedule(rows, 3 * eng.n_colours, reach, budget)
+            assert len(plan) > 0, (rows, reach, budget)
+            assert cyc_launches == 2 * R * len(plan) + (0 if graph else 2), "the time-skewed plan was not used"
+        else:
+            assert not usable
+    assert np.array_equal(res[0][0], res[1][0])
+    assert np.array_equal(res[0][1], res[1][1]) and res[0][1].min() > 0
+
+
 def test_anneal_temperature_schedule_matches_reference_loop():
     """csmc_anneal_temperature == the `while t < t_thermalization` loop of src/monte_carlo.jl:169-182."""
     md = ModelData(models.kitaev_honeycomb(), (4, 4), 1.0)

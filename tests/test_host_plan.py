@@ -114,3 +114,51 @@ def test_jit_source_generation_and_nvrtc_compile():
     md2 = ModelData(models.square_heisenberg(), (11, 13), 1.0)     # no periodic pattern -> no specialisation
     with pytest.raises(_lib.CsmcError, match="explicit-table"):
         _lib.jit_check(md2, compile=False)
+
+
+def _check_skew_plan(n_rows, n_passes, reach, plan):
+    """Replays a launch plan on per-row pass counters: every row runs every pass exactly once and in order, and
+    whenever a row runs pass p each row within `reach` (periodic) has finished pass p - 1 and not finished pass
+    p + 1 -- the neighbours a site reads (always of another colour) then hold exactly the values of the
+    pass-by-pass order."""
+    done = np.zeros(n_rows, np.int64)          # passes finished per row
+    for p, row0, nrows in plan:
+        assert 0 <= row0 and nrows >= 1 and row0 + nrows <= n_rows, (p, row0, nrows)
+        rows = np.arange(row0, row0 + nrows)
+        assert (done[rows] == p).all(), f"pass {p} out of order on rows {row0}..{row0 + nrows}"
+        for k in range(1, reach + 1):
+            for nb in ((rows - k) % n_rows, (rows + k) % n_rows):
+                assert ((done[nb] == p) | (done[nb] == p + 1)).all(), f"pass {p}, rows {row0}+{nrows}: neighbour state"
+        done[rows] = p + 1
+    assert (done == n_passes).all()
+
+
+@pytest.mark.parametrize("n_rows,n_passes,reach,budget", [(512, 22, 1, 85), (512, 44, 1, 120), (64, 4, 1, 16), (1024, 22, 2, 170),
+                                                            (100, 6, 3, 40), (37, 2, 1, 5), (512, 22, 1, 43), (512, 22, 1, 44), (128, 12, 1, 85),
+                                                            (32, 6, 1, 21), (64, 6, 1, 200), (40, 22, 1, 30)])
+def test_time_skewed_strip_schedule_preserves_every_dependency(n_rows, n_passes, reach, budget):
+    plan = _lib.skew_schedule(n_rows, n_passes, reach, budget)
+    shift = (n_passes - 1) * reach
+    if min(budget, (n_rows + 2 * shift) // 2) - 2 * shift < 1:
+        assert len(plan) == 0          # the strips would vanish before the last pass: pass by pass
+        return
+    assert len(plan) > 0
+    _check_skew_plan(n_rows, n_passes, reach, [tuple(int(v) for v in row) for row in plan])
+    # the L2 working set: no launch is wider than the budget
+    assert plan[:, 2].max() <= budget
+
+
+def test_time_skewed_schedule_checker_rejects_a_wrong_plan():
+    plan = [tuple(int(v) for v in row) for row in _lib.skew_schedule(64, 4, 1, 16)]
+    unskewed = [(p, r0, n) for s in range(4) for p in range(4) for (r0, n) in [(16 * s, 16)]]   # strips that do not move
+    with pytest.raises(AssertionError):
+        _check_skew_plan(64, 4, 1, unskewed)
+    with pytest.raises(AssertionError):
+        _check_skew_plan(64, 4, 1, plan[:-1])
+
+
+def test_skew_kernels_compile_and_default_source_is_unchanged(monkeypatch):
+    md = ModelData(models.square_heisenberg(), (256, 256), 1.0)
+    monkeypatch.delenv("CSMC_SKEW", raising=False)
+    src, _ = _lib.jit_check(md, compile=False)
+    assert "#define CSMC_SKEW" not in src.split("typedef unsigned int uint32_t;")[0]
