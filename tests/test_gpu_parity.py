@@ -385,7 +385,9 @@ def test_time_skewed_strips_match_pass_by_pass_order(monkeypatch, name, builder,
     it is L2-resident, the strip moving one dependency reach per pass).  Every site update must read exactly what
     the pass-by-pass order gives it: spins and acceptance counts are bit-identical, and the launch count shows
     that the strips were actually used."""
-    from classicalspinmc.jl_b200._abi import FLAG_SKEW
+    from classicalspinmc.jl_b200._abi import FLAG_NO_AUTOTUNE, FLAG_SKEW
+    if "triangular" in name or "open" in name:
+        graph |= FLAG_NO_AUTOTUNE          # the cubic / quartic kernels take seconds to compile: one variant is enough
     monkeypatch.setenv("CSMC_L2_BLOCK_MB", "1")
     monkeypatch.setenv("CSMC_SWEEP_GROUPS", "1")
     md = ModelData(builder(), shape, S, bc="open" if "open" in name else "periodic")
@@ -409,7 +411,7 @@ def test_time_skewed_strips_match_pass_by_pass_order(monkeypatch, name, builder,
             assert usable and rows >= 8 and reach >= 1
             plan = _lib.skew_schedule(rows, 3 * eng.n_colours, reach, budget)
             assert len(plan) > 0, (rows, reach, budget)
-            assert cyc_launches == 2 * R * len(plan) + (0 if graph else 2), "the time-skewed plan was not used"
+            assert cyc_launches == 2 * R * len(plan) + (0 if graph & FLAG_NO_GRAPH else 2), "the time-skewed plan was not used"
         else:
             assert not usable
     assert np.array_equal(res[0][0], res[1][0])

@@ -13,7 +13,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from classicalspinmc.jl_b200 import _lib  # noqa: E402
-from classicalspinmc.jl_b200._abi import FLAG_JIT, FLAG_NO_RESIDENT, FLAG_SKEW, ModelData  # noqa: E402
+from classicalspinmc.jl_b200._abi import (FLAG_JIT, FLAG_NO_AUTOTUNE, FLAG_NO_GRAPH, FLAG_NO_RESIDENT, FLAG_SKEW,  # noqa: E402
+                                          ModelData)
 from tests import models  # noqa: E402
 
 
@@ -21,12 +22,12 @@ def out(**kw):
     print(json.dumps(kw), flush=True)
 
 
-def small(name, builder, shape, bc="periodic"):
+def small(name, builder, shape, bc="periodic", extra=0):
     os.environ["CSMC_L2_BLOCK_MB"] = "1"
     os.environ["CSMC_SWEEP_GROUPS"] = "1"
     md = ModelData(builder(), shape, 1.0, bc=bc)
     R, T, res, info = 2, np.array([0.7, 1.3]), [], {}
-    for flags in (FLAG_JIT | FLAG_NO_RESIDENT, FLAG_JIT | FLAG_NO_RESIDENT | FLAG_SKEW):
+    for flags in (FLAG_JIT | FLAG_NO_RESIDENT | extra, FLAG_JIT | FLAG_NO_RESIDENT | FLAG_SKEW | extra):
         eng = _lib.Engine(md, n_replicas=R, seed=77, flags=flags)
         usable, rows, reach, budget = eng.skew_info()
         eng.randomize(5)
@@ -41,7 +42,7 @@ def small(name, builder, shape, bc="periodic"):
         if flags & FLAG_SKEW:
             plan = _lib.skew_schedule(rows, 3 * eng.n_colours, reach, budget)
             info = dict(usable=usable, rows=rows, reach=reach, budget=budget, plan_launches=len(plan), cycle_launches=int(dl),
-                        strips_used=bool(len(plan) > 0 and dl == 2 * R * len(plan) + 2))
+                        strips_used=bool(len(plan) > 0 and dl == 2 * R * len(plan) + (0 if extra & FLAG_NO_GRAPH else 2)))
         eng.close()
     same = bool(np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1]))
     out(check="skew_identical", case=name, identical=same, accepted=res[0][1].tolist(), **info)
@@ -78,15 +79,19 @@ def big(L, n_cycles=10):
 
 def main():
     t0 = time.perf_counter()
+    if "more" in sys.argv[1:]:
+        small("square-open-512x128", models.square_heisenberg, (512, 128), bc="open", extra=FLAG_NO_AUTOTUNE)
+        small("square-256-plain-launches", models.square_heisenberg, (256, 256), extra=FLAG_NO_GRAPH)
+        small("triangular-multispin-1024x64", models.triangular_multispin, (1024, 64), extra=FLAG_NO_AUTOTUNE)
+        out(t=round(time.perf_counter() - t0, 1))
+        big(8192, 5)
+        out(t=round(time.perf_counter() - t0, 1))
+        return
     small("square-256", models.square_heisenberg, (256, 256))
     small("honeycomb-J3-512x64", lambda: models.kitaev_honeycomb(J3=0.25), (512, 64))
     out(t=round(time.perf_counter() - t0, 1))
     big(4096)
     out(t=round(time.perf_counter() - t0, 1))
-    if "more" in sys.argv[1:]:
-        small("square-open-512x128", models.square_heisenberg, (512, 128), bc="open")
-        big(8192, 5)
-        out(t=round(time.perf_counter() - t0, 1))
 
 
 if __name__ == "__main__":
