@@ -383,11 +383,15 @@ def run_ours(args):
 
     line = None
     if rank == 0:
+        sk_usable, sk_rows, _, sk_budget = eng.skew_info()
         cfg.update(cycle=f"{orc_} OR + {mc_} Metropolis", cycles_per_step=args.cycles_per_step,
+                   time_skewed_strips=bool(sk_usable and sk_budget < sk_rows),
                    colours=n_col, kernel_mode=eng.kernel_mode, parallelism=f"replicas x{world}",
                    launch_autotune=dict(zip(("ms_plain", "ms_pdl", "pdl_selected"), eng.autotune_report())),
                    l2=f"flushed between timed steps (256 MiB memset); lattice is {N * 24 / 2 ** 20:.0f} MiB "
-                      + ("(L2-resident within a step)" if N * 24 < 100 * 2 ** 20 else "(larger than L2: HBM-bound)"))
+                      + ("(L2-resident within a step)" if N * 24 < 100 * 2 ** 20 else
+                         "(larger than L2: the colour pass is HBM-bound; sweep sequences run strip by strip through L2)"
+                         if sk_usable and sk_budget < sk_rows else "(larger than L2: HBM-bound)"))
         line = {"metric": "single-spin updates/sec (Metropolis+overrelax)", "value": value, "unit": "updates/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -540,9 +540,15 @@ std::string load_jit_module(const HostModel &hm, bool pdl, JitModule &m, bool wa
     return "";
 }
 
+// kernels with a tile offset (time-skewed strips): on request (CSMC_FLAG_SKEW, CSMC_SKEW=1), never with CSMC_SKEW=0,
+// otherwise exactly when one replica's spins exceed the L2 budget -- smaller lattices keep the offset-free kernels
 bool want_skew(const csmc_handle *h) {
     const char *e = std::getenv("CSMC_SKEW");
-    return (h->flags & CSMC_FLAG_SKEW) != 0 || (e && e[0] == '1');
+    if (e && e[0] == '0') return false;
+    if ((h->flags & CSMC_FLAG_SKEW) != 0 || (e && e[0] == '1')) return true;
+    double budget_mb = 64.0;
+    if (const char *b = std::getenv("CSMC_L2_BLOCK_MB")) budget_mb = std::max(0.001, std::atof(b));
+    return 3.0 * sizeof(double) * (double)h->hm.npad > budget_mb * 1048576.0;
 }
 
 void drop_graphs(csmc_handle *h) {

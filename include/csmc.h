@@ -102,7 +102,9 @@ typedef struct csmc_opts {
                                      two-colour periodic 1-D/2-D models).  Measured slower than the   \
                                      per-colour passes on B200 (shared-memory wavefront bound, see    \
                                      DESIGN.md section 5), kept for that comparison                   */
-#define CSMC_FLAG_SKEW 256        /* experimental, off by default (also CSMC_SKEW=1): a single lattice whose      \
+#define CSMC_FLAG_SKEW 256        /* build the tile-offset kernels even for small lattices (also CSMC_SKEW=1;     \
+                                     CSMC_SKEW=0 never builds them; default: built when one replica's spins exceed    \
+                                     the L2 budget).  With them a single lattice whose                                \
                                      spins exceed the L2 budget (64 MiB; CSMC_L2_BLOCK_MB) runs sequences of sweeps  \
                                      as time-skewed strips of CTA-tile rows -- all colour passes of the sequence on   \
                                      one strip while it is L2-resident, the strip moving one dependency reach per     \

@@ -395,6 +395,7 @@ def test_time_skewed_strips_match_pass_by_pass_order(monkeypatch, name, builder,
     T = np.array([0.7, 1.3])
     res = []
     for flags in (FLAG_JIT | FLAG_NO_RESIDENT | graph, FLAG_JIT | FLAG_NO_RESIDENT | FLAG_SKEW | graph):
+        monkeypatch.setenv("CSMC_SKEW", "1" if flags & FLAG_SKEW else "0")    # "0": pass by pass whatever the lattice size
         eng = _lib.Engine(md, n_replicas=R, seed=77, flags=flags)
         usable, rows, reach, budget = eng.skew_info()
         eng.randomize(5)

@@ -28,6 +28,7 @@ def small(name, builder, shape, bc="periodic", extra=0):
     md = ModelData(builder(), shape, 1.0, bc=bc)
     R, T, res, info = 2, np.array([0.7, 1.3]), [], {}
     for flags in (FLAG_JIT | FLAG_NO_RESIDENT | extra, FLAG_JIT | FLAG_NO_RESIDENT | FLAG_SKEW | extra):
+        os.environ["CSMC_SKEW"] = "1" if flags & FLAG_SKEW else "0"
         eng = _lib.Engine(md, n_replicas=R, seed=77, flags=flags)
         usable, rows, reach, budget = eng.skew_info()
         eng.randomize(5)
@@ -55,6 +56,7 @@ def big(L, n_cycles=10):
     sig = []
     for flags in (0, FLAG_SKEW):
         t0 = time.perf_counter()
+        os.environ["CSMC_SKEW"] = "1" if flags & FLAG_SKEW else "0"
         eng = _lib.Engine(md, n_replicas=1, seed=3, flags=flags)
         t_create = time.perf_counter() - t0
         eng.randomize(7)
