@@ -123,6 +123,8 @@ struct csmc_handle {
     std::map<int, long long> or_graph_launches;
     // replica groups on separate streams (sweep_groups)
     std::map<int, std::vector<SkewLaunch>> skew_cache;   // time-skewed launch plans by number of passes
+    bool skew_off = false;             // autotune found the pass-by-pass order faster on this model
+    float tune_skew_ms[2] = {0.f, 0.f};   // autotune: ms per probe run pass by pass / strip by strip
     int n_blocks = 1;                  // replica blocks run one after the other (L2 residency), see enqueue_sweep_seq
     float tune_blocks_ms[2] = {0.f, 0.f};   // autotune: ms per probe run unblocked / with n_blocks_wanted blocks
     int n_groups = 0;                  // 0: not decided yet
@@ -330,7 +332,7 @@ void enqueue_skewed(csmc_handle *h, const SweepOp *seq, const std::vector<SkewLa
 // A sequence of n sweeps as time-skewed strips, in chunks short enough that a strip boundary moves over at most a
 // quarter of the L2 budget (longer chunks leave too little of the first strip).  false: not applicable, nothing enqueued.
 bool enqueue_skewed_seq(csmc_handle *h, const SweepOp *seq, int n) {
-    if (!h->jit || !h->jit_plan.skew || n < 2) return false;
+    if (!h->jit || !h->jit_plan.skew || h->skew_off || n < 2) return false;
     const long budget = skew_budget_rows(h);
     if (budget >= h->jit_plan.skew_rows) return false;            // the whole lattice fits in the budget: nothing to gain
     const int C = h->hm.n_colours, reach = std::max(1, h->jit_plan.skew_reach);
@@ -970,6 +972,21 @@ static int autotune_pdl(csmc_handle *h) {
     install_jit_module(h, *mods[keep]);
     cudaLibraryUnload(mods[1 - keep]->lib);
     float best_so_far = h->tune_ms[keep];
+    // time-skewed strips (enqueue_skewed_seq) were in use during the probes above if they apply to this lattice; unless
+    // they were asked for explicitly, time the pass-by-pass order too and keep the faster
+    {
+        const char *e = std::getenv("CSMC_SKEW");
+        const bool forced = (h->flags & CSMC_FLAG_SKEW) != 0 || (e && e[0] == '1');
+        if (!forced && h->jit_plan.skew && skew_budget_rows(h) < h->jit_plan.skew_rows) {
+            h->tune_skew_ms[1] = best_so_far;
+            h->skew_off = true;
+            drop_graphs(h);
+            int rc = probe(h->tune_skew_ms[0]); if (rc) return rc;
+            if (h->tune_skew_ms[0] < 0.97f * best_so_far) best_so_far = h->tune_skew_ms[0];
+            else h->skew_off = false;
+            drop_graphs(h);
+        }
+    }
     // replica blocks (enqueue_sweep_seq): all replicas per pass, or block by block so that a block stays in L2
     if (!std::getenv("CSMC_REPLICA_BLOCKS") && replica_blocks_wanted(h) > 1) {
         h->tune_blocks_ms[0] = best_so_far;
@@ -1109,7 +1126,7 @@ int32_t csmc_skew_geometry(const csmc_model *model, int32_t *usable, int32_t *ti
 
 int32_t csmc_skew_info(const csmc_handle *h, int32_t *usable, int32_t *tile_rows, int32_t *reach, int32_t *budget_rows) {
     NEED(h); NEEDARG(h, usable);
-    *usable = (h->jit && h->jit_plan.skew) ? 1 : 0;
+    *usable = (h->jit && h->jit_plan.skew && !h->skew_off) ? 1 : 0;
     if (tile_rows) *tile_rows = h->jit_plan.skew_rows;
     if (reach) *reach = h->jit_plan.skew_reach;
     if (budget_rows) *budget_rows = *usable ? (int32_t)std::min<long>(skew_budget_rows(h), 1L << 30) : 0;

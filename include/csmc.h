@@ -175,7 +175,8 @@ int32_t csmc_replica_blocks(const csmc_handle *h, int32_t *blocks, float ms[2]);
  * launches[3 * i] = {pass, first row, rows}; *n = number of launches (0: not applicable, run pass by pass);
  * at most cap triples are written.  Executed in that order every site update reads exactly the values the
  * pass-by-pass order would give it (tests/test_host_plan.py checks this for the plan itself, the GPU tests for the
- * spins).  csmc_skew_info: whether the handle's kernels can run such plans, and the geometry they would use. */
+ * spins).  csmc_skew_info: whether the handle runs such plans (its kernels carry the tile offset and the create-time
+ * probe did not find the pass-by-pass order faster), and the geometry they use. */
 int32_t csmc_skew_schedule(int32_t n_rows, int32_t n_passes, int32_t reach, int32_t budget_rows,
                            int32_t *launches, int64_t cap, int64_t *n);
 int32_t csmc_skew_info(const csmc_handle *h, int32_t *usable, int32_t *tile_rows, int32_t *reach,
