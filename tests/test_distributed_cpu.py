@@ -100,3 +100,22 @@ def test_bench_reference_arm_other_ranks_exit_quietly():
     import json
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+
+
+def test_bench_reference_arm_contract_fields():
+    """The reference arm's JSON line: same metric / unit / config keys as our arm, a cpu_baseline describing the run and
+    an e2e object with zero copies; the PT workloads run the reference's parallel-tempering loop."""
+    import json
+    import subprocess
+    for extra, metric_tail in ((["--L", "64"], "(Metropolis+overrelax)"),
+                               (["--workload", "C3", "--L", "16", "--replicas", "4", "--ref-sweeps", "20"], "parallel tempering")):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"] + extra,
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        line = json.loads(r.stdout.strip().splitlines()[-1])
+        assert line["impl"] == "reference" and line["metric"].endswith(metric_tail) and line["unit"] == "updates/s"
+        assert line["steps"] == 2 and line["warmup"] == 1 and line["higher_is_better"] is True and line["dtype"] == "f64"
+        assert line["value"] > 0 and line["ms_per_step"] > 0 and line["vs_baseline"] is None
+        assert line["cpu_baseline"]["value"] == line["value"] and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["sample"]
+        assert line["e2e"] == {"value": line["value"], "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+        assert line["config"]["workload"] in ("C2", "C3") and line["gpu_launches"] == 0
