@@ -521,8 +521,12 @@ struct Gen {
             plan.sweep_tpb = sw_tpb;
             int left = sw_tpb;
             const int last = hm.D - 1;
-            T[last] = std::min(std::min(32, pow2_ceil(M[last])), left);
-            if (hm.D == 3) T[last] = std::min(T[last], 16);
+            // CSMC_JIT_TLAST (A/B knob): tile extent along the fastest dimension; larger values make the tile rows that
+            // time-skewed strips move by thinner (32 -> 4 supercell rows per tile row in 2-D, 128 -> 1)
+            static const int tlast_env = std::getenv("CSMC_JIT_TLAST") ? std::atoi(std::getenv("CSMC_JIT_TLAST")) : 0;
+            const int tlast_max = (tlast_env == 16 || tlast_env == 32 || tlast_env == 64 || tlast_env == 128) ? tlast_env : 32;
+            T[last] = std::min(std::min(tlast_max, pow2_ceil(M[last])), left);
+            if (hm.D == 3 && !tlast_env) T[last] = std::min(T[last], 16);
             left /= T[last];
             for (int d = last - 1; d >= 0; --d) {
                 int want = (d == 0) ? left : std::min(left, std::max(1, (int)pow2_floor((int)std::max(1.0, std::sqrt((double)left)))));
