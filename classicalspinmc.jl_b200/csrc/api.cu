@@ -291,14 +291,20 @@ int sweep_groups(csmc_handle *h, int n) {
     return n >= 2 ? h->n_groups : 1;
 }
 
+// spins that replica blocks / time-skewed strips keep L2-resident at a time: 64 MiB of the 126 MB L2 (measured: blocks
+// of 64 MiB are resident, blocks of 96 MiB are not, profiles/r1c_replica_blocks_sweep.jsonl); CSMC_L2_BLOCK_MB overrides
+double l2_budget_bytes() {
+    double budget_mb = 64.0;
+    if (const char *e = std::getenv("CSMC_L2_BLOCK_MB")) budget_mb = std::max(0.001, std::atof(e));
+    return budget_mb * 1048576.0;
+}
+
 // Time-skewed strips (jit.cpp, skew_schedule): a lattice whose spins exceed L2 runs a sequence of n sweeps strip by
 // strip instead of pass by pass, each strip of CTA-tile rows staying L2-resident for all n * colours passes.
 // Opt-in (CSMC_FLAG_SKEW / CSMC_SKEW=1); results are bit-identical to the pass-by-pass order.
 long skew_budget_rows(const csmc_handle *h) {
-    double budget_mb = 64.0;
-    if (const char *e = std::getenv("CSMC_L2_BLOCK_MB")) budget_mb = std::max(0.001, std::atof(e));
     const double row_bytes = 3.0 * sizeof(double) * (double)h->hm.N / std::max(1, h->jit_plan.skew_rows);
-    return (long)std::min(1e9, budget_mb * 1048576.0 / row_bytes);
+    return (long)std::min(1e9, l2_budget_bytes() / row_bytes);
 }
 
 // launch plan for a sequence of n sweeps (cached), or nullptr when the strips would vanish before the last pass
@@ -356,10 +362,8 @@ bool enqueue_skewed_seq(csmc_handle *h, const SweepOp *seq, int n) {
 // the per-block budget, default 64 MiB of the 126 MB L2).
 int replica_blocks_wanted(const csmc_handle *h) {
     if (const char *e = std::getenv("CSMC_REPLICA_BLOCKS")) return std::max(1, std::min(std::atoi(e), h->R));
-    double budget_mb = 64.0;
-    if (const char *e = std::getenv("CSMC_L2_BLOCK_MB")) budget_mb = std::max(0.001, std::atof(e));
     const double bytes = (double)h->R * 3.0 * h->hm.npad * sizeof(double);
-    const int nb = (int)std::ceil(bytes / (budget_mb * 1048576.0));
+    const int nb = (int)std::ceil(bytes / l2_budget_bytes());
     return std::max(1, std::min(nb, h->R));
 }
 
@@ -548,9 +552,7 @@ bool want_skew(const csmc_handle *h) {
     const char *e = std::getenv("CSMC_SKEW");
     if (e && e[0] == '0') return false;
     if ((h->flags & CSMC_FLAG_SKEW) != 0 || (e && e[0] == '1')) return true;
-    double budget_mb = 64.0;
-    if (const char *b = std::getenv("CSMC_L2_BLOCK_MB")) budget_mb = std::max(0.001, std::atof(b));
-    return 3.0 * sizeof(double) * (double)h->hm.npad > budget_mb * 1048576.0;
+    return 3.0 * sizeof(double) * (double)h->hm.npad > l2_budget_bytes();
 }
 
 void drop_graphs(csmc_handle *h) {
