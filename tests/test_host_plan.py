@@ -209,3 +209,33 @@ def test_time_skewed_order_reproduces_colour_order_in_the_oracle(name, builder, 
             sel = sites[(colour == p % n_col) & (row_of >= r0) & (row_of < r1)]
             lat.overrelax(s_bad, sel, 1)
     assert not np.array_equal(s_bad, s_ref)
+
+
+def test_time_skewed_order_with_a_metropolis_sweep_in_the_oracle():
+    """Same check for a cycle of 2 overrelaxation sweeps + 1 Metropolis sweep (counter-based Philox stream per site, so
+    the visiting order cannot change the random numbers): spins and the accepted count are identical."""
+    md = ModelData(models.kitaev_honeycomb(J3=0.25), (64, 32), 1.0)
+    _, rows, reach, _ = _lib.skew_geometry(md)
+    colour, n_col, _, _ = _lib.plan(md)
+    lat = orc.OracleLattice(md)
+    row_of = _site_rows(md, rows)
+    sites = np.arange(1, md.n_sites + 1)
+    kinds = ["or", "or", "metro"]
+    T, seed = 0.6, 4242
+
+    def run(spins, sel, kind):
+        if kind == "or":
+            lat.overrelax(spins, sel, 1)
+            return 0
+        return lat.metropolis_philox(spins, sel, T, seed, 0, 7)
+
+    s_ref = lat.randomize(seed=3)
+    s_skew = s_ref.copy()
+    acc_ref = sum(run(s_ref, sites[colour == c], kinds[k]) for k in range(3) for c in range(n_col))
+    acc_skew = 0
+    plan = _lib.skew_schedule(rows, 3 * n_col, reach, 12)
+    assert len(plan) > 0
+    for p, row0, nrows in plan:
+        sel = sites[(colour == p % n_col) & (row_of >= row0) & (row_of < row0 + nrows)]
+        acc_skew += run(s_skew, sel, kinds[p // n_col])
+    assert np.array_equal(s_skew, s_ref) and acc_skew == acc_ref and 0 < acc_ref < md.n_sites
