@@ -1,15 +1,26 @@
 #!/usr/bin/env python
 """bench.py — single-spin updates/sec of the sweep hot path (BASELINE.json metric).
 
-Workload (config.workload = "C2"): BASELINE.json configs[1], square-lattice Heisenberg L=1024 with a
-z-field, single replica per GPU, cycle = 10 overrelaxation sweeps + 1 Metropolis sweep
-(checkerboard, 2 colours).  A "step" is `cycles_per_step` such cycles over the lattice.
-N > 1 GPUs: the path does not shard a single lattice ("replicas only"), so
-every rank runs an independent replica of the same workload (weak scaling, no collective); the
-parallel-tempering exchange path over NCCL is measured separately with --workload C3/C4.
+Headline workload (config.workload = "C2"): BASELINE.json configs[1], square-lattice Heisenberg L=1024 with a
+z-field, single replica per GPU, cycle = 10 overrelaxation sweeps + 1 Metropolis sweep (checkerboard, 2 colours).
+A "step" is `cycles_per_step` such cycles over the lattice.  N > 1 GPUs: the path does not shard a single lattice
+("replicas only"), so every rank runs an independent replica of the same workload (weak
+scaling, no collective).  The path that does shard — parallel tempering, replicas block-partitioned over the GPUs,
+per-replica energies gathered over NVLink, temperatures swapped — is measured in the same run at EVERY N
+(including 1) for C3 and C4 and printed under "pt", together with a bit-identity check of the sharded run against
+the single-GPU run ("pt_bit_identical").
 
-    python bench.py --gpus N --steps K --warmup W            # our arm
-    python bench.py --impl reference --gpus N --steps K --warmup W   # reference algorithm on host cores
+    python bench.py --gpus N --steps K --warmup W                      # our arm
+    python bench.py --impl reference --gpus N --steps K --warmup W     # reference algorithm on the host cores
+
+Keys beyond the base contract:
+  roofline       the dominant kernel (overrelaxation colour pass) on the headline workload, timed inside the same
+                 graph shape as `value` (replays of the 10-sweep OR block).  The 24 MiB lattice is L2-resident, so
+                 the bound is L2 bandwidth / latency, not HBM: `peak` is an L2-resident copy measured live.
+  roofline_hbm   the same kernel family where it IS HBM-bound: C2 at L=4096 (384 MiB), pass by pass, against the
+                 measured HBM copy bandwidth of MEASURED_PEAKS.json; `traffic` from the committed ncu capture.
+  cpu_baseline   the reference algorithm (C restatement, performance build -O3 -march=native) on the host cores:
+                 all-cores aggregate (`value`) and one thread (`single_thread`).
 """
 import argparse
 import json
@@ -25,28 +36,33 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 B_ALG = {2: 72.0, 4: 120.0}  # algorithmic bytes per single-spin update: 24 (C + 1), SURVEY.md 8(d)
+COLOURS = {"C2": 2, "C3": 2, "C4": 4, "C5": 4}
+L2_NOTE = ("GPU arm: L2 flushed between timed steps (256 MiB memset), the lattice is L2-resident within a step unless "
+           "it exceeds 64 MiB; CPU arm: not applicable")
 
 
 def workload_model(name, L=None):
-    from classicalspinmc.jl_b200._abi import ModelData
-    from tests import models
-    if name == "C2":
-        L = L or 1024
-        return ModelData(models.square_heisenberg(J=-1.0, h=(0.0, 0.0, 0.1)), (L, L), 1.0), dict(
-            workload="C2", lattice="square", L=L, model="Heisenberg J=-1 + h_z=0.1", T=1.0, replicas_per_gpu=1)
-    if name == "C3":
-        L = L or 256
-        return ModelData(models.kitaev_honeycomb(), (L, L), 1.0), dict(
-            workload="C3", lattice="honeycomb", L=L, model="Kitaev-Gamma K=-1 G=0.2 Gp=-0.02 h=0.1[111]")
-    if name == "C4":
-        L = L or 32
-        return ModelData(models.pyrochlore_local(), (L, L, L), 0.5), dict(
-            workload="C4", lattice="pyrochlore", L=L, model="local-frame Jxx/Jyy/Jzz + Zeeman")
-    if name == "C5":
-        L = L or 512
-        return ModelData(models.triangular_multispin(), (L, L), 1.0), dict(
-            workload="C5", lattice="triangular", L=L, model="Heisenberg + cubic + quartic")
-    raise SystemExit(f"unknown workload {name}")
+    from classicalspinmc.jl_b200 import workloads
+    try:
+        return workloads.workload_model(name, L)
+    except ValueError as e:
+        raise SystemExit(str(e))
+
+
+def make_config(args):
+    """The workload description both arms print (identical keys and values for the same command line)."""
+    from classicalspinmc.jl_b200.workloads import PT_DEFAULTS
+    md, cfg = workload_model(args.workload, args.L)
+    cfg["colours"] = COLOURS[args.workload]
+    if args.workload in PT_DEFAULTS:
+        d = PT_DEFAULTS[args.workload]
+        cfg.update(replicas=args.replicas or d["R"], T_range=[d["Tmin"], d["Tmax"]], swap_rate=50, overrelaxation_rate=10,
+                   probe_rate=2000, parallelism="replicas block-partitioned over the GPUs; temperatures swapped")
+    else:
+        cfg.update(cycle=f"{args.or_per_cycle} OR + {args.metro_per_cycle} Metropolis",
+                   parallelism="independent replicas, one per GPU (no collective)")
+    cfg["l2"] = L2_NOTE
+    return md, cfg
 
 
 class ClockSampler:
@@ -81,7 +97,7 @@ class ClockSampler:
                         self.reasons.add(n)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.05)
 
     def __enter__(self):
         if self.nv:
@@ -107,29 +123,27 @@ def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
-            return float(json.load(open(p))["hbm_gbs"]), "measured"
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
         except Exception:
             pass
-    return 6650.0, "fallback"
+    return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(workload, L=None):
+def ncu_traffic(key):
     """dram bytes per launch of the dominant kernel from the committed ncu --set full capture."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(p):
-        try:
-            d = json.load(open(p))
-            return d.get(f"{workload}:{L}") if (L and f"{workload}:{L}" in d) else (d.get(workload) if not L or L == 1024 else None)
-        except Exception:
-            return None
-    return None
+    try:
+        return json.load(open(p)).get(key)
+    except Exception:
+        return None
 
 
-def cpu_baseline(md, T, or_per_cycle, metro_per_cycle, n_cycles, threads):
-    """The oracle's restatement of the reference algorithm (random-site Metropolis with two energy()
-    evaluations, sequential overrelaxation) timed on the host cores: `threads` independent replicas."""
+# ---- CPU legs (the only places bench.py executes anything under oracle/) ---------------------------------------------
+def cpu_cycles(md, T, or_per_cycle, metro_per_cycle, n_cycles, threads):
+    """The oracle's restatement of the reference algorithm (random-site Metropolis with two energy() evaluations,
+    sequential overrelaxation), performance build, timed on the host cores: `threads` independent replicas."""
     from oracle import oracle as orc
-    lat = orc.OracleLattice(md)
+    lat = orc.OracleLattice(md, fast=True)
     spins = np.concatenate([lat.randomize(seed=12345, replica=r) for r in range(threads)])
     t0 = time.perf_counter()
     updates = lat.cycles(spins, threads, T, n_cycles, or_per_cycle, metro_per_cycle)
@@ -137,12 +151,12 @@ def cpu_baseline(md, T, or_per_cycle, metro_per_cycle, n_cycles, threads):
     return updates / dt, updates, dt
 
 
-def cpu_pt_baseline(md, T_all, sweeps, threads, swap_rate=50, rate=10, seed=3):
+def cpu_pt(md, T_all, sweeps, threads, swap_rate=50, rate=10, seed=3):
     """The oracle's restatement of the reference parallel-tempering loop (src/monte_carlo.jl:289-349: OR every
     sweep, random-site Metropolis + total_energy every `rate`-th, configuration-swapping exchange every
     `swap_rate`-th), one temperature per host thread as examples/parallel_tempering/README.txt:17."""
     from oracle import oracle as orc
-    lat = orc.OracleLattice(md)
+    lat = orc.OracleLattice(md, fast=True)
     R = len(T_all)
     spins = np.concatenate([lat.randomize(seed=12345, replica=r) for r in range(R)])
     t0 = time.perf_counter()
@@ -152,38 +166,38 @@ def cpu_pt_baseline(md, T_all, sweeps, threads, swap_rate=50, rate=10, seed=3):
     return updates / dt, updates, dt
 
 
+def cpu_flags():
+    from oracle import oracle as orc
+    return "gcc " + orc.FAST_CFLAGS
+
+
 def run_reference(args):
     """Reference arm: the reference's CPU algorithm for the workload (C restatement under oracle/, the
     reference itself is Julia and cannot run here) on all host threads; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import oracle as orc
-    md, cfg = workload_model(args.workload, args.L)
+    from classicalspinmc.jl_b200.workloads import PT_DEFAULTS
+    md, cfg = make_config(args)
     threads = args.cpu_threads or (os.cpu_count() or 1)
-    orc.lib()
     pt = args.workload in PT_DEFAULTS
     if pt:
-        d = PT_DEFAULTS[args.workload]
-        R = args.replicas or d["R"]
-        T_all = np.geomspace(d["Tmin"], d["Tmax"], R)
+        T_all = np.geomspace(cfg["T_range"][0], cfg["T_range"][1], cfg["replicas"])
         sweeps = args.ref_sweeps
 
         def step(n):
-            return cpu_pt_baseline(md, T_all, n, threads)
+            return cpu_pt(md, T_all, n, threads)
         one, warm = sweeps, 10
-        sample = (f"reference parallel-tempering loop, {R} temperatures on {threads} host threads, {sweeps} sweeps per "
+        sample = (f"reference parallel-tempering loop, {len(T_all)} temperatures on {threads} host threads, {sweeps} sweeps per "
                   f"step (swap 50, OR 10, total_energy after every Metropolis sweep, configurations swapped); "
-                  f"C restatement, not Julia")
-        cfg.update(replicas=R, swap_rate=50, overrelaxation_rate=10, sweeps_per_step=sweeps, l2="n/a (host)")
+                  f"C restatement, not Julia; {cpu_flags()}")
     else:
         def step(n):
-            return cpu_baseline(md, 1.0, args.or_per_cycle, args.metro_per_cycle, n, threads)
+            return cpu_cycles(md, 1.0, args.or_per_cycle, args.metro_per_cycle, n, threads)
         one, warm = args.ref_cycles, 1
         sample = (f"{threads} independent replicas (one per host thread, as one MPI rank per temperature) x "
                   f"{one} cycle(s) of the {cfg['workload']} lattice per step; reference algorithm unchanged "
-                  f"(C restatement, not Julia)")
-        cfg.update(cycle=f"{args.or_per_cycle} OR + {args.metro_per_cycle} Metropolis", l2="n/a (host)")
+                  f"(C restatement, not Julia); {cpu_flags()}")
     for _ in range(args.warmup):          # untimed: a short pass (pages in the lattice and the thread pool)
         step(warm)
     tot_u, tot_t = 0.0, 0.0
@@ -203,20 +217,22 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-PT_DEFAULTS = {"C3": dict(R=64, Tmin=0.01, Tmax=1.0), "C4": dict(R=128, Tmin=0.09 / 11.6, Tmax=14 / 11.6)}
-
-
-def run_pt(workload, L, world, rank, local_rank, stream, steps, warmup, sweeps_per_step, R_total=None):
+# ---- parallel tempering (the sharded path) ---------------------------------------------------------------------------
+def run_pt(workload, L, world, rank, local_rank, stream, steps, warmup, sweeps_per_step, R_total=None, single=False):
     """Parallel tempering (BASELINE configs[2]/[3]): R temperature slots block-partitioned over the
-    ranks' GPUs, per-replica energies gathered with NCCL on the sweep stream, temperatures exchanged
-    (csmc_pt_run).  swap_rate=50, overrelaxation_rate=10 (examples/parallel_tempering/input_file.jl:19-25)."""
+    ranks' GPUs, per-replica energies gathered over NVLink on the sweep stream, temperatures exchanged
+    (csmc_pt_run).  swap_rate=50, overrelaxation_rate=10 (examples/parallel_tempering/input_file.jl:19-25).
+    single=True: this process alone holds every replica (the N=1 point of the strong-scaling curve)."""
     import torch
     import torch.distributed as dist
 
     from classicalspinmc.jl_b200 import _lib, parallel
-    md, cfg = workload_model(workload, L)
+    from classicalspinmc.jl_b200.workloads import PT_DEFAULTS
+    md, _ = workload_model(workload, L)
     d = PT_DEFAULTS[workload]
     R_total = R_total or d["R"]
+    if single:
+        world, rank = 1, 0
     if R_total % world:
         raise SystemExit("replica count must divide over the GPUs")
     R = R_total // world
@@ -252,25 +268,82 @@ def run_pt(workload, L, world, rank, local_rank, stream, steps, warmup, sweeps_p
     updates = (steps * sweeps_per_step + n_metro) * float(eng.N) * R_total
     _, ex = eng.pt_stats()
     n_col = eng.n_colours
-    peak, kind = measured_peak_gbs()
+    peak, _ = measured_peak_gbs()
     value = updates / (ms * 1e-3)
-    cfg.update(replicas=R_total, replicas_per_gpu=R, swap_rate=50, overrelaxation_rate=10, sweeps_per_step=sweeps_per_step,
-               colours=n_col, kernel_mode=eng.kernel_mode, sweep_groups=eng.sweep_groups()[0],
-               replica_blocks=eng.replica_blocks()[0],
-               exchange="temperatures swapped; "
-                        + {0: "single GPU", 1: "energies via ncclAllGather", 2: "energies via peer-memory stores (push + wait kernels)",
-                           3: "energies via peer-memory stores from the energy reduction kernel"}[eng.comm_mode()])
-    return {"metric": "single-spin updates/sec (Metropolis+overrelax), parallel tempering", "value": value, "unit": "updates/s",
-            "n_gpus": world, "steps": steps, "ms_per_step": ms / steps, "config": cfg,
-            "exchanges_accepted": float(ex.sum()), "gpu_launches": int(eng.launches - l0),
-            "roofline_frac_of_updates": value / world * B_ALG.get(n_col, 24.0 * (n_col + 1)) / (peak * 1e9)}
+    out = {"workload": workload, "value": value, "unit": "updates/s", "n_gpus": world, "replicas": R_total, "replicas_per_gpu": R,
+           "steps": steps, "sweeps_per_step": sweeps_per_step, "ms_per_step": ms / steps,
+           "exchanges_accepted": float(ex.sum()), "gpu_launches": int(eng.launches - l0),
+           "engine": {"kernel_mode": eng.kernel_mode, "sweep_groups": eng.sweep_groups()[0], "replica_blocks": eng.replica_blocks()[0],
+                      "persistent_tiles": eng.persist_info()[0] if hasattr(eng, "persist_info") else 0,
+                      "exchange": {0: "single GPU", 1: "energies via ncclAllGather", 2: "energies via peer-memory stores (push + wait kernels)",
+                                   3: "energies via peer-memory stores from the energy reduction kernel"}[eng.comm_mode()]},
+           "hbm_roofline_frac_of_updates": value / world * B_ALG.get(n_col, 24.0 * (n_col + 1)) / (peak * 1e9)}
+    eng.close()
+    return out
+
+
+def pt_records(world, rank, local_rank, stream, args):
+    """The "pt" object of the bench line: C3 and C4 at this N, each with the single-GPU point measured in the same
+    process set (rank 0 alone, N > 1 only) and the strong-scaling efficiency value / (N * single-GPU value); plus the
+    bit-identity check of the sharded run against the single-GPU run on a small lattice (N > 1)."""
+    import torch.distributed as dist
+
+    from classicalspinmc.jl_b200 import parallel
+    out = {}
+    for wl in ("C3", "C4"):
+        rec = run_pt(wl, None, world, rank, local_rank, stream, args.pt_steps, 1, args.sweeps_per_step)
+        if world > 1:
+            if rank == 0:
+                one = run_pt(wl, None, world, rank, local_rank, stream, args.pt_steps, 1, args.sweeps_per_step, single=True)
+                rec["single_gpu_value"] = one["value"]
+                rec["pt_efficiency"] = rec["value"] / (world * one["value"])
+            dist.barrier()
+        else:
+            rec["single_gpu_value"] = rec["value"]
+            rec["pt_efficiency"] = 1.0
+        out[wl] = rec
+    ident = None
+    if world > 1:
+        checks = {}
+        for split in ("even", "uneven"):
+            checks[split] = parallel.pt_selfcheck(world, rank, local_rank, split)
+        ident = {"ok": all(c["ok"] for c in checks.values()), **checks}
+    return out, ident
+
+
+# ---- our arm ---------------------------------------------------------------------------------------------------------
+def l2_copy_peak(torch, stream, n_bytes=12 << 20, reps=50):
+    """GB/s (read + write) of an L2-resident device copy (src and dst together = the lattice's 24 MiB), replayed as a
+    CUDA graph so that launch gaps do not count: the live denominator of the L2-resident roofline."""
+    a = torch.empty(n_bytes, dtype=torch.uint8, device="cuda")
+    b = torch.empty(n_bytes, dtype=torch.uint8, device="cuda")
+    a.zero_()
+    for _ in range(3):
+        b.copy_(a)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=stream):
+        for _ in range(reps):
+            b.copy_(a)
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = 1e30
+    for _ in range(3):
+        e0.record(stream)
+        g.replay()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return 2.0 * n_bytes * reps / (best * 1e-3) / 1e9
 
 
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from classicalspinmc.jl_b200 import _lib
+    from classicalspinmc.jl_b200 import _abi, _lib
+    from classicalspinmc.jl_b200.workloads import PT_DEFAULTS
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -280,30 +353,33 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    if args.workload in PT_DEFAULTS:
-        stream = torch.cuda.Stream()
-        torch.cuda.set_stream(stream)
-        with ClockSampler(local_rank) as clk:
-            line = run_pt(args.workload, args.L, world, rank, local_rank, stream, args.steps, args.warmup, args.sweeps_per_step, args.replicas)
-        if rank == 0:
-            line.update(warmup=max(args.warmup, 1), higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
-                        data="synthetic", clocks=clk.summary())
-            print(json.dumps(line))
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return line
-
-    md, cfg = workload_model(args.workload, args.L)
+    md, cfg = make_config(args)
     # a real (non-NULL) stream: a NULL cudaStream_t in csmc_opts means "library creates its own", and
     # torch.cuda.Event only sees work on the stream it is recorded on
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
+
+    if args.workload in PT_DEFAULTS:
+        with ClockSampler(local_rank) as clk:
+            rec = run_pt(args.workload, args.L, world, rank, local_rank, stream, args.steps, args.warmup, args.sweeps_per_step, args.replicas)
+        if rank == 0:
+            line = {"metric": "single-spin updates/sec (Metropolis+overrelax), parallel tempering", "value": rec["value"], "unit": "updates/s",
+                    "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": rec["ms_per_step"],
+                    "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                    "config": cfg, "engine": rec["engine"], "exchanges_accepted": rec["exchanges_accepted"],
+                    "gpu_launches": rec["gpu_launches"], "hbm_roofline_frac_of_updates": rec["hbm_roofline_frac_of_updates"],
+                    "clocks": clk.summary()}
+            print(json.dumps(line))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
     eng = _lib.Engine(md, n_replicas=1, seed=12345 + rank, device=local_rank, stream=stream.cuda_stream)
     N = eng.N
     n_col = eng.n_colours
+    assert n_col == cfg["colours"]
     orc_, mc_ = args.or_per_cycle, args.metro_per_cycle
     updates_per_step = args.cycles_per_step * (orc_ + mc_) * N
     eng.randomize(12345 + rank)
@@ -337,24 +413,46 @@ def run_ours(args):
     ms = float(t.item())
     value = world * args.steps * updates_per_step / (ms * 1e-3)
 
-    # ---- dominant kernel: the overrelaxation colour pass, timed live ------------------------------------
-    n_or = 200
-    eng.cycles_async(20, 1, 0)
+    # ---- dominant kernel: the overrelaxation colour pass, timed live inside the same graph shape as `value`
+    # (replays of the `orc_`-sweep OR block of the cycle graph, no Metropolis sweeps) -------------------------
+    def time_or_block(e, or_sweeps, reps):
+        e.cycles_async(max(reps // 5, 2), or_sweeps, 0)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush.zero_()
+        a.record(stream)
+        e.cycles_async(reps, or_sweeps, 0)
+        b.record(stream)
+        barrier()
+        return a.elapsed_time(b) / reps          # ms per block
+    or_block = max(orc_, 1)
+    block_ms = time_or_block(eng, or_block, 100)
+    l_before = eng.launches
+    eng.cycles_async(1, or_block, 0)
+    launches_per_block = int(eng.launches - l_before)          # the library counts the launches of a graph replay
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    flush.zero_()
-    e0.record(stream)
-    eng.cycles_async(n_or, 1, 0)
-    e1.record(stream)
-    barrier()
-    pass_ms = e0.elapsed_time(e1) / (n_or * n_col)
-    bytes_per_launch = B_ALG.get(n_col, 24.0 * (n_col + 1)) * N / n_col
-    peak, peak_kind = measured_peak_gbs()
+    pass_ms = block_ms / launches_per_block
+    balg = B_ALG.get(n_col, 24.0 * (n_col + 1))
+    bytes_per_launch = balg * N * or_block / launches_per_block
     achieved = bytes_per_launch / (pass_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "csmc_sweep_c<colour>_u0 (overrelaxation colour pass)", "achieved": achieved, "peak": peak,
-                "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
-                "us_per_launch": pass_ms * 1e3, "algorithmic_bytes_per_launch": bytes_per_launch,
-                "traffic": ncu_traffic(cfg["workload"], cfg.get("L"))}
+    hbm_peak, hbm_kind = measured_peak_gbs()
+    l2_resident = N * 24 <= 64 * 2 ** 20
+    if l2_resident:
+        l2_peak = l2_copy_peak(torch, stream)
+        roofline = {"bound": "l2", "bound_note": "the 24 MiB lattice is L2-resident within a step: the pass is bound by L2 bandwidth and "
+                    "launch / load latency, not by HBM (see roofline_hbm for the HBM-bound point of the same kernel)",
+                    "achieved": achieved, "peak": l2_peak, "peak_kind": "measured live: L2-resident device copy (12 MiB -> 12 MiB, graph replay), read + write bytes",
+                    "unit": "GB/s", "frac": achieved / l2_peak, "frac_of_hbm_peak": achieved / hbm_peak}
+    else:
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "peak_kind": hbm_kind, "unit": "GB/s", "frac": achieved / hbm_peak}
+    pm = eng.persist_info() if hasattr(eng, "persist_info") else (0, 0, 0)
+    roofline.update(kernel=("csmc_persist (tile-resident multi-pass kernel: one launch per OR block)" if pm[0] else
+                            "csmc_sweep_c<colour>_u0 (overrelaxation colour pass)"),
+                    timed_as=f"replays of the {or_block}-sweep OR block graph ({launches_per_block} launch(es) per block)",
+                    us_per_launch=pass_ms * 1e3, us_per_colour_pass=block_ms * 1e3 / (or_block * n_col),
+                    algorithmic_bytes_per_launch=bytes_per_launch,
+                    traffic=ncu_traffic(f"{cfg['workload']}:{cfg['L']}" + (":persist" if pm[0] else "")),
+                    traffic_note="ncu flushes caches between replays: cold-cache figure (whole lattice read once); steady state ~0")
 
     # ---- end to end through the C-ABI with HOST buffers ---------------------------------------------------
     host_in = torch.empty((N, 3), dtype=torch.float64).pin_memory()
@@ -381,44 +479,74 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     e2e_value = world * args.steps * updates_per_step / float(tt.item())
 
-    line = None
+    sk_usable, sk_rows, _, sk_budget = eng.skew_info()
+    engine = dict(kernel_mode=eng.kernel_mode, cycles_per_step=args.cycles_per_step,
+                  time_skewed_strips=bool(sk_usable and sk_budget < sk_rows), persistent_tiles=pm[0],
+                  launch_autotune=dict(zip(("ms_plain", "ms_pdl", "pdl_selected"), eng.autotune_report())),
+                  lattice_MiB=N * 24 / 2 ** 20)
+    eng.close()
+
+    # ---- the same kernel family where it is HBM-bound: C2 at L=4096, pass by pass ------------------------------
+    roofline_hbm = None
+    if args.workload == "C2" and not args.no_hbm_point and rank == 0:
+        md4, _ = workload_model("C2", 4096)
+        e4 = _lib.Engine(md4, n_replicas=1, seed=1, device=local_rank, stream=stream.cuda_stream, flags=_abi.FLAG_NO_AUTOTUNE)
+        e4.randomize(7)
+        e4.set_temperatures(1.0)
+        ms4 = time_or_block(e4, 1, 40) / 2        # one sweep per graph: pass-by-pass order (no strips), 2 launches
+        b4 = 72.0 * e4.N / 2
+        a4 = b4 / (ms4 * 1e-3) / 1e9
+        roofline_hbm = {"bound": "hbm", "workload": "C2 at L=4096 (384 MiB of spins, 3x the L2)", "kernel": "csmc_sweep_c<colour>_u0 (overrelaxation colour pass)",
+                        "achieved": a4, "peak": hbm_peak, "peak_kind": hbm_kind, "unit": "GB/s", "frac": a4 / hbm_peak, "us_per_launch": ms4 * 1e3,
+                        "algorithmic_bytes_per_launch": b4, "traffic": ncu_traffic("C2:4096")}
+        # whole cycle at this size (time-skewed strips keep a strip of the lattice L2-resident across the 22 passes)
+        e4.cycles_async(3, orc_, mc_)
+        barrier_local = torch.cuda.synchronize
+        barrier_local()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        e4.cycles_async(10, orc_, mc_)
+        b.record(stream)
+        barrier_local()
+        roofline_hbm["cycle_updates_per_s"] = 10 * (orc_ + mc_) * e4.N / (a.elapsed_time(b) * 1e-3)
+        roofline_hbm["cycle_time_skewed_strips"] = bool(e4.skew_info()[0])
+        e4.close()
+    if world > 1:
+        dist.barrier()
+
+    pt, ident = (None, None)
+    if not args.no_pt:
+        pt, ident = pt_records(world, rank, local_rank, stream, args)
+
     if rank == 0:
-        sk_usable, sk_rows, _, sk_budget = eng.skew_info()
-        cfg.update(cycle=f"{orc_} OR + {mc_} Metropolis", cycles_per_step=args.cycles_per_step,
-                   time_skewed_strips=bool(sk_usable and sk_budget < sk_rows),
-                   colours=n_col, kernel_mode=eng.kernel_mode, parallelism=f"replicas x{world}",
-                   launch_autotune=dict(zip(("ms_plain", "ms_pdl", "pdl_selected"), eng.autotune_report())),
-                   l2=f"flushed between timed steps (256 MiB memset); lattice is {N * 24 / 2 ** 20:.0f} MiB "
-                      + ("(L2-resident within a step)" if N * 24 < 100 * 2 ** 20 else
-                         "(larger than L2: the colour pass is HBM-bound; sweep sequences run strip by strip through L2)"
-                         if sk_usable and sk_budget < sk_rows else "(larger than L2: HBM-bound)"))
         line = {"metric": "single-spin updates/sec (Metropolis+overrelax)", "value": value, "unit": "updates/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "engine": engine,
                 "roofline": roofline, "clocks": clk.summary(), "gpu_launches": int(gpu_launches),
                 "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": int(N * 24),
                         "d2h_bytes_per_step": int(N * 24 + 8)},
-                "roofline_frac_of_updates": value / world * B_ALG.get(n_col, 24.0 * (n_col + 1)) / (peak * 1e9)}
+                "hbm_roofline_frac_of_updates": value / world * balg / (hbm_peak * 1e9)}
+        if roofline_hbm:
+            line["roofline_hbm"] = roofline_hbm
+        if pt:
+            line["pt"] = pt
+        if ident is not None:
+            line["pt_bit_identical"] = ident["ok"]
+            line["pt_bit_identical_detail"] = ident
         if world == 1 and not args.no_cpu_baseline:
             threads = args.cpu_threads or (os.cpu_count() or 1)
-            n_ref = max(4 * args.ref_cycles, 16)          # ~10-20 s of CPU work
-            v, u, dtc = cpu_baseline(md, 1.0, orc_, mc_, n_ref, threads)
+            n_ref = max(2 * args.ref_cycles, 8)          # ~5-10 s of CPU work per leg
+            v, u, dtc = cpu_cycles(md, 1.0, orc_, mc_, n_ref, threads)
+            v1, u1, dt1 = cpu_cycles(md, 1.0, orc_, mc_, max(n_ref // 2, 2), 1)
             line["cpu_baseline"] = {"value": v, "unit": "updates/s", "cores": threads, "kind": "port",
                                     "sample": f"{threads} independent replicas x {n_ref} cycle(s) of the same "
-                                              f"lattice ({u:.3g} updates, {dtc:.1f} s); C restatement of the reference algorithm"}
-    if world > 1 and not args.no_pt:
-        # the path that actually exchanges data between GPUs: parallel tempering (configs[2]), short run
-        eng.close()
-        pt = run_pt("C3", None, world, rank, local_rank, stream, 3, 1, 550)
-        if rank == 0:
-            line["pt"] = pt
-    if rank == 0:
+                                              f"lattice ({u:.3g} updates, {dtc:.1f} s); C restatement of the reference algorithm; {cpu_flags()}",
+                                    "single_thread": {"value": v1, "cores": 1, "sample": f"1 replica x {max(n_ref // 2, 2)} cycles ({u1:.3g} updates, {dt1:.1f} s)"}}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    return line
 
 
 def main():
@@ -437,7 +565,9 @@ def main():
     ap.add_argument("--ref-sweeps", type=int, default=55, help="PT workloads: sweeps per step in the reference arm")
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-pt", action="store_true", help="N > 1: skip the extra parallel-tempering measurement")
+    ap.add_argument("--no-pt", action="store_true", help="skip the parallel-tempering records (C3, C4) and the bit-identity check")
+    ap.add_argument("--no-hbm-point", action="store_true", help="skip the L=4096 HBM-bound measurement of the dominant kernel")
+    ap.add_argument("--pt-steps", type=int, default=3, help="timed steps of the parallel-tempering records")
     ap.add_argument("--sweeps-per-step", type=int, default=550, help="PT workloads: sweeps per timed step")
     ap.add_argument("--replicas", type=int, default=None, help="PT workloads: total replicas")
     args = ap.parse_args()

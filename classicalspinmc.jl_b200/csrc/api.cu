@@ -95,6 +95,7 @@ struct csmc_handle {
     double *d_acc_slot = nullptr, *d_exch_slot = nullptr, *d_series_E = nullptr, *d_series_M = nullptr;
     int *d_slot_of_rep = nullptr, *d_rep_of_slot = nullptr, *d_accepted_pairs = nullptr, *d_prev_rep_of_slot = nullptr;
     long long series_cap = 0, n_probes = 0;
+    unsigned long long exchange_calls = 0;   // csmc_pt_exchange calls so far: Philox counter of their uniforms
     ncclComm_t comm = nullptr;
     int n_ranks = 1, rank = 0;
 
@@ -659,7 +660,7 @@ void free_pt(csmc_handle *h) {
     h->d_T_slot = h->d_meas_all = h->d_E_last = h->d_acc_prev_pt = h->d_acc_slot = h->d_exch_slot = nullptr;
     h->d_series_E = h->d_series_M = nullptr;
     h->d_slot_of_rep = h->d_rep_of_slot = h->d_accepted_pairs = h->d_prev_rep_of_slot = nullptr;
-    h->series_cap = 0; h->n_probes = 0; h->n_slots = 0;
+    h->series_cap = 0; h->n_probes = 0; h->n_slots = 0; h->exchange_calls = 0;
     cudaFree(h->d_ssf_sum); h->d_ssf_sum = nullptr; h->ssf_probes = 0;
 }
 
@@ -1848,7 +1849,9 @@ int32_t csmc_pt_exchange(csmc_handle *h, int32_t parity, int32_t *accepted_pairs
     int rc = enqueue_measure_all(h, true); if (rc) return rc;
     PtState st = pt_state(h);
     k_pt_update<<<(h->n_slots + 127) / 128, 128, 0, h->stream>>>(st, 1); h->launches++;
-    k_pt_exchange<<<1, 128, 0, h->stream>>>(st, parity & 1, (unsigned long long)(parity), h->seed); h->launches++;
+    // every call draws fresh uniforms: the Philox counter is a per-handle call index (offset past the range
+    // csmc_pt_run uses, sweep / swap_rate), `parity` only selects the pairing
+    k_pt_exchange<<<1, 128, 0, h->stream>>>(st, parity & 1, (1ULL << 48) + h->exchange_calls++, h->seed); h->launches++;
     if (accepted_pairs) CK(cudaMemcpyAsync(accepted_pairs, h->d_accepted_pairs, sizeof(int) * h->n_slots, cudaMemcpyDeviceToHost, h->stream));
     return finish(h);
 }

@@ -2,6 +2,7 @@
 // (unrolled interaction terms, literal coefficients, constant geometry) and compiles it to an
 // sm_100a cubin with NVRTC (loaded with dlopen so libcsmc.so has no link-time dependency on it).
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <array>
@@ -770,6 +771,12 @@ std::vector<SkewLaunch> skew_schedule(int n_rows, int n_passes, int reach, int b
 // returns "" on success
 // Optional on-disk cache of compiled cubins (CSMC_CACHE_DIR=<dir>), keyed by a hash of the generated
 // source: repeated runs of the same model skip NVRTC (seconds for cubic / quartic models).
+static uint64_t fnv1a(const char *p, size_t n) {
+    uint64_t h = 1469598103934665603ULL;
+    for (size_t i = 0; i < n; ++i) { h ^= (unsigned char)p[i]; h *= 1099511628211ULL; }
+    return h;
+}
+
 static std::string cache_path(const std::string &src) {
     const char *dir = std::getenv("CSMC_CACHE_DIR");
     if (!dir || !*dir) return "";
@@ -782,13 +789,23 @@ std::string jit_compile(const std::string &src, std::vector<char> &cubin, std::s
     std::lock_guard<std::mutex> lk(g_rtc_mu);
     const std::string cpath = cache_path(src);
     if (!cpath.empty()) {
+        // cache file = cubin followed by a 16-byte trailer {length, FNV-1a of the cubin}: a torn or foreign file is
+        // ignored (and recompiled) instead of being handed to the module loader
         if (FILE *f = std::fopen(cpath.c_str(), "rb")) {
             std::fseek(f, 0, SEEK_END);
             const long n = std::ftell(f);
             std::fseek(f, 0, SEEK_SET);
-            if (n > 0) { cubin.resize((size_t)n); if (std::fread(cubin.data(), 1, (size_t)n, f) != (size_t)n) cubin.clear(); }
+            std::vector<char> blob;
+            if (n > 16) { blob.resize((size_t)n); if (std::fread(blob.data(), 1, (size_t)n, f) != (size_t)n) blob.clear(); }
             std::fclose(f);
-            if (!cubin.empty()) return "";
+            if (!blob.empty()) {
+                uint64_t trailer[2];
+                std::memcpy(trailer, blob.data() + blob.size() - 16, 16);
+                if (trailer[0] == blob.size() - 16 && trailer[1] == fnv1a(blob.data(), blob.size() - 16)) {
+                    cubin.assign(blob.begin(), blob.end() - 16);
+                    return "";
+                }
+            }
         }
     }
     if (!load_nvrtc()) return g_rtc.err;
@@ -823,9 +840,11 @@ std::string jit_compile(const std::string &src, std::vector<char> &cubin, std::s
     rc = g_rtc.GetCUBIN(prog, cubin.data());
     g_rtc.DestroyProgram(&prog);
     if (rc == 0 && !cpath.empty()) {
-        const std::string tmp = cpath + ".tmp";
+        // per-process temporary name: the ranks of a job compile the same model at the same time
+        const std::string tmp = cpath + "." + std::to_string((long)getpid()) + ".tmp";
         if (FILE *f = std::fopen(tmp.c_str(), "wb")) {
-            const bool ok = std::fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+            const uint64_t trailer[2] = {(uint64_t)cubin.size(), fnv1a(cubin.data(), cubin.size())};
+            const bool ok = std::fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size() && std::fwrite(trailer, 1, 16, f) == 16;
             std::fclose(f);
             if (ok) std::rename(tmp.c_str(), cpath.c_str()); else std::remove(tmp.c_str());
         }

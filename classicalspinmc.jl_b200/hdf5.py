@@ -48,6 +48,24 @@ def _get(f, path):
     return f.data[path]
 
 
+def _jl(a):
+    """Julia <-> on-disk orientation.  HDF5.jl stores a column-major Julia array A[i1, ..., ik] with the dataspace
+    dimensions reversed (the bytes stay in place), so an HDF5 reader in C order (h5py, this module) sees
+    A.T[ik, ..., i1] (util/load.py:88-93 relies on it for ``spins``).  Every array in the reference's files goes
+    through this one function, on write and on read, so a file written by Julia reads back identically here and the
+    other way round; it is its own inverse."""
+    a = np.asarray(a)
+    return np.ascontiguousarray(a.transpose()) if a.ndim >= 2 else a
+
+
+def _set_jl(f, path, value):
+    _set(f, path, _jl(value))
+
+
+def _get_jl(f, path):
+    return _jl(_get(f, path))
+
+
 def _mkgroup(f, path):
     """create_group(...): the reference creates its groups even when they stay empty (src/hdf5.jl:37-71)
     and its reader iterates over them unconditionally (:92-116)."""
@@ -96,18 +114,19 @@ def dump_unit_cell(f, uc):
     """src/hdf5.jl:36-76"""
     for g in ("field", "onsite", "bilinear", "cubic", "quartic"):
         _mkgroup(f, "unit_cell/" + g)
-    _set(f, "unit_cell/lattice_vectors", np.stack(uc.lattice_vectors, axis=1))   # columns = a_i
-    _set(f, "unit_cell/basis", np.stack(uc.basis, axis=0))                        # n_basis x D
+    # Julia shapes: lattice_vectors D x D with columns a_i (:39), basis n_basis x D (:40), tensors [a, b, (c, (d))]
+    _set_jl(f, "unit_cell/lattice_vectors", np.stack(uc.lattice_vectors, axis=1))
+    _set_jl(f, "unit_cell/basis", np.stack(uc.basis, axis=0))
     for b, vec in uc.field:
         _set(f, f"unit_cell/field/{b}", vec)
     for b, mat in uc.onsite:
-        _set(f, f"unit_cell/onsite/{b}", mat)
+        _set_jl(f, f"unit_cell/onsite/{b}", mat)
     for b1, b2, mat, off in uc.bilinear:
-        _set(f, f"unit_cell/bilinear/({b1},{b2}),{_julia_tuple(off)}", mat)           # :60
+        _set_jl(f, f"unit_cell/bilinear/({b1},{b2}),{_julia_tuple(off)}", mat)           # :60
     for b1, b2, b3, mat, o2, o3 in uc.cubic:
-        _set(f, f"unit_cell/cubic/({b1},{b2},{b3}),{_julia_tuple(o2)},{_julia_tuple(o3)}", mat)   # :67
+        _set_jl(f, f"unit_cell/cubic/({b1},{b2},{b3}),{_julia_tuple(o2)},{_julia_tuple(o3)}", mat)   # :67
     for b1, b2, b3, b4, mat, o2, o3, o4 in uc.quartic:
-        _set(f, f"unit_cell/quartic/({b1},{b2},{b3},{b4}),{_julia_tuple(o2)},{_julia_tuple(o3)},{_julia_tuple(o4)}", mat)  # :74
+        _set_jl(f, f"unit_cell/quartic/({b1},{b2},{b3},{b4}),{_julia_tuple(o2)},{_julia_tuple(o3)},{_julia_tuple(o4)}", mat)  # :74
 
 
 def dump_metadata(f, mc):
@@ -139,23 +158,23 @@ def write_attributes(filename, d):
 def read_unit_cell(f):
     """src/hdf5.jl:81-120"""
     from .unit_cell import UnitCell
-    lv = np.asarray(_get(f, "unit_cell/lattice_vectors"))
+    lv = np.asarray(_get_jl(f, "unit_cell/lattice_vectors"))
     uc = UnitCell(*[lv[:, i] for i in range(lv.shape[1])])
-    for row in np.atleast_2d(_get(f, "unit_cell/basis")):
+    for row in np.atleast_2d(_get_jl(f, "unit_cell/basis")):
         uc.basis.append(np.array(row, dtype=np.float64))
     for key in _keys(f, "unit_cell/field"):
         uc.field.append((int(key), np.array(_get(f, f"unit_cell/field/{key}"))))
     for key in _keys(f, "unit_cell/onsite"):
-        uc.onsite.append((int(key), np.array(_get(f, f"unit_cell/onsite/{key}"))))
+        uc.onsite.append((int(key), np.array(_get_jl(f, f"unit_cell/onsite/{key}"))))
     for key in _keys(f, "unit_cell/bilinear"):
         (b1, b2), off = ast.literal_eval(key)                                    # eval(Meta.parse(key)), :103
-        uc.bilinear.append((b1, b2, np.array(_get(f, f"unit_cell/bilinear/{key}")), tuple(off)))
+        uc.bilinear.append((b1, b2, np.array(_get_jl(f, f"unit_cell/bilinear/{key}")), tuple(off)))
     for key in _keys(f, "unit_cell/cubic"):
         (b1, b2, b3), o2, o3 = ast.literal_eval(key)
-        uc.cubic.append((b1, b2, b3, np.array(_get(f, f"unit_cell/cubic/{key}")), tuple(o2), tuple(o3)))
+        uc.cubic.append((b1, b2, b3, np.array(_get_jl(f, f"unit_cell/cubic/{key}")), tuple(o2), tuple(o3)))
     for key in _keys(f, "unit_cell/quartic"):
         (b1, b2, b3, b4), o2, o3, o4 = ast.literal_eval(key)
-        uc.quartic.append((b1, b2, b3, b4, np.array(_get(f, f"unit_cell/quartic/{key}")), tuple(o2), tuple(o3), tuple(o4)))
+        uc.quartic.append((b1, b2, b3, b4, np.array(_get_jl(f, f"unit_cell/quartic/{key}")), tuple(o2), tuple(o3), tuple(o4)))
     return uc
 
 
@@ -177,7 +196,7 @@ def read_lattice(f):
 # ---- configuration file (src/hdf5.jl:164-270) ---------------------------------------------------------
 def _spins_for_file(spins):
     """Julia writes its 3 x N column-major array; h5py readers see (N, 3) (util/load.py:88-93)."""
-    return np.ascontiguousarray(np.asarray(spins).T)
+    return _jl(spins)
 
 
 def initialize_hdf5(mc, paramsfile, outpath=None, T=None, spins=None):
@@ -186,7 +205,7 @@ def initialize_hdf5(mc, paramsfile, outpath=None, T=None, spins=None):
     _set_attr(f, "T", float(mc.T if T is None else T))
     _set_attr(f, "paramsfile", paramsfile)
     _set(f, "spins", _spins_for_file(mc.lattice.spins if spins is None else spins))
-    _set(f, "site_positions", np.ascontiguousarray(mc.lattice.site_positions.T))
+    _set_jl(f, "site_positions", mc.lattice.site_positions)                      # Julia D x N
     f.close()
 
 
@@ -231,15 +250,15 @@ def write_final_observables(mc, outpath=None, spins=None, observables=None, T=No
 
 
 def overwrite_keys(fid, d):
-    """src/hdf5.jl:244-252"""
+    """src/hdf5.jl:244-252.  Arrays are given in the Julia orientation (e.g. SSF 9 x N_k, momenta D x N_k)."""
     for k, v in d.items():
-        _set(fid, k, v)
+        _set_jl(fid, k, v)
 
 
 def read_spin_configuration(lat, filename):
     """src/hdf5.jl:266-270"""
     f = _open(filename, "r")
-    lat.spins[:, :] = np.asarray(_get(f, "spins")).T
+    lat.spins[:, :] = _get_jl(f, "spins")
     f.close()
 
 

@@ -18,7 +18,11 @@ class SweepAlgorithm:
         self.kind = kind
 
     def __call__(self, mc, T: float) -> float:
-        eng = mc._device()
+        """``alg(mc, T)``: one sweep that mutates ``mc.lattice.spins`` like the reference's metropolis!(mc, T).  Called
+        on its own it uploads the host spins, sweeps and downloads the result; inside a driver that keeps the state on
+        the device (``mc._device_resident``) the copies are skipped."""
+        standalone = not getattr(mc, "_device_resident", False)
+        eng = mc._upload() if standalone else mc._device()
         if self.kind == "metropolis":
             acc = eng.metropolis(T, 1)
         elif self.kind == "adaptive":
@@ -31,6 +35,8 @@ class SweepAlgorithm:
                 "MetropolisConstraint / MetropolisConstraintAdaptive are out of scope: they call a global "
                 "user constraint per proposal, and metropolis_constraint! is broken in the reference "
                 "(undefined e_diff, src/metropolis.jl:44)")
+        if standalone:
+            mc._download()
         return float(acc[0])
 
 

@@ -168,15 +168,31 @@ def simulated_annealing(mc: MonteCarlo, schedule, T0: float = 1.0, alg=None):
             acc, sig = eng.anneal_temperature_cone(T, mc.sigma, kind == "adaptive", p.t_thermalization, p.overrelaxation_rate)
             R, mc.sigma = float(acc[0]), float(sig[0])
         else:
-            t = 1
-            while t < p.t_thermalization:                                       # :172-182
-                if p.overrelaxation_rate != 0:
-                    eng.overrelax(1)
-                    if t % p.overrelaxation_rate == 0:
-                        R += alg(mc, T)
-                else:
-                    R += alg(mc, T)
-                t += 1
+            # sweep by sweep through the alg(mc, T) seam.  The library's own algorithms work on the device copy
+            # (_device_resident); any other callable sees and may edit mc.lattice.spins, so the state is brought to
+            # the host before the call and back to the device after it.
+            own = isinstance(alg, SweepAlgorithm)
+
+            def call_alg():
+                if own:
+                    return alg(mc, T)
+                mc._download()
+                acc = alg(mc, T)
+                mc._upload()
+                return acc
+            mc._device_resident = own
+            try:
+                t = 1
+                while t < p.t_thermalization:                                   # :172-182
+                    if p.overrelaxation_rate != 0:
+                        eng.overrelax(1)
+                        if t % p.overrelaxation_rate == 0:
+                            R += call_alg()
+                    else:
+                        R += call_alg()
+                    t += 1
+            finally:
+                mc._device_resident = False
         _print_acceptance(T, R, accept_total)                                   # :183
         T = schedule(time)                                                      # :184
         time += 1

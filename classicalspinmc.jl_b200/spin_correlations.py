@@ -59,9 +59,9 @@ def compute_equal_time_structure_factor(path, dest):
     print("Collecting correlations from", len(files), "files")
     for name in files:
         f = h5._open(os.path.join(path, name), "r")
-        S = np.asarray(h5._get(f, "spin_correlations/SSF"), dtype=np.float64)
+        S = np.asarray(h5._get_jl(f, "spin_correlations/SSF"), dtype=np.float64)
         if ks is None:
-            ks = np.asarray(h5._get(f, "spin_correlations/SSF_momentum"))
+            ks = np.asarray(h5._get_jl(f, "spin_correlations/SSF_momentum"))
         f.close()
         total = S.copy() if total is None else total + S
     mean = total / len(files)

@@ -315,8 +315,10 @@ int32_t csmc_pt_set_momenta(csmc_handle *h, const double *lattice_vectors, const
                             const double *ks, int64_t n_k);
 int32_t csmc_pt_get_ssf(csmc_handle *h, double *sums, int64_t *n_probes);
 /* Replaces the exchange block alone (src/monte_carlo.jl:308-349) on fresh energies;
- * parity = (sweep / swap_rate) % 2.  accepted_pairs[n_slots] (may be NULL): 1 where the
- * pair starting at that slot swapped. */
+ * parity = (sweep / swap_rate) % 2 selects the pairing (:311-315) and nothing else: the uniforms of the
+ * acceptance test (:327-330) come from the shared Philox stream at a per-handle call index that advances
+ * with every call (reset by csmc_pt_init), so a caller's own loop over this export is a valid chain.
+ * accepted_pairs[n_slots] (may be NULL): 1 where the pair starting at that slot swapped. */
 int32_t csmc_pt_exchange(csmc_handle *h, int32_t parity, int32_t *accepted_pairs);
 /* slot_of_replica[n_slots] for ALL global replicas (identical on every rank). */
 int32_t csmc_pt_get_slots(csmc_handle *h, int32_t *slot_of_replica);

@@ -61,3 +61,7 @@ function susceptibility(obs::Observables, T, N)
     chi = (m[2] - m[1]^2) / (T * N)
     return chi, propagated_error(obs.magnetization, [-2.0 * m[1] / (T * N), 1 / (T * N)])
 end
+
+# the reference's signatures (src/observables.jl:36-63): observables, temperature and size taken from the driver state
+specific_heat(mc) = specific_heat(mc.observables, mc.T, mc.lattice.size)
+susceptibility(mc) = susceptibility(mc.observables, mc.T, mc.lattice.size)

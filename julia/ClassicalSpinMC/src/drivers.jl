@@ -50,11 +50,12 @@ mutable struct MonteCarlo
 end
 
 # hooks a host program overrides when it runs under MPI.jl (kept as plain functions so the package
-# loads without MPI):  comm_rank(), comm_size(), allgather_temperatures(T), bcast_bytes(v), barrier()
+# loads without MPI):  comm_rank(), comm_size(), allgather_temperatures(T), bcast_bytes(v), allgather_sigma(s), barrier()
 comm_rank() = 0
 comm_size() = 1
 allgather_temperatures(T::Vector{Float64}) = T
 bcast_bytes(v::Vector{UInt8}) = v
+allgather_sigma(sig::Vector{Float64}) = sig          # with MPI: element-wise merge of the ranks' non-NaN entries
 barrier() = nothing
 
 function MonteCarlo(T::Union{Float64,Vector{Float64}}, lattice::Lattice{D}, parameters::Dict{String,Int64};
@@ -217,6 +218,16 @@ function parallel_tempering!(mc::MonteCarlo, saveIC::Vector{Int64}=Int64[]; alg:
     pt_init!(e, T_all)
     set_sigma!(e, fill(Float64(mc.sigma), R))
     slotfile(s) = string(mc.outdir, mc.outprefix, "_", s, ".h5")
+    if out && !isempty(saveIC)                                   # src/monte_carlo.jl:278-283
+        if rank == 0
+            for s in saveIC
+                d = string(mc.outdir, "IC_", s)
+                isdir(d) || (println("Initializing IC collection on rank $s"); mkpath(d))
+            end
+        end
+        barrier()
+    end
+    acc_prev, exch_prev, t_prev = zeros(n_slots), zeros(n_slots), 0   # progress report state (src/helper.jl:26)
     rank == 0 && @printf("Running sweeps on %s.\n", Dates.format(Dates.now(), "dd u yyyy HH:MM:SS"))
     total = p.t_thermalization + p.t_measurement
     cp = CsmcPtParams(p.t_thermalization, p.t_measurement, p.probe_rate, p.swap_rate, p.overrelaxation_rate, algid)
@@ -244,12 +255,30 @@ function parallel_tempering!(mc::MonteCarlo, saveIC::Vector{Int64}=Int64[]; alg:
             end
         end
         sweep = nxt
-        if p.report_interval > 0 && sweep % p.report_interval == 0 && rank == 0
+        if p.report_interval > 0 && sweep % p.report_interval == 0
+            # print_runtime_statistics!, src/helper.jl:25-78: rates since the previous report, per temperature slot
+            # (== per MPI rank in the reference); the device keeps the counters per slot
             acc, exch = pt_stats(e, n_slots)
-            @printf("Sweep %d / %d (%.1f%%)\n", sweep, total, 100.0 * sweep / total)
-            for k in 1:n_slots
-                @printf("\t\tsimulation %d accepted updates : %.0f\texchanges : %.0f\n", k - 1, acc[k], exch[k])
+            sig = pt_sigma_by_slot(e, n_slots, base, R)
+            if rank == 0
+                dt = sweep - t_prev
+                rate = max(p.overrelaxation_rate, 1)
+                str = @sprintf("Sweep %d / %d (%.1f%%)\n", sweep, total, 100.0 * sweep / total)
+                str *= @sprintf("\t\tthermalized : %s\n", sweep >= p.t_thermalization ? "YES" : "NO")
+                for k in 1:n_slots
+                    local_rate = (acc[k] - acc_prev[k]) / (dt * mc.lattice.size / rate) * 100.0          # :30-31
+                    if n_slots == 1
+                        str *= @sprintf("\t\tupdate acceptance rate : %.2f%%\tsigma : %.2f\n", local_rate, sig[k])
+                    else
+                        attempted = (k == 1 || k == n_slots) ? dt / p.swap_rate / 2.0 : dt / p.swap_rate   # :39
+                        str *= @sprintf("\t\tsimulation %d update acceptance rate : %.2f%%\tsigma : %.2f\n", k - 1, local_rate, sig[k])
+                        str *= @sprintf("\t\tsimulation %d replica exchange acceptance rate : %.2f%%\n", k - 1,
+                                        (exch[k] - exch_prev[k]) / attempted * 100.0)
+                    end
+                end
+                print(str * "\n")
             end
+            acc_prev, exch_prev, t_prev = copy(acc), copy(exch), sweep
         end
     end
     mc.sigma = get_sigma(e)[1]
@@ -258,6 +287,14 @@ function parallel_tempering!(mc::MonteCarlo, saveIC::Vector{Int64}=Int64[]; alg:
         update_observables!(mc.observables_all[r], E[base+r, k], M[base+r, k])
     end
     download!(mc)          # configurations stay with their replicas; replica r sits in slot slots[base+r]
+    # the reference leaves at every rank the configuration that sits at that rank's temperature (it swaps
+    # configurations, src/monte_carlo.jl:336-347): re-order the local copies by slot where the slot is local
+    let slots = pt_slots(e, n_slots), byslot = Dict(slots[base+r] => mc.replica_spins[r] for r in 1:R)
+        if all(haskey(byslot, base + r - 1) for r in 1:R)      # single process: every slot is local
+            mc.replica_spins = [byslot[base+r-1] for r in 1:R]
+            mc.lattice.spins = mc.replica_spins[1]
+        end
+    end
     if out
         slots = pt_slots(e, n_slots)
         for r in 1:R

@@ -171,3 +171,16 @@ function pt_stats(e::Engine, n_slots)
     check(e, ccall((:csmc_pt_get_stats, libcsmc), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), e.ptr, a, x))
     return a, x
 end
+
+# cone widths per temperature slot for the progress report (src/helper.jl:32,49-50): the local replicas' widths
+# (they travel with the slot) placed at their current slots; slots held by other processes are gathered by the caller
+# through `allgather_sigma` (identity in a single process)
+function pt_sigma_by_slot(e::Engine, n_slots, base, R)
+    sig = fill(NaN, n_slots)
+    slots = pt_slots(e, n_slots)
+    s = get_sigma(e)
+    for r in 1:R
+        sig[slots[base+r]+1] = s[r]
+    end
+    return allgather_sigma(sig)
+end

@@ -568,6 +568,114 @@ double orc_metropolis_philox(const orc_lattice *L, double *spins, const int64_t 
     return accepted;
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* Test helpers that are not in the reference: all-sites field, and colour-order sweeps that carry a
+   per-site forward error bound along (the "conditioning-aware" tolerance of the full-size parity
+   tests).  Two implementations of the same update that differ only in rounding (summation order,
+   fused multiply-adds) differ after the update by at most TOL * S * kappa[i], where kappa follows
+   the first-order recursion below with a rounding budget of TOL * ORC_ROUND per field term. */
+void orc_local_field_all(const orc_lattice *L, const double *spins, double *out) {
+    for (int64_t p = 1; p <= L->N; ++p) orc_local_field(L, spins, p, out + 3 * (p - 1));
+}
+
+#define ORC_ROUND (1.0 / 512.0)   /* in units of TOL = 1e-12: 1.95e-15 = 17.6 u per term of the field sum */
+
+static double frob(const double *T, int n) {
+    double s = 0.0;
+    for (int k = 0; k < n; ++k) s += T[k] * T[k];
+    return sqrt(s);
+}
+
+/* spectral norm of a 3x3 matrix: sqrt of the largest eigenvalue of J^T J (trigonometric closed form for a
+   symmetric 3x3 matrix), times 1 + 1e-9 so that it stays an upper bound under its own rounding */
+static double spec3(const double *J) {
+    double M[3][3];
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) M[a][b] = J[0 + a] * J[0 + b] + J[3 + a] * J[3 + b] + J[6 + a] * J[6 + b];
+    const double p1 = M[0][1] * M[0][1] + M[0][2] * M[0][2] + M[1][2] * M[1][2];
+    const double q = (M[0][0] + M[1][1] + M[2][2]) / 3.0;
+    const double p2 = (M[0][0] - q) * (M[0][0] - q) + (M[1][1] - q) * (M[1][1] - q) + (M[2][2] - q) * (M[2][2] - q) + 2.0 * p1;
+    if (p2 <= 1e-300) return sqrt(fmax(q, 0.0)) * (1.0 + 1e-9);
+    const double p = sqrt(p2 / 6.0);
+    double B[3][3];
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) B[a][b] = (M[a][b] - (a == b ? q : 0.0)) / p;
+    double r = (B[0][0] * (B[1][1] * B[2][2] - B[1][2] * B[2][1]) - B[0][1] * (B[1][0] * B[2][2] - B[1][2] * B[2][0]) +
+                B[0][2] * (B[1][0] * B[2][1] - B[1][1] * B[2][0])) / 2.0;
+    r = r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);
+    const double lmax = q + 2.0 * p * cos(acos(r) / 3.0);
+    return sqrt(fmax(lmax, 0.0)) * (1.0 + 1e-9);
+}
+
+/* kF = S * sum_slots |T| S^(order-2) sum_nbrs kappa_nbr + ORC_ROUND * sum |terms of get_local_field|:
+   bound (in units of TOL) on the error of the local field of site i given the neighbours' bounds */
+static double field_error_bound(const orc_lattice *L, const double *spins, const double *kappa, int64_t i) {
+    const double *s = spins + 3 * i, *o = L->onsite + 9 * i, *h = L->field + 3 * i;
+    const double S = L->S;
+    double A = fabs(h[0]) + fabs(h[1]) + fabs(h[2]), prop = 0.0;
+    for (int k = 0; k < 9; ++k) A += 2 * fabs(o[k] * s[k % 3]);
+    prop += 2 * spec3(o) * kappa[i];
+    for (int n = 0; n < L->N2; ++n) {
+        const int64_t j = L->bil_site[i * L->N2 + n];
+        if (j == 0) continue;
+        const double *J = L->mats + 9 * L->bil_mat[i * L->N2 + n], *sj = spins + 3 * (j - 1);
+        for (int k = 0; k < 9; ++k) A += fabs(J[k] * sj[k % 3]);
+        prop += spec3(J) * kappa[j - 1];
+    }
+    for (int n = 0; n < L->N3; ++n) {
+        const int64_t *c = L->cub_site + (i * L->N3 + n) * 2;
+        if (c[0] == 0 && c[1] == 0) continue;
+        const double *C = L->tens3 + 27 * L->cub_ten[i * L->N3 + n];
+        const double *sj = spins + 3 * (c[0] - 1), *sk = spins + 3 * (c[1] - 1);
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b)
+                for (int cc = 0; cc < 3; ++cc) A += fabs(C[a * 9 + b * 3 + cc] * sj[b] * sk[cc]);
+        prop += frob(C, 27) * S * (kappa[c[0] - 1] + kappa[c[1] - 1]);
+    }
+    for (int n = 0; n < L->N4; ++n) {
+        const int64_t *r = L->quar_site + (i * L->N4 + n) * 3;
+        if (r[0] == 0 && r[1] == 0 && r[2] == 0) continue;
+        const double *R = L->tens4 + 81 * L->quar_ten[i * L->N4 + n];
+        const double *sj = spins + 3 * (r[0] - 1), *sk = spins + 3 * (r[1] - 1), *sl = spins + 3 * (r[2] - 1);
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b)
+                for (int c = 0; c < 3; ++c)
+                    for (int d = 0; d < 3; ++d) A += fabs(R[a * 27 + b * 9 + c * 3 + d] * sj[b] * sk[c] * sl[d]);
+        prop += frob(R, 81) * S * S * (kappa[r[0] - 1] + kappa[r[1] - 1] + kappa[r[2] - 1]);
+    }
+    return S * prop + ORC_ROUND * A;
+}
+
+/* kind 0: overrelaxation (s' = R(F) s: |ds'| <= |ds| + 4 S |dF| / |F|), 1: deterministic
+   (s' = -S F/|F|: |ds'| <= 2 S |dF| / |F|), 2: Metropolis with the shared Philox stream (an accepted
+   proposal does not depend on the neighbours; a rejected one keeps the old spin).  Performs the same
+   updates as orc_overrelax / orc_deterministic_order / orc_metropolis_philox and advances kappa[N]
+   (start it at zeros for bit-identical inputs).  Returns the accepted count (kind 2). */
+double orc_sweep_tracked(const orc_lattice *L, double *spins, const int64_t *order, int64_t n, int kind,
+                         double T, uint64_t seed, uint32_t replica, uint64_t sweep_ctr, double *kappa) {
+    double accepted = 0.0;
+    for (int64_t q = 0; q < n; ++q) {
+        const int64_t p = order ? order[q] : q + 1, i = p - 1;
+        if (kind == 2) {
+            const int64_t one = p;
+            double *s = spins + 3 * i;
+            const double o0 = s[0], o1 = s[1], o2 = s[2];
+            const double a = orc_metropolis_philox(L, spins, &one, 1, T, -1.0, seed, replica, sweep_ctr);
+            if (a != 0.0 || s[0] != o0 || s[1] != o1 || s[2] != o2) kappa[i] = ORC_ROUND;
+            accepted += a;
+            continue;
+        }
+        double H[3];
+        orc_local_field(L, spins, p, H);
+        const double nrm = sqrt(H[0] * H[0] + H[1] * H[1] + H[2] * H[2]);
+        if (nrm == 0.0) continue;
+        const double kF = field_error_bound(L, spins, kappa, i);
+        if (kind == 0) { kappa[i] = kappa[i] + 4.0 * kF / nrm + ORC_ROUND; or_update(L, spins, p); }
+        else { kappa[i] = 2.0 * kF / nrm + ORC_ROUND; det_update(L, spins, p); }
+    }
+    return accepted;
+}
+
 /* adaptive sigma rule: src/metropolis.jl:129-131 */
 double orc_adapt_sigma(double sigma, double accepted, double n) {
     double a = accepted / n, f = 0.5 / fmax(1 - a, 0.05);

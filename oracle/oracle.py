@@ -13,6 +13,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
+_FAST = None
+FAST_CFLAGS = "-O3 -march=native -ffp-contract=fast -fno-math-errno -fPIC -fopenmp -std=gnu11"
 
 f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
@@ -26,11 +28,43 @@ def build(force: bool = False) -> str:
     return so
 
 
-def lib():
-    global _LIB
+def build_fast() -> str:
+    """Performance build of the same source for the TIMED CPU legs of bench.py (cpu_baseline, --impl reference):
+    -O3 -march=native with FMA contraction allowed.  It is not the bit-exact checker (the parity tests use the
+    -ffp-contract=off build above).  -march=native is only valid on the machine that compiled it, so the library is
+    rebuilt on the box that runs it, into a directory keyed by the host's CPU flags."""
+    import hashlib
+    import platform
+    try:
+        flags = next(l for l in open("/proc/cpuinfo") if l.startswith("flags"))
+    except Exception:
+        flags = platform.processor()
+    key = hashlib.sha1((flags + FAST_CFLAGS).encode()).hexdigest()[:12]
+    out_dir = os.path.join(_HERE, "_fast")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, f"liboracle_fast_{key}.so")
+    src = os.path.join(_HERE, "csmc_oracle.c")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        cc = "/usr/bin/gcc" if os.access("/usr/bin/gcc", os.X_OK) else "gcc"
+        tmp = so + f".{os.getpid()}.tmp"
+        subprocess.check_call([cc] + FAST_CFLAGS.split() + ["-shared", "-o", tmp, src, "-lm"])
+        os.replace(tmp, so)
+    return so
+
+
+def lib(fast: bool = False):
+    global _LIB, _FAST
+    if fast:
+        if _FAST is None:
+            _FAST = _declare(C.CDLL(build_fast()))
+        return _FAST
     if _LIB is not None:
         return _LIB
-    L = C.CDLL(build())
+    _LIB = _declare(C.CDLL(build()))
+    return _LIB
+
+
+def _declare(L):
     vp = C.c_void_p
     L.orc_build.restype = vp
     L.orc_build.argtypes = [vp, C.c_int]
@@ -67,7 +101,9 @@ def lib():
     L.orc_cycles.argtypes = [vp, f64p, C.c_int, C.c_double, C.c_int64, C.c_int, C.c_int, C.c_uint64]
     L.orc_max_threads.restype = C.c_int
     L.orc_philox_raw.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, vp]
-    _LIB = L
+    L.orc_local_field_all.argtypes = [vp, f64p, f64p]
+    L.orc_sweep_tracked.restype = C.c_double
+    L.orc_sweep_tracked.argtypes = [vp, f64p, vp, C.c_int64, C.c_int, C.c_double, C.c_uint64, C.c_uint32, C.c_uint64, f64p]
     return L
 
 
@@ -80,9 +116,9 @@ class OracleLattice:
 
     Spin arrays are (N, 3) C-contiguous float64 (== Julia's 3 x N column-major)."""
 
-    def __init__(self, model_data, literal: bool = False):
+    def __init__(self, model_data, literal: bool = False, fast: bool = False):
         self._md = model_data
-        self._L = lib()
+        self._L = lib(fast)
         self._h = self._L.orc_build(C.byref(model_data.struct), 1 if literal else 0)
         self.N = int(self._L.orc_n_sites(self._h))
         self.N2, self.N3, self.N4 = model_data.n2, model_data.n3, model_data.n4
@@ -118,10 +154,7 @@ class OracleLattice:
 
     def local_field_all(self, spins):
         out = np.zeros((self.N, 3))
-        row = np.zeros(3)
-        for p in range(1, self.N + 1):
-            self._L.orc_local_field(self._h, spins, p, row)
-            out[p - 1] = row
+        self._L.orc_local_field_all(self._h, spins, out)
         return out
 
     def site_energy(self, spins, p):
@@ -148,6 +181,12 @@ class OracleLattice:
     def deterministic(self, spins, order=None, n_sweeps=1):
         o = None if order is None else np.ascontiguousarray(order, np.int64)
         self._L.orc_deterministic_order(self._h, spins, _ptr(o), 0 if o is None else len(o), n_sweeps)
+
+    def sweep_tracked(self, spins, order, kind, kappa, T=1.0, seed=0, replica=0, sweep_ctr=0):
+        """One colour-order sweep (kind 0 overrelaxation, 1 deterministic, 2 same-stream Metropolis) that also advances
+        the per-site forward error bound ``kappa`` (units of TOL * S, see csmc_oracle.c); returns the accepted count."""
+        o = np.ascontiguousarray(order, np.int64)
+        return self._L.orc_sweep_tracked(self._h, spins, _ptr(o), len(o), kind, T, seed, replica, sweep_ctr, kappa)
 
     def randomize(self, seed, replica=0):
         s = np.zeros((self.N, 3))

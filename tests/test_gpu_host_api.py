@@ -157,7 +157,7 @@ def test_parallel_tempering_accumulates_structure_factor(tmp_path):
     assert tr(S_cold)[0] > 0.9 * lat.size and tr(S_cold)[1] < 0.05 * lat.size     # ordered: Bragg peak at k = 0
     assert np.all(np.abs(tr(S_hot) - 1.0) < 0.25)                                  # paramagnet: flat, = S^2
     f = h5._open(out + "configuration_0.h5", "r")
-    assert np.allclose(h5._get(f, "spin_correlations/SSF"), S_cold) and np.allclose(h5._get(f, "spin_correlations/SSF_momentum"), ks)
+    assert np.allclose(h5._get_jl(f, "spin_correlations/SSF"), S_cold) and np.allclose(h5._get_jl(f, "spin_correlations/SSF_momentum"), ks)
     f.close()
 
 
@@ -182,8 +182,8 @@ def test_structure_factor_batch_runner_over_configuration_files(tmp_path):
     csm.runEqualTimeStructureFactor(ic_dir, lat, ks)
     for n in range(3):
         f = h5._open(ic_dir + f"IC_{n}.h5", "r")
-        assert np.array_equal(h5._get(f, "spin_correlations/SSF"), expected[n])
-        assert np.array_equal(h5._get(f, "spin_correlations/SSF_momentum"), ks)
+        assert np.array_equal(h5._get_jl(f, "spin_correlations/SSF"), expected[n])
+        assert np.array_equal(h5._get_jl(f, "spin_correlations/SSF_momentum"), ks)
         assert np.array_equal(np.asarray(h5._get(f, "spins")).T, lat.spins) == (n == 2)
         f.close()
     # already processed files are skipped unless override is set
@@ -192,13 +192,13 @@ def test_structure_factor_batch_runner_over_configuration_files(tmp_path):
     f.close()
     csm.runEqualTimeStructureFactor(ic_dir, lat, ks)
     f = h5._open(ic_dir + "IC_1.h5", "r")
-    assert not np.any(h5._get(f, "spin_correlations/SSF"))
+    assert not np.any(h5._get_jl(f, "spin_correlations/SSF"))
     f.close()
     csm.runEqualTimeStructureFactor(ic_dir, lat, ks, True)
     mean = csm.compute_equal_time_structure_factor(ic_dir, mc.outpath)
     assert np.allclose(mean, np.mean(expected, axis=0), rtol=1e-13, atol=1e-13)
     f = h5._open(mc.outpath, "r")
-    assert np.allclose(h5._get(f, "spin_correlations/SSF"), mean) and np.array_equal(h5._get(f, "spin_correlations/SSF_momentum"), ks)
+    assert np.allclose(h5._get_jl(f, "spin_correlations/SSF"), mean) and np.array_equal(h5._get_jl(f, "spin_correlations/SSF_momentum"), ks)
     f.close()
 
 

@@ -462,12 +462,16 @@ def test_exchange_decisions_match_oracle():
     eng.pt_init(T)
     E = eng.total_energy()
     slot_of_rep = np.arange(R)
-    for parity in (0, 1, 0, 1):
+    seen = set()
+    for call, parity in enumerate((0, 1, 0, 1, 0, 1)):
         acc = eng.pt_exchange(parity)
         rep_of_slot = np.argsort(slot_of_rep)
         for a in range(parity, R - 1, 2):
             ra, rb = rep_of_slot[a], rep_of_slot[a + 1]
-            r4 = orc.philox(seed, a, 0xFFFFFFFF, parity, 3)
+            # the Philox counter is the per-handle call index (fresh uniforms on every call), parity only pairs
+            r4 = orc.philox(seed, a, 0xFFFFFFFF, (1 << 48) + call, 3)
+            assert (int(r4[0]), int(r4[1])) not in seen
+            seen.add((int(r4[0]), int(r4[1])))
             u = float(((int(r4[0]) << 32 | int(r4[1])) >> 11) * 2.0 ** -53)
             expect = orc.exchange_accept(T[a], E[ra], T[a + 1], E[rb], u)
             assert bool(acc[a]) == expect
@@ -547,17 +551,34 @@ def test_cuda_path_against_committed_golden_vectors(name, flags):
 
 
 FULL_SIZE = [
+    ("C2-square-1024", lambda: models.square_heisenberg(), (1024, 1024), 1.0, 2),
     ("C3-honeycomb-256", lambda: models.kitaev_honeycomb(), (256, 256), 1.0, 2),
     ("C4-pyrochlore-32", lambda: models.pyrochlore_local(), (32, 32, 32), 0.5, 4),
     ("C5-triangular-512", lambda: models.triangular_multispin(), (512, 512), 1.0, 4),
 ]
 
 
+def assert_within_bound(out, ref, kappa, S):
+    """|out - ref| <= TOL * S * max(kappa_i, floor) on EVERY site.  kappa is the oracle's forward error bound of the
+    updates in units of TOL * S (oracle/csmc_oracle.c, orc_sweep_tracked): two implementations of the same update that
+    differ only in rounding (summation order, fused multiply-adds) stay within TOL * S * kappa_i, where a reflection
+    adds 4 |dF_i| / |F_i| with dF_i = S sum_j |J_ij| kappa_j + (TOL / 512) sum |J s_j| (first-order, worst case).
+    Well-conditioned sites have kappa < 1, i.e. the plain 1e-12 of north_star; sites whose neighbour contributions
+    nearly cancel (|F| << sum |J s|) get the larger, explicit bound instead of a blanket relaxation.  Returns the
+    fraction of sites on which the bound is at least as tight as the plain 1e-12."""
+    d = np.abs(out - ref).max(axis=1)
+    bad = np.nonzero(d > TOL * S * kappa)[0]
+    assert bad.size == 0, (bad[:5], d[bad[:5]], kappa[bad[:5]])
+    return float((kappa <= 1.0).mean())
+
+
 @pytest.mark.parametrize("name,builder,shape,S,colours", FULL_SIZE, ids=[c[0] for c in FULL_SIZE])
 def test_full_size_oracle_parity_and_properties(name, builder, shape, S, colours):
-    """BASELINE configs C3 / C4 / C5 at their full lattice sizes: the oracle's tables are closed-form O(N)
-    and one sweep takes it seconds, so fields, energies, overrelaxation, deterministic and same-stream
-    Metropolis sweeps are compared directly, followed by the size-independent properties."""
+    """BASELINE configs C2 / C3 / C4 / C5 at their full lattice sizes against the oracle (closed-form O(N) tables, a
+    sweep takes it about a second): fields on ALL sites, energy, magnetisation, then overrelaxation, same-stream
+    Metropolis and deterministic sweeps in colour order, each compared on EVERY site within the explicit per-site
+    bound; then the size-independent properties.  Reference semantics: src/monte_carlo.jl:126-139,201-213,
+    src/metropolis.jl:65-101."""
     seed = 2024
     md = ModelData(builder(), shape, S)
     lat = orc.OracleLattice(md)
@@ -566,36 +587,48 @@ def test_full_size_oracle_parity_and_properties(name, builder, shape, S, colours
     s = lat.randomize(seed=61)
     eng.set_spins(s)
     N = lat.N
-    # fields on a sample of sites (the oracle's per-site call is a Python loop), energy on all
     F = eng.local_field_all()
-    sample = np.random.default_rng(1).choice(N, 4000, replace=False) + 1
-    F_ref = np.stack([lat.local_field(s, int(p)) for p in sample])
-    assert np.abs(F[sample - 1] - F_ref).max() <= TOL * max(1.0, np.abs(F_ref).max())
+    F_ref = lat.local_field_all(s)
+    assert np.abs(F - F_ref).max() <= TOL * max(1.0, np.abs(F_ref).max())
     E_ref, E_abs = lat.total_energy(s, with_abs=True)
     assert abs(eng.total_energy()[0] - E_ref) <= TOL * E_abs
     assert np.abs(eng.magnetization_vector()[0] - lat.magnetization(s, vector=True)).max() <= TOL * N * S
-    def close(out, ref):
-        # the reflection 2(s.F)/(F.F) F - s is ill-conditioned where neighbour contributions nearly cancel
-        # (|F| << sum |J s_j|): among 1e5 sites a handful amplify the 1e-16 rounding differences past 1e-12,
-        # so the per-component bound is asserted on 99.9 % of the sites and a conditioning-aware one on all
-        d = np.abs(out - ref)
-        return np.quantile(d, 0.999) <= TOL * S and d.max() <= 1e-9 * S
-
-    # two overrelaxation sweeps and one deterministic sweep in colour order
     order = eng.colour_order()
+    # (1) sweep by sweep from identical inputs (the device is re-synchronised with the oracle's state before each
+    #     sweep, so the bound only spans the colour passes of one sweep): two overrelaxation sweeps
+    s2 = s.copy()
+    for sw in range(2):
+        kappa = np.zeros(N)
+        eng.set_spins(s)
+        eng.overrelax(1)
+        lat.sweep_tracked(s, order, 0, kappa)
+        frac_plain = assert_within_bound(eng.get_spins(), s, kappa, S)
+        # two-colour models: the plain 1e-12 covers all but the ill-conditioned ~1 % of the sites
+        assert frac_plain > (0.97 if colours == 2 else 0.3), frac_plain
+    # (2) the two sweeps in one go, against the bound accumulated over both (first-order worst case, hence looser)
+    kappa = np.zeros(N)
+    eng.set_spins(s2)
     eng.overrelax(2)
-    lat.overrelax(s, order, 2)
-    assert close(eng.get_spins(), s)
+    for sw in range(2):
+        lat.sweep_tracked(s2, order, 0, kappa)
+    assert np.array_equal(s2, s)
+    assert_within_bound(eng.get_spins(), s, kappa, S)
     E1 = eng.total_energy()[0]
     assert abs(E1 - E_ref) <= 1e-10 * E_abs                       # reflections are microcanonical (no on-site term)
     # Metropolis with the shared Philox stream: same accept decisions on every site
-    acc_ref = lat.metropolis_philox(s, order, 0.7, seed, 0, 0)
+    kappa = np.zeros(N)
+    eng.set_spins(s)
+    acc_ref = lat.sweep_tracked(s, order, 2, kappa, T=0.7, seed=seed, replica=0, sweep_ctr=0)
     assert eng.metropolis(0.7, 1)[0] == acc_ref and 0.05 * N < acc_ref <= N   # C4: couplings ~0.05, almost all accepted
-    assert close(eng.get_spins(), s)
-    eng.deterministic(1)
-    lat.deterministic(s, order, 1)
     out = eng.get_spins()
-    assert close(out, s)
+    assert np.abs(out - s).max() <= TOL * S                       # proposals do not depend on the neighbours
+    kappa = np.zeros(N)
+    eng.set_spins(s)
+    eng.deterministic(1)
+    lat.sweep_tracked(s, order, 1, kappa)
+    out = eng.get_spins()
+    frac_plain = assert_within_bound(out, s, kappa, S)
+    assert frac_plain > (0.99 if colours == 2 else 0.5), frac_plain
     assert np.allclose(np.linalg.norm(out, axis=1), S, rtol=0, atol=1e-13)
     # aligning against the local field lowers the energy colour pass by colour pass
     E_prev = eng.total_energy()[0]

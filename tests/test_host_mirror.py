@@ -216,3 +216,51 @@ def test_reciprocal_space_helpers():
     assert np.allclose(kpath[:, 12], 0)
     line = csm.get_k_path(uc, np.array([1.0, 0.0]), (6, 6))
     assert line.shape[0] == 2 and line.shape[1] > 0 and np.allclose(line[1], 0.0, atol=1e-9)
+
+
+def test_on_disk_orientation_is_what_hdf5_jl_produces(tmp_path):
+    """HDF5.jl writes a column-major Julia array with its dataspace dimensions reversed, so a C-order reader sees the
+    transpose of every array (src/hdf5.jl:39-40,60,67,74,229-236; util/load.py:88-93 relies on it for ``spins``).
+    Checked on a non-symmetric cell: honeycomb lattice vectors, two basis sites, a DM-type (antisymmetric) bilinear
+    matrix, a rank-3 tensor, the D x N site positions and a 9 x N_k structure factor."""
+    from classicalspinmc.jl_b200 import hdf5 as h5
+    uc = csm.Honeycomb()
+    J = np.array([[1.0, 2.0, 3.0], [-2.0, 4.0, 5.0], [-3.0, -5.0, 6.0]])      # J[r, c] with J != J^T
+    csm.addBilinear(uc, 1, 2, J, (0, -1))
+    C = np.arange(27, dtype=float).reshape(3, 3, 3) + 1.0                      # C[a, b, c]
+    csm.addCubic(uc, 1, 2, 1, C, (0, 0), (1, 0))
+    lat = csm.Lattice((3, 2), uc, 1.0)
+    mc = csm.MonteCarlo(1.0, lat, {"t_thermalization": 2}, outpath=str(tmp_path) + "/", outprefix="orient")
+    f = h5._open(str(tmp_path) + "/orient.h5.params", "r")
+    D, nb = 2, 2
+    lv_disk = np.asarray(h5._get(f, "unit_cell/lattice_vectors"))
+    # Julia: lattice_vectors[:, i] = a_i  ->  on disk row i = a_i
+    assert lv_disk.shape == (D, D) and all(np.allclose(lv_disk[i], uc.lattice_vectors[i]) for i in range(D))
+    basis_disk = np.asarray(h5._get(f, "unit_cell/basis"))
+    assert basis_disk.shape == (D, nb)                                         # Julia n_basis x D  ->  disk D x n_basis
+    assert all(np.allclose(basis_disk[:, b], uc.basis[b]) for b in range(nb))
+    key = "unit_cell/bilinear/(1,2),(0, -1)"
+    assert np.array_equal(np.asarray(h5._get(f, key)), J.T)                    # disk[c, r] = J[r, c]
+    ckey = [k for k in h5._keys(f, "unit_cell/cubic")][0]
+    assert np.array_equal(np.asarray(h5._get(f, "unit_cell/cubic/" + ckey)), C.transpose(2, 1, 0))
+    f.close()
+    g = h5._open(str(tmp_path) + "/orient_0.h5", "r")
+    assert np.asarray(h5._get(g, "spins")).shape == (lat.size, 3)
+    assert np.asarray(h5._get(g, "site_positions")).shape == (lat.size, D)
+    g.close()
+    # and the reader undoes it: every field of the unit cell and the lattice comes back
+    lat2 = h5.read_lattice(str(tmp_path) + "/orient.h5.params")
+    uc2 = lat2.unit_cell
+    assert all(np.allclose(a, b) for a, b in zip(uc2.lattice_vectors, uc.lattice_vectors))
+    assert len(uc2.basis) == nb and all(np.allclose(a, b) for a, b in zip(uc2.basis, uc.basis))
+    assert np.array_equal(uc2.bilinear[0][2], J) and np.array_equal(uc2.cubic[0][3], C)
+    assert np.allclose(lat2.site_positions, lat.site_positions)
+    S = np.arange(9 * 4, dtype=float).reshape(9, 4)
+    ks = np.arange(2 * 4, dtype=float).reshape(2, 4)
+    g = h5._open(str(tmp_path) + "/orient_0.h5", "r+")
+    h5.overwrite_keys(g, {"spin_correlations/SSF": S, "spin_correlations/SSF_momentum": ks})
+    g.close()
+    g = h5._open(str(tmp_path) + "/orient_0.h5", "r")
+    assert np.asarray(h5._get(g, "spin_correlations/SSF")).shape == (4, 9)     # Julia 9 x N_k
+    assert np.array_equal(h5._get_jl(g, "spin_correlations/SSF"), S)
+    g.close()

@@ -167,3 +167,35 @@ def test_oracle_reproduces_the_committed_vectors():
             ref = z[f"{name}/{k}"]
             assert ref.shape == np.asarray(v).shape, (name, k)
             assert np.abs(ref - v).max() <= 1e-13 * max(1.0, np.abs(ref).max()), (name, k)
+
+
+@pytest.mark.parametrize("name,builder,shape,S,frac", [
+    ("square-96", lambda: models.square_heisenberg(), (96, 96), 1.0, 0.97),
+    ("honeycomb-J3-48", lambda: models.kitaev_honeycomb(J3=0.25), (48, 48), 1.0, 0.9),
+    ("pyrochlore-8", lambda: models.pyrochlore_local(), (8, 8, 8), 0.5, 0.5),
+    ("triangular-multispin-32", lambda: models.triangular_multispin(), (32, 32), 1.0, 0.3),
+])
+def test_forward_error_bound_covers_a_differently_rounded_build(name, builder, shape, S, frac):
+    """The per-site bound the full-size GPU parity tests assert (orc_sweep_tracked: |difference| <= 1e-12 * S * kappa_i
+    on every site) must cover two implementations of the same updates that differ only in rounding.  Here: the
+    bit-exactness build of the oracle (-ffp-contract=off) against its performance build (-O3 -march=native, FMA
+    contraction) in the library's colour order, sweep by sweep from identical inputs and over two sweeps in one go; and
+    the bound must stay informative (kappa <= 1, i.e. the plain 1e-12, on most sites of a sweep)."""
+    from classicalspinmc.jl_b200 import _lib
+    md = ModelData(builder(), shape, S)
+    a, b = orc.OracleLattice(md), orc.OracleLattice(md, fast=True)
+    order = (np.argsort(_lib.plan(md)[0], kind="stable") + 1).astype(np.int64)
+    s = a.randomize(seed=77)
+    s0 = s.copy()
+    for kind in (0, 0, 1):
+        t = s.copy()
+        kappa = np.zeros(a.N)
+        a.sweep_tracked(s, order, kind, kappa)
+        (b.overrelax if kind == 0 else b.deterministic)(t, order, 1)
+        assert np.all(np.abs(s - t).max(axis=1) <= 1e-12 * S * kappa)
+        assert (kappa <= 1.0).mean() > frac
+    s, t, kappa = s0.copy(), s0.copy(), np.zeros(a.N)
+    for _ in range(2):
+        a.sweep_tracked(s, order, 0, kappa)
+    b.overrelax(t, order, 2)
+    assert np.all(np.abs(s - t).max(axis=1) <= 1e-12 * S * kappa)

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from classicalspinmc.jl_b200 import _lib  # noqa: E402
 from classicalspinmc.jl_b200._abi import FLAG_FUSED, FLAG_JIT, FLAG_NO_GRAPH, FLAG_NO_RESIDENT, ModelData  # noqa: E402
-from tests import models  # noqa: E402
+from classicalspinmc.jl_b200 import workloads as models  # noqa: E402
 
 for name, uc, shape in (("square", models.square_heisenberg(), (64, 64)), ("honeycomb", models.kitaev_honeycomb(), (32, 32))):
     md = ModelData(uc, shape, 1.0)

@@ -15,7 +15,7 @@ sys.path.insert(0, ROOT)
 from classicalspinmc.jl_b200 import _lib  # noqa: E402
 from classicalspinmc.jl_b200._abi import (FLAG_JIT, FLAG_NO_AUTOTUNE, FLAG_NO_GRAPH, FLAG_NO_RESIDENT, FLAG_SKEW,  # noqa: E402
                                           ModelData)
-from tests import models  # noqa: E402
+from classicalspinmc.jl_b200 import workloads as models  # noqa: E402
 
 
 def out(**kw):

@@ -16,9 +16,8 @@ from classicalspinmc.jl_b200 import _lib  # noqa: E402
 
 
 def _unit_cell(name):
-    from tests import models
-    uc = {"C2": models.square_heisenberg, "C3": models.kitaev_honeycomb, "C4": models.pyrochlore_local,
-          "C5": models.triangular_multispin}[name]()
+    from classicalspinmc.jl_b200 import workloads
+    uc = workloads.unit_cell(name)
     if not uc.basis:
         uc.basis.append(np.zeros(uc.D))
     return uc

@@ -15,7 +15,7 @@ sys.path.insert(0, ROOT)
 from classicalspinmc.jl_b200 import _lib  # noqa: E402
 from classicalspinmc.jl_b200._abi import FLAG_JIT, FLAG_NO_RESIDENT, ModelData  # noqa: E402
 import bench  # noqa: E402
-from tests import models  # noqa: E402
+from classicalspinmc.jl_b200 import workloads as models  # noqa: E402
 
 
 def pt_case(md, R, sweeps, flags):
