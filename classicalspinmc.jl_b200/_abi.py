@@ -67,6 +67,8 @@ FLAG_NO_RESIDENT = 32
 FLAG_NO_AUTOTUNE = 64
 FLAG_FUSED = 128
 FLAG_SKEW = 256
+FLAG_NO_PERSIST = 512
+FLAG_PERSIST = 1024
 
 
 def resolve_field_onsite(uc):

@@ -28,7 +28,7 @@ EXPORTS = [
     "csmc_metropolis", "csmc_metropolis_cone", "csmc_anneal_temperature", "csmc_anneal_temperature_cone", "csmc_set_temperatures",
     "csmc_set_sigma", "csmc_get_sigma",
     "csmc_cycles_async", "csmc_sync", "csmc_get_accepted", "csmc_pt_init", "csmc_comm_unique_id",
-    "csmc_comm_init", "csmc_comm_mode", "csmc_replica_blocks", "csmc_skew_schedule", "csmc_skew_info", "csmc_skew_geometry", "csmc_pt_run", "csmc_pt_exchange", "csmc_pt_get_slots", "csmc_pt_get_series",
+    "csmc_comm_init", "csmc_comm_mode", "csmc_replica_blocks", "csmc_persist_info", "csmc_persist_check", "csmc_skew_schedule", "csmc_skew_info", "csmc_skew_geometry", "csmc_pt_run", "csmc_pt_exchange", "csmc_pt_get_slots", "csmc_pt_get_series",
     "csmc_pt_get_stats", "csmc_pt_set_momenta", "csmc_pt_get_ssf",
 ]
 
@@ -75,6 +75,8 @@ def lib():
     L.csmc_autotune_report.argtypes = [vp, vp, P(i32)]
     L.csmc_sweep_groups.argtypes = [vp, P(i32), vp]
     L.csmc_replica_blocks.argtypes = [vp, P(i32), vp]
+    L.csmc_persist_info.argtypes = [vp, P(i32), vp, P(i32), P(i32), vp]
+    L.csmc_persist_check.argtypes = [P(CsmcModel), i32, i32, i32, i32, vp, i64, P(i64), vp, i64, vp]
     L.csmc_skew_schedule.argtypes = [i32, i32, i32, i32, vp, i64, P(i64)]
     L.csmc_skew_info.argtypes = [vp, P(i32), P(i32), P(i32), P(i32)]
     L.csmc_skew_geometry.argtypes = [P(CsmcModel), P(i32), P(i32), P(i32), P(i32)]
@@ -162,6 +164,24 @@ def jit_check(model: ModelData, compile: bool = True):
     if rc:
         raise CsmcError(f"csmc_jit_check failed ({rc}): {L.csmc_last_error(None).decode()}")
     return src.value.decode(), log.value.decode()
+
+
+def persist_check(model: ModelData, n_replicas: int = 1, n_sms: int = 0, smem_max: int = 0, compile: bool = True):
+    """Host-only: plan (and optionally NVRTC-compile for sm_100a) the tile-resident persistent kernel of ``model``.
+    Returns (info dict, source, log); info["usable"] is False when no tiling fits."""
+    L = lib()
+    n = C.c_int64(0)
+    cap = 1 << 23
+    src = C.create_string_buffer(cap)
+    log = C.create_string_buffer(1 << 16)
+    info = (C.c_int32 * 8)()
+    rc = L.csmc_persist_check(C.byref(model.struct), n_replicas, n_sms, smem_max, int(compile), src, cap, C.byref(n), log, 1 << 16, info)
+    if rc:
+        raise CsmcError(f"csmc_persist_check failed ({rc}): {L.csmc_last_error(None).decode()}")
+    keys = ("usable", "tiles", "g0", "g1", "w0", "w1", "replicas_per_launch", "smem")
+    d = dict(zip(keys, [int(v) for v in info]))
+    d["usable"] = bool(d["usable"])
+    return d, src.value.decode(), log.value.decode()
 
 
 def skew_schedule(n_rows: int, n_passes: int, reach: int, budget_rows: int):
@@ -279,6 +299,15 @@ class Engine:
         v = [C.c_int32() for _ in range(4)]
         self._ck(self._L.csmc_skew_info(self._h, *[C.byref(x) for x in v]))
         return bool(v[0].value), v[1].value, v[2].value, v[3].value
+
+    def persist_info(self):
+        """(CTA tiles per replica of the tile-resident kernel (0: not in use), (tiles along dim 0, dim 1), replicas per
+        launch, shared memory per CTA, (ms pass kernels, ms persistent) of the create-time probe)."""
+        t, r, sm = C.c_int32(), C.c_int32(), C.c_int32()
+        g = (C.c_int32 * 2)()
+        ms = (C.c_float * 2)()
+        self._ck(self._L.csmc_persist_info(self._h, C.byref(t), g, C.byref(r), C.byref(sm), ms))
+        return int(t.value), (int(g[0]), int(g[1])), int(r.value), int(sm.value), (float(ms[0]), float(ms[1]))
 
     def replica_blocks(self):
         """(replica blocks in use, (ms unblocked, ms blocked) of the create-time probe; zeros if not measured)."""

@@ -106,7 +106,17 @@ struct csmc_handle {
     JitPlan jit_plan;
     cudaKernel_t jit_resident = nullptr;
     cudaKernel_t jit_fused[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaKernel_t jit_persist = nullptr;
+    cudaLibrary_t persist_lib = nullptr;             // its own module: independent of the launch-mode (PDL) variants
+    JitPlan persist_plan;
     bool jit_tried = false, jit_pdl = false;
+    // tile-resident persistent kernel (jit.cpp emit_persist)
+    unsigned long long *d_persist_flags = nullptr;   // [R][tiles * PERSIST_FLAG_STRIDE] progress counters
+    int *persist_err = nullptr;                      // mapped host memory, sticky
+    bool persist_off = false;                        // autotune / CSMC_PERSIST=0 / a failed launch: pass kernels instead
+    int persist_min_sweeps = 2;
+    unsigned long long *d_persist_prof = nullptr;    // CSMC_PERSIST_PROF=1: per-tile phase cycle counters of the last launch
+    float tune_persist_ms[2] = {0.f, 0.f};           // autotune: ms per probe run with pass kernels / persistent kernel
     float tune_ms[2] = {0.f, 0.f};   // autotune: ms per probe run without / with programmatic dependent launch
     std::string jit_note;
 
@@ -251,6 +261,7 @@ void launch_fused(csmc_handle *h, int upd, const double *in, double *out, const 
 }
 
 struct SweepOp { int upd; unsigned long long ctr_off; bool device_ctr; };
+bool enqueue_persist_seq(csmc_handle *h, const SweepOp *seq, int n);
 
 void enqueue_pass_sweep(csmc_handle *h, const SweepOp &op, cudaStream_t stream = nullptr, int rep0 = 0, int nrep = -1) {
     switch (op.upd) {
@@ -395,6 +406,7 @@ void enqueue_sweep_seq(csmc_handle *h, const SweepOp *seq, int n, bool fused) {
         }
         return;
     }
+    if (enqueue_persist_seq(h, seq, n)) return;
     if (enqueue_skewed_seq(h, seq, n)) return;
     const int B = n >= 2 ? std::max(1, std::min(h->n_blocks, h->R)) : 1;
     for (int b = 0; b < B; ++b) {
@@ -575,6 +587,152 @@ void install_jit_module(csmc_handle *h, const JitModule &m) {
     h->jit = true;
 }
 
+// ---- tile-resident persistent kernel (jit.cpp emit_persist) ---------------------------------------------------
+// on request (CSMC_FLAG_PERSIST, CSMC_PERSIST=1), never with CSMC_FLAG_NO_PERSIST / CSMC_PERSIST=0, otherwise for every
+// eagerly specialised handle; whether sweep sequences then run on it is decided by the create-time autotune
+bool want_persist(const csmc_handle *h) {
+    const char *e = std::getenv("CSMC_PERSIST");
+    if ((h->flags & CSMC_FLAG_NO_PERSIST) || (e && e[0] == '0')) return false;
+    return true;
+}
+
+void persist_release(csmc_handle *h) {
+    if (h->d_persist_prof) {   // debugging aid: dump the phase counters of the last launch
+        std::vector<unsigned long long> pf(8 * 1024);
+        if (cudaMemcpy(pf.data(), h->d_persist_prof, sizeof(unsigned long long) * pf.size(), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            const int nt = std::min(1024, h->persist_plan.persist_tiles * std::max(1, h->persist_plan.persist_nrep));
+            double sum[4] = {0, 0, 0, 0}, mx[4] = {0, 0, 0, 0};
+            for (int t = 0; t < nt; ++t) for (int k = 0; k < 4; ++k) { sum[k] += (double)pf[t * 8 + k]; mx[k] = std::max(mx[k], (double)pf[t * 8 + k]); }
+            std::fprintf(stderr, "csmc_persist phases, cycles per CTA over the last launch (mean / max over %d CTAs): wait %.0f / %.0f, reload %.0f / %.0f, update %.0f / %.0f, publish %.0f / %.0f\n",
+                         nt, sum[0] / nt, mx[0], sum[1] / nt, mx[1], sum[2] / nt, mx[2], sum[3] / nt, mx[3]);
+        }
+        cudaFree(h->d_persist_prof); h->d_persist_prof = nullptr;
+    }
+    if (h->persist_lib) { cudaLibraryUnload(h->persist_lib); h->persist_lib = nullptr; }
+    h->jit_persist = nullptr;
+    h->persist_plan = JitPlan{};
+    cudaFree(h->d_persist_flags); h->d_persist_flags = nullptr;
+    if (h->persist_err) { cudaFreeHost(h->persist_err); h->persist_err = nullptr; }
+}
+
+// generate + compile + load csmc_persist for this handle's model and replica count; "" on success (or not applicable)
+std::string load_persist_module(csmc_handle *h) {
+    if (h->jit_persist || !want_persist(h)) return "";
+    int dev = 0, sms = 0, smem = 0, coop = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop) {
+        cudaGetLastError();
+        return "cooperative launch not available";
+    }
+    JitPlan plan;
+    plan.persist_only = true;
+    plan.persist_replicas = h->R;
+    plan.persist_sms = sms;
+    plan.persist_smem_max = smem;
+    std::string err, log;
+    std::vector<char> cubin;
+    try {
+        const std::string src = jit_generate_source(h->hm, false, &plan);
+        if (!plan.persist) return "";          // no tiling fits (lattice too large for the SMs' shared memory, open boundaries, ...)
+        const size_t key = std::hash<std::string>{}(src);
+        {
+            std::lock_guard<std::mutex> lk(g_cubin_mu);
+            auto it = g_cubin_cache.find(key);
+            if (it != g_cubin_cache.end()) cubin = it->second;
+        }
+        if (cubin.empty()) {
+            err = jit_compile(src, cubin, log);
+            if (err.empty()) {
+                std::lock_guard<std::mutex> lk(g_cubin_mu);
+                if (g_cubin_cache.size() > 64) g_cubin_cache.clear();
+                g_cubin_cache[key] = cubin;
+            }
+        }
+    } catch (const std::exception &ex) {
+        err = std::string("code generation failed: ") + ex.what();
+    }
+    if (!err.empty()) return err;
+    int per_sm = 0;
+    if (cudaLibraryLoadData(&h->persist_lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess ||
+        cudaLibraryGetKernel(&h->jit_persist, h->persist_lib, "csmc_persist") != cudaSuccess ||
+        cudaFuncSetAttribute((const void *)h->jit_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.persist_smem) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)h->jit_persist, plan.persist_tpb, plan.persist_smem) != cudaSuccess ||
+        per_sm < 1 ||
+        cudaMalloc((void **)&h->d_persist_flags, sizeof(unsigned long long) * (size_t)h->R * plan.persist_tiles * PERSIST_FLAG_STRIDE) != cudaSuccess ||
+        cudaMemsetAsync(h->d_persist_flags, 0, sizeof(unsigned long long) * (size_t)h->R * plan.persist_tiles * PERSIST_FLAG_STRIDE, h->stream) != cudaSuccess ||
+        cudaHostAlloc((void **)&h->persist_err, sizeof(int), cudaHostAllocMapped) != cudaSuccess) {
+        const std::string e = std::string("persistent kernel: ") + cudaGetErrorString(cudaGetLastError());
+        persist_release(h);
+        return e;
+    }
+    *h->persist_err = 0;
+    if (std::getenv("CSMC_PERSIST_PROF") && cudaMalloc((void **)&h->d_persist_prof, sizeof(unsigned long long) * 8 * 1024) != cudaSuccess) { cudaGetLastError(); h->d_persist_prof = nullptr; }
+    h->persist_plan = plan;
+    if (const char *e = std::getenv("CSMC_PERSIST_MIN_SWEEPS")) h->persist_min_sweeps = std::max(1, std::atoi(e));
+    return "";
+}
+
+// A sequence of n sweeps on the tile-resident kernel: one cooperative launch per batch of replicas that fills the SMs
+// and per <= PERSIST_MAX_OPS sweeps.  false: not applicable, nothing enqueued.
+bool enqueue_persist_seq(csmc_handle *h, const SweepOp *seq, int n) {
+    if (!h->jit_persist || h->persist_off || n < h->persist_min_sweeps) return false;
+    // the Metropolis counter source (device-resident for graph replays, by value otherwise) must be the same for every
+    // Metropolis sweep of the sequence; overrelaxation / deterministic sweeps do not read it
+    int dc = -1;
+    for (int i = 0; i < n; ++i)
+        if (seq[i].upd >= UPD_METRO) {
+            if (dc >= 0 && dc != (seq[i].device_ctr ? 1 : 0)) return false;
+            dc = seq[i].device_ctr ? 1 : 0;
+        }
+    const bool device_ctr = dc == 1;
+    const JitPlan &pl = h->persist_plan;
+    int *d_err = nullptr;
+    if (cudaHostGetDevicePointer((void **)&d_err, h->persist_err, 0) != cudaSuccess) { cudaGetLastError(); return false; }
+    for (int i = 0; i < n; i += PERSIST_MAX_OPS) {
+        const int len = std::min(PERSIST_MAX_OPS, n - i);
+        unsigned long long ctr_min = ~0ULL;
+        for (int k = 0; k < len; ++k) if (seq[i + k].upd >= UPD_METRO) ctr_min = std::min(ctr_min, seq[i + k].ctr_off);
+        if (ctr_min == ~0ULL) ctr_min = 0;
+        PersistArgs pa{};
+        pa.flags = h->d_persist_flags;
+        pa.err = d_err;
+        pa.timeout_cycles = 4000000000ULL;       // ~2 s at 2 GHz
+        pa.prof = h->d_persist_prof;
+        pa.n_ops = len;
+        for (int k = 0; k < len; ++k) {
+            const unsigned long long rel = seq[i + k].upd >= UPD_METRO ? seq[i + k].ctr_off - ctr_min : 0ULL;
+            if (rel > 65535ULL) return false;
+            pa.upd[k] = (unsigned char)seq[i + k].upd;
+            pa.ctr_rel[k] = (unsigned short)rel;
+        }
+        for (int r0 = 0; r0 < h->R; r0 += pl.persist_nrep) {
+            SweepArgs a = sweep_args(h, ctr_min, device_ctr);
+            a.rep0 = r0;
+            void *args[] = {(void *)&h->d_spins, (void *)&a, (void *)&pa};
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(pl.persist_tiles, std::min(pl.persist_nrep, h->R - r0), 1);
+            cfg.blockDim = dim3(pl.persist_tpb);
+            cfg.dynamicSmemBytes = pl.persist_smem;
+            cfg.stream = h->stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeCooperative;
+            attr[0].val.cooperative = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            if (cudaLaunchKernelExC(&cfg, (const void *)h->jit_persist, args) != cudaSuccess) {
+                // nothing of this launch ran; earlier launches of the sequence are complete sweeps on other replicas /
+                // earlier sweeps, so the caller cannot simply redo the sequence: report through the error word
+                cudaGetLastError();
+                *h->persist_err = 2;
+                return true;
+            }
+            h->launches++;
+        }
+    }
+    return true;
+}
+
 // Builds (once) the kernels specialised for this handle's model; "" on success.  On failure the
 // ahead-of-time kernels stay in use and csmc_kernel_mode reports the reason.
 std::string build_jit(csmc_handle *h) {
@@ -588,8 +746,13 @@ std::string build_jit(csmc_handle *h) {
     }
     JitModule m;
     const std::string err = load_jit_module(hm, (h->flags & CSMC_FLAG_PDL) != 0, m, (h->flags & CSMC_FLAG_FUSED) != 0, want_skew(h));
-    if (err.empty()) install_jit_module(h, m);
-    else {
+    if (err.empty()) {
+        install_jit_module(h, m);
+        if ((int64_t)hm.N * h->R >= 32768) {
+            const std::string perr = load_persist_module(h);
+            if (!perr.empty()) h->jit_note = "persistent kernel unavailable: " + perr;
+        }
+    } else {
         if (m.lib) cudaLibraryUnload(m.lib);
         cudaGetLastError();
         h->jit_note = err;
@@ -617,6 +780,13 @@ void enqueue_resident(csmc_handle *h, int n_cycles, int orc, int mc, int cone, i
 int finish(csmc_handle *h) {
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
+    if (h->persist_err && *h->persist_err) {
+        const int code = *h->persist_err;
+        *h->persist_err = 0;
+        h->persist_off = true;
+        return fail(h, CSMC_ERR_CUDA, code == 2 ? "tile-resident kernel: cooperative launch failed (spins are in an intermediate state)"
+                                                 : "tile-resident kernel: a neighbour tile did not arrive in time (CTAs not co-resident?)");
+    }
     if (h->peer.err && *h->peer.err) {
         const int who = *h->peer.err - 1;
         *h->peer.err = 0;
@@ -967,6 +1137,9 @@ static int autotune_pdl(csmc_handle *h) {
     };
     const bool groups_from_env = std::getenv("CSMC_SWEEP_GROUPS") != nullptr;
     if (!groups_from_env) h->n_groups = 1;
+    // the tile-resident kernel is timed last, against the best configuration of the pass kernels
+    const bool persist_candidate = h->jit_persist && !h->persist_off;
+    h->persist_off = true;
     for (int v = 0; v < 2; ++v) {
         install_jit_module(h, *mods[v]);
         int rc = probe(h->tune_ms[v]); if (rc) return rc;
@@ -1016,6 +1189,16 @@ static int autotune_pdl(csmc_handle *h) {
         h->n_groups = best_g;
         drop_graphs(h);
     }
+    if (persist_candidate) {
+        const char *e = std::getenv("CSMC_PERSIST");
+        const bool forced = (h->flags & CSMC_FLAG_PERSIST) != 0 || (e && e[0] == '1');
+        h->tune_persist_ms[0] = best_so_far;
+        h->persist_off = false;
+        drop_graphs(h);
+        int rc = probe(h->tune_persist_ms[1]);
+        if (rc) { h->persist_off = true; h->err.clear(); drop_graphs(h); }
+        else if (!forced && !(h->tune_persist_ms[1] < 0.97f * best_so_far)) { h->persist_off = true; drop_graphs(h); }
+    }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     // back to the freshly created state
     CK(cudaMemsetAsync(h->d_spins, 0, sizeof(double) * h->R * 3 * npad, h->stream));
@@ -1044,6 +1227,15 @@ int32_t csmc_reference_tables(const csmc_model *model, int64_t *bil, int64_t *cu
 int32_t csmc_destroy(csmc_handle *h) {
     if (!h) return CSMC_OK;
     cudaSetDevice(h->device);
+    if (h->stream) {   // a call that failed inside a stream capture must not leave the stream capturing
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(h->stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone) {
+            cudaGraph_t g = nullptr;
+            cudaStreamEndCapture(h->stream, &g);
+            if (g) cudaGraphDestroy(g);
+        }
+        cudaGetLastError();
+    }
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (auto &kv : h->cycle_graphs) cudaGraphExecDestroy(kv.second.exec);
     for (auto &kv : h->or_graphs) cudaGraphExecDestroy(kv.second);
@@ -1051,6 +1243,7 @@ int32_t csmc_destroy(csmc_handle *h) {
     for (auto ev : h->aux_done) cudaEventDestroy(ev);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->jit_lib) cudaLibraryUnload(h->jit_lib);
+    persist_release(h);
     peer_gather_release(h);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     free_pt(h);
@@ -1136,6 +1329,17 @@ int32_t csmc_skew_info(const csmc_handle *h, int32_t *usable, int32_t *tile_rows
     return CSMC_OK;
 }
 
+int32_t csmc_persist_info(const csmc_handle *h, int32_t *tiles, int32_t grid[2], int32_t *replicas_per_launch, int32_t *smem_bytes, float ms[2]) {
+    NEED(h);
+    const bool on = h->jit_persist && !h->persist_off;
+    if (tiles) *tiles = on ? h->persist_plan.persist_tiles : 0;
+    if (grid) { grid[0] = on ? h->persist_plan.persist_g[0] : 0; grid[1] = on ? h->persist_plan.persist_g[1] : 0; }
+    if (replicas_per_launch) *replicas_per_launch = on ? h->persist_plan.persist_nrep : 0;
+    if (smem_bytes) *smem_bytes = on ? h->persist_plan.persist_smem : 0;
+    if (ms) { ms[0] = h->tune_persist_ms[0]; ms[1] = h->tune_persist_ms[1]; }
+    return CSMC_OK;
+}
+
 int32_t csmc_replica_blocks(const csmc_handle *h, int32_t *blocks, float ms[2]) {
     NEED(h); NEEDARG(h, blocks);
     *blocks = std::max(1, std::min(h->n_blocks, h->R));
@@ -1162,6 +1366,36 @@ int32_t csmc_jit_check(const csmc_model *model, int32_t compile, char *source, i
     } catch (const std::exception &ex) {
         e = std::string("jit check failed: ") + ex.what();
     }
+    if (source_len) *source_len = (int64_t)src.size();
+    if (source && source_cap > 0) { std::strncpy(source, src.c_str(), (size_t)source_cap - 1); source[source_cap - 1] = 0; }
+    if (log && log_cap > 0) { std::strncpy(log, lg.c_str(), (size_t)log_cap - 1); log[log_cap - 1] = 0; }
+    if (!e.empty()) return fail(nullptr, CSMC_ERR_UNSUPPORTED, e);
+    return CSMC_OK;
+}
+
+int32_t csmc_persist_check(const csmc_model *model, int32_t n_replicas, int32_t n_sms, int32_t smem_max, int32_t compile,
+                           char *source, int64_t source_cap, int64_t *source_len, char *log, int64_t log_cap, int32_t info[8]) {
+    if (!model || !info) return fail(nullptr, CSMC_ERR_INVALID, "csmc_persist_check: NULL argument");
+    HostModel hm;
+    std::string e, src, lg;
+    JitPlan plan;
+    plan.persist_only = true;
+    plan.persist_replicas = n_replicas;
+    plan.persist_sms = n_sms > 0 ? n_sms : 148;
+    plan.persist_smem_max = smem_max > 0 ? smem_max : 227 * 1024;
+    try {
+        e = build_host_model(model, 0, hm);
+        if (e.empty() && (!hm.structured || hm.self_loop)) e = "model has no periodic colouring pattern (or interacts with itself): pass kernels only";
+        if (e.empty()) src = jit_generate_source(hm, false, &plan);
+        if (e.empty() && plan.persist && compile) {
+            std::vector<char> cubin;
+            e = jit_compile(src, cubin, lg);
+        }
+    } catch (const std::exception &ex) {
+        e = std::string("persist check failed: ") + ex.what();
+    }
+    info[0] = plan.persist ? 1 : 0; info[1] = plan.persist_tiles; info[2] = plan.persist_g[0]; info[3] = plan.persist_g[1];
+    info[4] = plan.persist_w[0]; info[5] = plan.persist_w[1]; info[6] = plan.persist_nrep; info[7] = plan.persist_smem;
     if (source_len) *source_len = (int64_t)src.size();
     if (source && source_cap > 0) { std::strncpy(source, src.c_str(), (size_t)source_cap - 1); source[source_cap - 1] = 0; }
     if (log && log_cap > 0) { std::strncpy(log, lg.c_str(), (size_t)log_cap - 1); log[log_cap - 1] = 0; }
@@ -1288,7 +1522,11 @@ int32_t csmc_deterministic(csmc_handle *h, int32_t n_sweeps) {
     NEED(h);
     CK(cudaSetDevice(h->device));
     if (n_sweeps > 0 && use_resident(h, n_sweeps)) enqueue_resident(h, 0, 0, 0, 0, n_sweeps, nullptr, 0);
-    else for (int s = 0; s < n_sweeps; ++s) enqueue_sweep<UPD_DET>(h);
+    else {
+        // as a sequence (blocks of <= 48 sweeps), so that the tile-resident kernel / strips / replica blocks apply
+        const std::vector<SweepOp> seq((size_t)std::min(std::max(n_sweeps, 0), 48), SweepOp{UPD_DET, 0ULL, false});
+        for (int left = n_sweeps; left > 0; left -= 48) enqueue_sweep_seq(h, seq.data(), std::min(left, 48), false);
+    }
     return finish(h);
 }
 
@@ -1356,7 +1594,18 @@ int32_t csmc_metropolis_cone(csmc_handle *h, const double *T, double *sigma, int
         CK(cudaStreamSynchronize(h->stream));
     }
     if (n_sweeps > 0 && use_resident(h, n_sweeps)) enqueue_resident(h, 1, 0, n_sweeps, 1, 0, nullptr, 0, adapt ? 1 : 0);
-    else for (int s = 0; s < n_sweeps; ++s) {
+    else if (!adapt && n_sweeps >= 2) {
+        // fixed cone width: the sweeps are one sequence (tile-resident kernel / strips / replica blocks apply)
+        std::vector<SweepOp> seq;
+        for (int done = 0; done < n_sweeps;) {
+            const int k = std::min(n_sweeps - done, 48);
+            seq.clear();
+            for (int s = 0; s < k; ++s) seq.push_back({UPD_CONE, h->metro_ctr + (unsigned long long)s, false});
+            enqueue_sweep_seq(h, seq.data(), k, false);
+            h->metro_ctr += (unsigned long long)k;
+            done += k;
+        }
+    } else for (int s = 0; s < n_sweeps; ++s) {
         enqueue_metropolis(h, true);
         if (adapt) { k_adapt_sigma<<<(h->R + 127) / 128, 128, 0, h->stream>>>(h->d_sigma, h->d_acc, h->d_acc_prev, (double)h->hm.N, h->R); h->launches++; }
     }

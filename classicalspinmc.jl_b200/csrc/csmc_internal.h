@@ -124,7 +124,33 @@ struct JitPlan {
     int skew_rows = 0;           // CTA-tile rows along dimension 0
     int skew_tiles_per_row = 0;  // CTA tiles per tile row (grid.x = rows * tiles_per_row)
     int skew_reach = 0;          // tile rows a site's neighbours can be away (>= 1)
+    // tile-resident persistent kernel (jit.cpp emit_persist, api.cu enqueue_persist): one CTA per SM keeps a tile of the
+    // lattice (plus halo) in shared memory for a whole sequence of sweeps and exchanges only halos through L2
+    int persist_replicas = 0;    // in: replicas of the handle (0: do not generate the kernel)
+    bool persist_only = false;   // in: emit nothing but the persistent kernel (it lives in a module of its own)
+    int persist_sms = 148;       // in: SMs of the device (CTAs that can be co-resident at one CTA per SM)
+    int persist_smem_max = 227 * 1024;   // in: opt-in shared memory per CTA
+    bool persist = false;        // out: usable
+    int persist_tiles = 0;       // CTA tiles per replica (grid.x)
+    int persist_nrep = 0;        // replicas per launch (grid.y <= this)
+    int persist_smem = 0, persist_tpb = 512;
+    int persist_g[2] = {1, 1}, persist_w[2] = {1, 1};   // tiles / tile extent (supercells) along dimensions 0 and 1
 };   // per colour: grid.x (CTA tiles), grid.y (class groups)
+
+// by-value argument of csmc_persist (mirrored in jit_prelude.h)
+constexpr int PERSIST_MAX_OPS = 48;
+struct PersistArgs {
+    unsigned long long *flags;          // [replica][tile * PERSIST_FLAG_STRIDE]: passes completed, monotonic across launches
+    int *err;                           // sticky error word (mapped host memory): a neighbour tile did not arrive in time
+    unsigned long long timeout_cycles;  // spin budget per wait
+    int n_ops;                          // sweeps of this launch
+    unsigned char upd[PERSIST_MAX_OPS];        // update kind of sweep k
+    unsigned short ctr_rel[PERSIST_MAX_OPS];   // Metropolis counter of sweep k relative to SweepArgs::ctr_off
+    int pad_;
+    unsigned long long *prof;           // optional (CSMC_PERSIST_PROF=1): [tile][8] cycles spent waiting / reloading / updating / publishing
+};
+constexpr int PERSIST_FLAG_STRIDE = 4;   // 32 bytes per flag: one L2 sector each
+static_assert(sizeof(PersistArgs) == 184, "PersistArgs layout (jit_prelude.h mirrors it)");
 // launches (pass, first tile row, tile rows) that run P colour passes strip by strip without changing any result;
 // empty when the lattice is too small for the budget to matter (csmc_skew_schedule exports it for the tests)
 struct SkewLaunch { int pass, row0, nrows; };

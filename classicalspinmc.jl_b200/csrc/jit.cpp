@@ -492,6 +492,271 @@ struct Gen {
         return true;
     }
 
+    // ---- tile-resident persistent kernel ---------------------------------------------------------------------
+    // A per-colour pass over an L2-resident lattice is mostly fixed latency (launch, ramp, load latency, tail:
+    // issue slots 25 % busy), so a sequence of sweeps is bound by the number of launches, not by bytes.  This kernel
+    // removes the launches: the lattice of each replica is cut into CTA tiles over supercell coordinates (dimensions
+    // 0 and 1; dimension 2 stays whole), one CTA per SM loads its tile plus the halo its sites read into shared
+    // memory ONCE and then runs every colour pass of the whole sequence (n sweeps x C colours) on it.  After a pass
+    // a CTA stores the sites other tiles read ("export region", within halo reach of the tile edge) to their home
+    // in the global spin array and raises its progress counter (st.release.gpu); before a pass it waits for the
+    // counters of its <= 8 neighbour tiles (ld.acquire.gpu, no grid-wide barrier) and reloads the halo cells of
+    // the colour updated in the previous pass.  Same per-site arithmetic and Philox counters as the pass kernels
+    // (site_finish_ptr), so results are bit-identical.  Launched cooperatively (co-residency guaranteed).
+    bool emit_persist(JitPlan &plan) {
+        plan.persist = false;
+        if (plan.persist_replicas < 1 || !hm.periodic || hm.n_colours < 2) return false;
+        const int nq = (int)hm.segs.size();
+        int M[MAXD] = {1, 1, 1};
+        for (int d = 0; d < MAXD; ++d) M[d] = hm.segs[0].M[d];
+        int nnb_max = 0, nnb_colour_max = 0;
+        for (int q = 0; q < nq; ++q) {
+            if (!seg_preload[q] || seg_split[q] != 1) return false;
+            for (int d = 0; d < MAXD; ++d) if (hm.segs[q].M[d] != M[d]) return false;
+            int nnb = 0;
+            for (const auto &lv : seg_live[q]) nnb += lv.t->kind - 1;
+            nnb_max = std::max(nnb_max, nnb);
+        }
+        for (int c = 0; c < hm.n_colours; ++c) {
+            int nnb = 0;
+            for (int q = hm.colour_seg_begin[c]; q < hm.colour_seg_begin[c + 1]; ++q)
+                for (const auto &lv : seg_live[q]) nnb += lv.t->kind - 1;
+            nnb_colour_max = std::max(nnb_colour_max, nnb);
+        }
+        // halo of class q: how far beyond a tile the sites of the tile read class q (per tiled dimension and side)
+        std::vector<std::array<int, 4>> halo(nq);
+        for (auto &e : halo) e.fill(0);
+        int reach2 = 0;
+        for (int q = 0; q < nq; ++q)
+            for (const auto &lv : seg_live[q])
+                for (int k = 0; k < lv.t->kind - 1; ++k) {
+                    int dl[MAXD];
+                    const int qn = nbr_class(hm.segs[q], *lv.t, k, dl);
+                    if (qn < 0) return false;
+                    if (hm.segs[qn].colour == hm.segs[q].colour) return false;   // not a proper colouring for this scheme
+                    for (int d = 0; d < 2; ++d) {
+                        if (dl[d] < 0) halo[qn][2 * d] = std::max(halo[qn][2 * d], -dl[d]);
+                        if (dl[d] > 0) halo[qn][2 * d + 1] = std::max(halo[qn][2 * d + 1], dl[d]);
+                    }
+                    reach2 = std::max(reach2, std::abs(dl[2]));
+                }
+        if (reach2 >= M[2] && M[2] > 1) return false;        // single wrap along the untiled dimension
+        // every class is stored with the same padded tile geometry (halo = the largest any class needs), so that a
+        // neighbour's shared-memory address is the site's own cell index plus a compile-time constant: lanes that walk
+        // consecutive cells read consecutive addresses for every operand (no bank conflicts)
+        int H[4] = {0, 0, 0, 0};
+        for (int q = 0; q < nq; ++q) for (int k = 0; k < 4; ++k) H[k] = std::max(H[k], halo[q][k]);
+        const int hmax[2] = {std::max(H[0], H[1]), std::max(H[2], H[3])};
+        // classes of a colour fused per thread (shared neighbour loads are read once) while the registers allow it
+        int fuse = nnb_colour_max <= 12 ? 2 : 1;
+        if (const char *e = std::getenv("CSMC_PERSIST_FUSE")) fuse = std::max(1, std::atoi(e));
+        int tpb = nnb_max * fuse <= 16 ? 512 : 256;
+        if (const char *e = std::getenv("CSMC_PERSIST_TPB")) { const int v = std::atoi(e); if (v == 128 || v == 256 || v == 384 || v == 512 || v == 768 || v == 1024) tpb = v; }
+        // tiling: minimise launches x loop iterations per pass (whole warps of cells, padded columns included)
+        const int R = plan.persist_replicas, NSM = std::max(1, plan.persist_sms);
+        double best_cost = 1e300;
+        int bg[2] = {0, 0}, bw[2] = {0, 0};
+        int force_g[2] = {0, 0};
+        if (const char *e = std::getenv("CSMC_PERSIST_GRID")) std::sscanf(e, "%dx%d", &force_g[0], &force_g[1]);
+        for (int g0 = 1; g0 <= std::min(M[0], NSM); ++g0)
+            for (int g1 = 1; g1 <= std::min(M[1], NSM / g0); ++g1) {
+                if (force_g[0] > 0 && (g0 != force_g[0] || g1 != force_g[1])) continue;
+                const int g[2] = {g0, g1};
+                int w[2];
+                bool ok = true;
+                for (int d = 0; d < 2; ++d) {
+                    w[d] = (M[d] + g[d] - 1) / g[d];
+                    if ((M[d] + w[d] - 1) / w[d] != g[d]) ok = false;                 // g tiles of extent w cover M exactly
+                    const int last = M[d] - (g[d] - 1) * w[d];
+                    if (last < std::max(1, hmax[d])) ok = false;                      // halo reaches one tile only
+                    if (g[d] == 1 && hmax[d] > 0 && M[d] < 2 * hmax[d]) ok = false;   // tile wraps onto itself
+                }
+                if (!ok) continue;
+                const long s0 = w[0] + H[0] + H[1], s1 = w[1] + H[2] + H[3];
+                const long cells = (s0 * s1 * M[2] + 1) / 2 * 2;
+                const size_t smem = (size_t)3 * cells * nq * sizeof(double);
+                if (smem + 1024 > (size_t)plan.persist_smem_max) continue;
+                const int T = g0 * g1, nrep = std::min(R, NSM / T);
+                if (nrep < 1) continue;
+                const int launches = (R + nrep - 1) / nrep;
+                const long iters = ((long)w[0] * s1 * M[2] + tpb - 1) / tpb;          // per class group and pass
+                const double cost = (double)launches * ((double)iters * tpb + 0.05 * (double)(s0 * s1 - (long)w[0] * w[1]) * M[2]);
+                if (cost < best_cost) { best_cost = cost; bg[0] = g0; bg[1] = g1; bw[0] = w[0]; bw[1] = w[1]; }
+            }
+        if (bg[0] == 0) return false;
+        const int G0 = bg[0], G1 = bg[1], W0 = bw[0], W1 = bw[1], T = G0 * G1;
+        const int S0 = W0 + H[0] + H[1], S1 = W1 + H[2] + H[3], S2 = M[2];
+        const int CELLS = (S0 * S1 * S2 + 1) / 2 * 2;
+        plan.persist = true;
+        plan.persist_tiles = T;
+        plan.persist_nrep = std::min(R, NSM / T);
+        plan.persist_smem = 3 * CELLS * nq * (int)sizeof(double);
+        plan.persist_tpb = tpb;
+        plan.persist_g[0] = G0; plan.persist_g[1] = G1; plan.persist_w[0] = W0; plan.persist_w[1] = W1;
+
+        o << "\n// ---- tile-resident persistent kernel: " << G0 << " x " << G1 << " tiles of " << W0 << " x " << W1 << " x " << S2
+          << " supercells per replica (padded " << S0 << " x " << S1 << "), " << plan.persist_smem << " B of shared memory, " << tpb << " threads, "
+          << fuse << " class(es) per thread\n";
+        o << "#define PT_CELLS " << CELLS << "\n#define PT_TOTAL " << (CELLS * nq) << "\n#define PT_TPB " << tpb << "\n";
+        o << "#define PT_S1 " << S1 << "\n#define PT_S2 " << S2 << "\n#define PT_H0 " << H[0] << "\n#define PT_H1 " << H[2] << "\n";
+        // neighbour loads of class q for the site in padded cell `cell` (row r = l0 + PT_H0, column col = l1 + PT_H1, l2)
+        for (int q = 0; q < nq; ++q) {
+            const HostSeg &hs = hm.segs[q];
+            o << "__device__ __forceinline__ void pt_load" << q << "(const double *__restrict__ shx, const double *__restrict__ shy, const double *__restrict__ shz,\n"
+                 "        int cell, int l2, double (&nb)[3 * Seg" << q << "::NNB + 1]) {\n";
+            for (const auto &lv : seg_live[q])
+                for (int k = 0; k < lv.t->kind - 1; ++k) {
+                    int dl[MAXD];
+                    const int qn = nbr_class(hs, *lv.t, k, dl);
+                    const int b3 = 3 * (lv.slot + k);
+                    const long off = (long)qn * CELLS + ((long)dl[0] * S1 + dl[1]) * S2 + dl[2];
+                    std::string wrap;
+                    if (dl[2] > 0) wrap = " + (l2 + " + std::to_string(dl[2]) + " >= " + std::to_string(S2) + " ? " + std::to_string(-S2) + " : 0)";
+                    if (dl[2] < 0) wrap = " + (l2 - " + std::to_string(-dl[2]) + " < 0 ? " + std::to_string(S2) + " : 0)";
+                    o << "    { const int j = cell + (" << off << ")" << wrap << "; nb[" << b3 << "] = shx[j]; nb[" << b3 + 1 << "] = shy[j]; nb[" << b3 + 2 << "] = shz[j]; }\n";
+                }
+            o << "}\n";
+        }
+        // one colour pass on the tile: every thread walks padded cells of the core rows; the classes of a colour are taken
+        // `fuse` at a time: all loads of the group first (shared neighbours are read once), then the updates
+        o << "template <int UPD> __device__ __forceinline__ int pt_pass(int colour, double *shx, double *shy, double *shz, double *gx, double *gy, double *gz,\n"
+             "        int o0, int o1, int w0, int w1, int rep, const SweepArgs &a, unsigned long long ctr_extra) {\n    int n_acc = 0;\n    switch (colour) {\n";
+        for (int c = 0; c < hm.n_colours; ++c) {
+            o << "    case " << c << ": {\n";
+            const int q0 = hm.colour_seg_begin[c], q1 = hm.colour_seg_begin[c + 1];
+            for (int qa = q0; qa < q1; qa += fuse) {
+                const int qb = std::min(q1, qa + fuse);
+                o << "        for (int e = threadIdx.x; e < w0 * " << (S1 * S2) << "; e += PT_TPB) {\n";
+                o << "            const int l2 = e % " << S2 << ", col = (e / " << S2 << ") % " << S1 << ", l0 = e / " << (S1 * S2) << ", l1 = col - " << H[2] << ";\n";
+                o << "            if (l1 < 0 || l1 >= w1) continue;\n";
+                o << "            const int cell = e + " << (H[0] * S1 * S2) << ";\n";
+                for (int q = qa; q < qb; ++q) {
+                    o << "            Site<Seg" << q << "> d" << q << ";\n            d" << q << ".valid = true; d" << q << ".ok = 0xffffffffu; d" << q << ".m0 = o0 + l0; d" << q
+                      << ".m1 = o1 + l1; d" << q << ".m2 = l2;\n";
+                    o << "            d" << q << ".pos = cell + " << ((long)q * CELLS) << ";\n            d" << q << ".s0 = shx[d" << q << ".pos]; d" << q << ".s1 = shy[d" << q
+                      << ".pos]; d" << q << ".s2 = shz[d" << q << ".pos];\n";
+                    o << "            pt_load" << q << "(shx, shy, shz, cell, l2, d" << q << ".nb);\n";
+                }
+                for (int q = qa; q < qb; ++q) {
+                    o << "            n_acc += site_finish_ptr<UPD, Seg" << q << ", false, -1>(d" << q << ", shx, shy, shz, rep, a, ctr_extra, 0.0, 0.0, 0.0) ? 1 : 0;\n";
+                    const bool exported = halo[q][0] || halo[q][1] || halo[q][2] || halo[q][3];
+                    if (exported) {
+                        // sites other tiles keep in their halo: upper halo of the tile below = my first rows, ...
+                        o << "            if (l0 < " << halo[q][1] << " || l0 >= w0 - " << halo[q][0] << " || l1 < " << halo[q][3] << " || l1 >= w1 - " << halo[q][2] << ") {\n";
+                        o << "                const int g = Seg" << q << "::pos(o0 + l0, o1 + l1, l2);\n";
+                        o << "                gx[g] = shx[d" << q << ".pos]; gy[g] = shy[d" << q << ".pos]; gz[g] = shz[d" << q << ".pos];\n            }\n";
+                    }
+                }
+                o << "        }\n";
+            }
+            o << "    } break;\n";
+        }
+        o << "    default: break;\n    }\n    return n_acc;\n}\n";
+        // halo cells of the classes of one colour, re-read from their home in global memory (L2: ld.global.cg).  One flat
+        // loop over every band of every class, so that the loads of a thread are independent and the pass pays one round trip.
+        o << "__device__ __forceinline__ void pt_reload(int colour, double *shx, double *shy, double *shz, const double *gx, const double *gy, const double *gz,\n"
+             "        int o0, int o1, int w0, int w1) {\n    switch (colour) {\n";
+        for (int c = 0; c < hm.n_colours; ++c) {
+            o << "    case " << c << ": {\n";
+            // bands: (class, first row r0 [runtime expr], rows [expr], first col c0 [expr], cols [expr])
+            struct Band { int q; std::string r0, nr, c0, nc; };
+            std::vector<Band> bands;
+            for (int q = hm.colour_seg_begin[c]; q < hm.colour_seg_begin[c + 1]; ++q) {
+                const int HL0 = halo[q][0], HH0 = halo[q][1], HL1 = halo[q][2], HH1 = halo[q][3];
+                const std::string cfull0 = std::to_string(H[2] - HL1), cfulln = "(w1 + " + std::to_string(HL1 + HH1) + ")";
+                if (HL0) bands.push_back({q, std::to_string(H[0] - HL0), std::to_string(HL0), cfull0, cfulln});
+                if (HH0) bands.push_back({q, "(" + std::to_string(H[0]) + " + w0)", std::to_string(HH0), cfull0, cfulln});
+                if (HL1) bands.push_back({q, std::to_string(H[0]), "w0", std::to_string(H[2] - HL1), std::to_string(HL1)});
+                if (HH1) bands.push_back({q, std::to_string(H[0]), "w0", "(" + std::to_string(H[2]) + " + w1)", std::to_string(HH1)});
+            }
+            if (!bands.empty()) {
+                o << "        int n_[" << bands.size() + 1 << "];\n        n_[0] = 0;\n";
+                for (size_t b = 0; b < bands.size(); ++b)
+                    o << "        n_[" << b + 1 << "] = n_[" << b << "] + " << bands[b].nr << " * " << bands[b].nc << " * " << S2 << ";\n";
+                o << "        for (int i = threadIdx.x; i < n_[" << bands.size() << "]; i += PT_TPB) {\n";
+                o << "            int g, j;\n";
+                for (size_t b = 0; b < bands.size(); ++b) {
+                    const Band &B = bands[b];
+                    o << "            " << (b ? "else " : "") << (b + 1 < bands.size() ? "if (i < n_[" + std::to_string(b + 1) + "]) " : "") << "{\n";
+                    o << "                const int k = i - n_[" << b << "], e2 = k % " << S2 << ", t = k / " << S2 << ", cc = t % " << B.nc << ", rr = t / " << B.nc << ";\n";
+                    o << "                const int r = " << B.r0 << " + rr, col = " << B.c0 << " + cc;\n";
+                    o << "                int m0 = o0 + r - " << H[0] << ", m1 = o1 + col - " << H[2] << ";\n";
+                    o << "                m0 = m0 < 0 ? m0 + " << M[0] << " : (m0 >= " << M[0] << " ? m0 - " << M[0] << " : m0); m1 = m1 < 0 ? m1 + " << M[1] << " : (m1 >= " << M[1] << " ? m1 - " << M[1] << " : m1);\n";
+                    o << "                g = Seg" << B.q << "::pos(m0, m1, e2); j = " << ((long)B.q * CELLS) << " + (r * " << S1 << " + col) * " << S2 << " + e2;\n";
+                    o << "            }\n";
+                }
+                o << "            shx[j] = __ldcg(gx + g); shy[j] = __ldcg(gy + g); shz[j] = __ldcg(gz + g);\n        }\n";
+            }
+            o << "    } break;\n";
+        }
+        o << "    default: break;\n    }\n}\n";
+        o << "extern \"C\" __global__ void __launch_bounds__(PT_TPB, 1) csmc_persist(double *spins, const SweepArgs a, const PersistArgs pa) {\n";
+        o << "    extern __shared__ double sh[];\n    double *shx = sh, *shy = sh + PT_TOTAL, *shz = sh + 2 * PT_TOTAL;\n";
+        o << "    __shared__ int sh_acc;\n";
+        o << "    const int tile = blockIdx.x, rep = blockIdx.y + a.rep0;\n";
+        o << "    const int t1 = tile % " << G1 << ", t0 = tile / " << G1 << ";\n";
+        o << "    const int o0 = t0 * " << W0 << ", o1 = t1 * " << W1 << ";\n";
+        o << "    const int w0 = min(" << W0 << ", " << M[0] << " - o0), w1 = min(" << W1 << ", " << M[1] << " - o1);\n";
+        o << "    double *gx = spins + (size_t)rep * (3ull * NPAD), *gy = gx + NPAD, *gz = gy + NPAD;\n";
+        o << "    unsigned long long *flags = pa.flags + (size_t)rep * " << (T) << " * PERSIST_FLAG_STRIDE;\n";
+        o << "    const unsigned long long base = flags[tile * PERSIST_FLAG_STRIDE];\n";
+        // the (up to 8) neighbour tiles, one polling thread each
+        o << "    const unsigned long long *nbr_flag = nullptr;\n";
+        o << "    if (threadIdx.x < 8) {\n        const int k = threadIdx.x < 4 ? threadIdx.x : threadIdx.x + 1;   // 3 x 3 neighbourhood without the centre\n";
+        o << "        const int n0 = (t0 + k / 3 - 1 + " << G0 << ") % " << G0 << ", n1 = (t1 + k % 3 - 1 + " << G1 << ") % " << G1 << ";\n";
+        o << "        nbr_flag = flags + (n0 * " << G1 << " + n1) * PERSIST_FLAG_STRIDE;\n    }\n";
+        o << "    if (threadIdx.x == 0) sh_acc = 0;\n";
+        // load the tile and the halo each class needs (asynchronous copies: all of a thread's loads in flight at once)
+        for (int q = 0; q < nq; ++q) {
+            const int r_lo = H[0] - halo[q][0], c_lo = H[2] - halo[q][2];
+            o << "    for (int e = threadIdx.x; e < (w0 + " << (halo[q][0] + halo[q][1]) << ") * " << (S1 * S2) << "; e += PT_TPB) {\n";
+            o << "        const int e2 = e % " << S2 << ", col = (e / " << S2 << ") % " << S1 << ", r = " << r_lo << " + e / " << (S1 * S2) << ";\n";
+            o << "        if (col < " << c_lo << " || col >= " << H[2] << " + w1 + " << halo[q][3] << ") continue;\n";
+            o << "        int m0 = o0 + r - " << H[0] << ", m1 = o1 + col - " << H[2] << ";\n";
+            o << "        m0 = m0 < 0 ? m0 + " << M[0] << " : (m0 >= " << M[0] << " ? m0 - " << M[0] << " : m0); m1 = m1 < 0 ? m1 + " << M[1] << " : (m1 >= " << M[1] << " ? m1 - " << M[1] << " : m1);\n";
+            o << "        const int g = Seg" << q << "::pos(m0, m1, e2), j = " << ((long)q * CELLS) << " + (r * " << S1 << " + col) * " << S2 << " + e2;\n";
+            o << "        cp_async8(shx + j, gx + g); cp_async8(shy + j, gy + g); cp_async8(shz + j, gz + g);\n    }\n";
+        }
+        o << "    cp_async_wait_all();\n    __syncthreads();\n";
+        o << "    if (threadIdx.x == 0) st_release_gpu(flags + tile * PERSIST_FLAG_STRIDE, base + 1ULL);\n";
+        o << "    int n_acc = 0;\n    unsigned long long step = 0;\n";
+        o << "    long long pf_t = clock64(), pf[4] = {0, 0, 0, 0};\n";
+        o << "#define PT_PROF(k) do { if (pa.prof) { const long long now_ = clock64(); pf[k] += now_ - pf_t; pf_t = now_; } } while (0)\n";
+        o << "    for (int op = 0; op < pa.n_ops; ++op) {\n        const int upd = pa.upd[op];\n        const unsigned long long ce = pa.ctr_rel[op];\n";
+        o << "        for (int c = 0; c < " << hm.n_colours << "; ++c, ++step) {\n";
+        o << "            if (nbr_flag) persist_wait(nbr_flag, base + 1ULL + step, pa.err, pa.timeout_cycles);\n";
+        o << "            __syncthreads();   // the polling threads' ld.acquire + this barrier order the halo loads below after the neighbours' stores\n";
+        o << "            PT_PROF(0);\n";
+        o << "            if (step) pt_reload(c == 0 ? " << (hm.n_colours - 1) << " : c - 1, shx, shy, shz, gx, gy, gz, o0, o1, w0, w1);\n";
+        o << "            __syncthreads();\n";
+        o << "            PT_PROF(1);\n";
+        o << "            switch (upd) {\n";
+        o << "            case UPD_OR: pt_pass<UPD_OR>(c, shx, shy, shz, gx, gy, gz, o0, o1, w0, w1, rep, a, ce); break;\n";
+        o << "            case UPD_DET: pt_pass<UPD_DET>(c, shx, shy, shz, gx, gy, gz, o0, o1, w0, w1, rep, a, ce); break;\n";
+        o << "            case UPD_METRO: n_acc += pt_pass<UPD_METRO>(c, shx, shy, shz, gx, gy, gz, o0, o1, w0, w1, rep, a, ce); break;\n";
+        o << "            default: n_acc += pt_pass<UPD_CONE>(c, shx, shy, shz, gx, gy, gz, o0, o1, w0, w1, rep, a, ce); break;\n";
+        o << "            }\n";
+        o << "            __syncthreads();\n";
+        o << "            PT_PROF(2);\n";
+        o << "            if (threadIdx.x == 0) st_release_gpu(flags + tile * PERSIST_FLAG_STRIDE, base + 2ULL + step);   // release: cumulative over the barrier\n";
+        o << "            PT_PROF(3);\n";
+        o << "        }\n    }\n";
+        // write the tile back (core cells of every class)
+        for (int q = 0; q < nq; ++q) {
+            o << "    for (int e = threadIdx.x; e < w0 * " << (S1 * S2) << "; e += PT_TPB) {\n";
+            o << "        const int l2 = e % " << S2 << ", col = (e / " << S2 << ") % " << S1 << ", l0 = e / " << (S1 * S2) << ", l1 = col - " << H[2] << ";\n";
+            o << "        if (l1 < 0 || l1 >= w1) continue;\n";
+            o << "        const int g = Seg" << q << "::pos(o0 + l0, o1 + l1, l2), j = " << ((long)q * CELLS + (long)H[0] * S1 * S2) << " + e;\n";
+            o << "        gx[g] = shx[j]; gy[g] = shy[j]; gz[g] = shz[j];\n    }\n";
+        }
+        o << "    if (pa.prof && threadIdx.x == 0) for (int k = 0; k < 4; ++k) pa.prof[((size_t)blockIdx.y * gridDim.x + tile) * 8 + k] = (unsigned long long)pf[k];\n";
+        o << "    { const int w = __reduce_add_sync(0xffffffffu, n_acc); if ((threadIdx.x & 31) == 0 && w) atomicAdd(&sh_acc, w); }\n";
+        o << "    __syncthreads();\n";
+        o << "    if (threadIdx.x == 0 && sh_acc) atomicAdd(a.accepted + (size_t)rep * ACC_STRIPE + (tile & (ACC_STRIPE - 1)), (unsigned long long)sh_acc);\n";
+        o << "}\n";
+        return true;
+    }
+
     std::string run(JitPlan &plan) {
         {
             std::ostringstream head;
@@ -506,6 +771,10 @@ struct Gen {
             for (size_t k = 0; k < ktab.size(); ++k) o << (k ? ", " : "") << lit(ktab[k]);
             if (ktab.empty()) o << "0.0";
             o << "};\n\n" << segs;
+        }
+        if (plan.persist_only) {   // the tile-resident kernel lives in a module of its own
+            emit_persist(plan);
+            return o.str();
         }
         plan.tiles.assign(hm.n_colours, 1);
         plan.groups.assign(hm.n_colours, 1);

@@ -40,6 +40,48 @@ struct SweepArgs {
 #define CSMC_TILE_OFF(a) 0
 #endif
 
+// by-value argument of csmc_persist (csmc_internal.h mirrors it)
+#define PERSIST_MAX_OPS 48
+#define PERSIST_FLAG_STRIDE 4
+struct PersistArgs {
+    unsigned long long *flags;
+    int *err;
+    unsigned long long timeout_cycles;
+    int n_ops;
+    unsigned char upd[PERSIST_MAX_OPS];
+    unsigned short ctr_rel[PERSIST_MAX_OPS];
+    int pad_;
+    unsigned long long *prof;
+};
+__device__ __forceinline__ void st_release_gpu(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// spins until *p >= want; gives up (and raises the sticky error word) after `budget` cycles or when another CTA already
+// gave up, so a tile that never arrives fails the call instead of hanging the GPU
+__device__ __forceinline__ void persist_wait(const unsigned long long *p, unsigned long long want, int *err, unsigned long long budget) {
+    if (ld_acquire_gpu(p) >= want) return;
+    const long long t0 = clock64();
+    unsigned spins = 0;
+    while (ld_acquire_gpu(p) < want) {
+        if ((++spins & 255u) == 0u) {
+            if (*(volatile int *)err != 0) return;
+            if ((unsigned long long)(clock64() - t0) > budget) { *(volatile int *)err = 1; __threadfence_system(); return; }
+        }
+    }
+}
+
+// asynchronous 8-byte global -> shared copy (LDGSTS): no register staging, every copy of a thread in flight at once
+__device__ __forceinline__ void cp_async8(double *smem, const double *g) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 struct u4 { uint32_t x, y, z, w; };
 __device__ __forceinline__ u4 philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
 #pragma unroll

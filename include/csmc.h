@@ -110,6 +110,16 @@ typedef struct csmc_opts {
                                      one strip while it is L2-resident, the strip moving one dependency reach per     \
                                      pass -- instead of streaming the lattice through L2 once per pass.  Results are  \
                                      bit-identical (csmc_skew_schedule, csmc_skew_info)                               */
+#define CSMC_FLAG_NO_PERSIST 512  /* never use the tile-resident persistent kernel (also CSMC_PERSIST=0)              */
+#define CSMC_FLAG_PERSIST 1024    /* use it whenever it applies, without the create-time timing against the per-colour \
+                                     pass kernels (also CSMC_PERSIST=1).  The tile-resident kernel (csmc_persist_info)    \
+                                     runs a whole sequence of sweeps in ONE cooperative launch: every CTA (one per SM)    \
+                                     keeps a tile of the lattice plus its halo in shared memory for all colour passes of  \
+                                     the sequence, stores the sites other tiles read to the global spin array after each  \
+                                     pass and synchronises with its <= 8 neighbour tiles only (release / acquire progress \
+                                     counters in L2, no grid-wide barrier).  Applies to periodic pattern-coloured models  \
+                                     whose replicas fit the SMs' shared memory (<= ~28 MB of spins per launch; more        \
+                                     replicas run batch by batch).  Results are bit-identical to the pass kernels.         */
 /* Default: models whose colouring is a periodic pattern get kernels specialised for that model
  * (unrolled terms, literal coefficients, constant geometry; compiled for sm_100a with NVRTC at
  * csmc_create) when n_sites * n_replicas >= 32768; smaller problems are launch-latency bound and
@@ -179,6 +189,17 @@ int32_t csmc_replica_blocks(const csmc_handle *h, int32_t *blocks, float ms[2]);
  * probe did not find the pass-by-pass order faster), and the geometry they use. */
 int32_t csmc_skew_schedule(int32_t n_rows, int32_t n_passes, int32_t reach, int32_t budget_rows,
                            int32_t *launches, int64_t cap, int64_t *n);
+/* Tile-resident persistent kernel: *tiles = CTA tiles per replica in use (0: not in use for this handle), grid[2] =
+ * tiles along lattice dimensions 0 and 1, *replicas_per_launch, *smem_bytes per CTA; ms[2] = create-time probe
+ * (pass kernels / persistent kernel; zeros if not measured).  Any pointer may be NULL. */
+int32_t csmc_persist_info(const csmc_handle *h, int32_t *tiles, int32_t grid[2], int32_t *replicas_per_launch,
+                          int32_t *smem_bytes, float ms[2]);
+/* host-only (no GPU needed): plans -- and with compile != 0 compiles for sm_100a -- the tile-resident kernel of `model`
+ * for n_replicas replicas on a device with n_sms SMs and smem_max bytes of opt-in shared memory per CTA (0: B200's 148 /
+ * 227 KiB).  info = {usable, tiles per replica, tiles along dim 0, dim 1, tile extent (supercells) along dim 0, dim 1,
+ * replicas per launch, shared memory per CTA}.  source / log as csmc_jit_check. */
+int32_t csmc_persist_check(const csmc_model *model, int32_t n_replicas, int32_t n_sms, int32_t smem_max, int32_t compile,
+                           char *source, int64_t source_cap, int64_t *source_len, char *log, int64_t log_cap, int32_t info[8]);
 int32_t csmc_skew_info(const csmc_handle *h, int32_t *usable, int32_t *tile_rows, int32_t *reach,
                        int32_t *budget_rows);
 /* host-only: the strip geometry the specialised kernels of `model` would use (CTA-tile rows along lattice

@@ -57,9 +57,10 @@ def main():
         eng.set_temperatures(np.geomspace(0.5, 2.0, R))
         N, C = eng.N, eng.n_colours
         balg = B_ALG.get(C, 24.0 * (C + 1))
-        out = {"workload": spec, "N": N, "R": R, "colours": C, "mode": eng.kernel_mode, "groups": eng.sweep_groups()}
-        for label, orc, mc in (("or", 1, 0), ("or2", 2, 0), ("metro", 0, 1), ("metro2", 0, 2), ("cycle10+1", 10, 1)):
-            n = args.n if label != "cycle10+1" else max(args.n // 10, 5)
+        out = {"workload": spec, "N": N, "R": R, "colours": C, "mode": eng.kernel_mode, "groups": eng.sweep_groups(),
+               "persist": eng.persist_info(), "blocks": eng.replica_blocks()[0]}
+        for label, orc, mc in (("or", 1, 0), ("or2", 2, 0), ("or10", 10, 0), ("or40", 40, 0), ("metro", 0, 1), ("metro2", 0, 2), ("metro10", 0, 10), ("cycle10+1", 10, 1)):
+            n = max(args.n // max(orc + mc, 1), 5)
             dt = time_cycles(eng, stream, n, orc, mc)
             upd = n * (orc + mc) * N * R
             out[label] = {"Gupd_s": upd / dt / 1e9, "us_per_pass": dt / (n * (orc + mc) * C) * 1e6,
