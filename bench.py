@@ -264,15 +264,35 @@ def run_pt(workload, L, world, rank, local_rank, stream, steps, warmup, sweeps_p
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
+    launches_timed = int(eng.launches - l0)
+    _, ex = eng.pt_stats()
+    # the exchange step alone (energy reduction of every local replica, gather of the records across the GPUs, exchange
+    # decisions: what runs once per swap_rate sweeps), timed through csmc_pt_exchange with a host sync per call: an upper
+    # bound of the collective's share of an exchange period
+    for k in range(3):
+        eng.pt_exchange(k & 1)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    n_ex = 20
+    t0 = time.perf_counter()
+    for k in range(n_ex):
+        eng.pt_exchange(k & 1)
+    torch.cuda.synchronize()
+    ex_us = torch.tensor([(time.perf_counter() - t0) / n_ex * 1e6], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ex_us, op=dist.ReduceOp.MAX)
+    ex_us = float(ex_us.item())
+    period_us = ms / steps * 1e3 / (sweeps_per_step / 50.0)
     n_metro = steps * sweeps_per_step // 10
     updates = (steps * sweeps_per_step + n_metro) * float(eng.N) * R_total
-    _, ex = eng.pt_stats()
     n_col = eng.n_colours
     peak, _ = measured_peak_gbs()
     value = updates / (ms * 1e-3)
     out = {"workload": workload, "value": value, "unit": "updates/s", "n_gpus": world, "replicas": R_total, "replicas_per_gpu": R,
            "steps": steps, "sweeps_per_step": sweeps_per_step, "ms_per_step": ms / steps,
-           "exchanges_accepted": float(ex.sum()), "gpu_launches": int(eng.launches - l0),
+           "exchanges_accepted": float(ex.sum()), "gpu_launches": launches_timed,
+           "exchange_step_us": ex_us, "exchange_period_us": period_us, "exchange_share_upper_bound": ex_us / period_us,
            "engine": {"kernel_mode": eng.kernel_mode, "sweep_groups": eng.sweep_groups()[0], "replica_blocks": eng.replica_blocks()[0],
                       "persistent_tiles": eng.persist_info()[0] if hasattr(eng, "persist_info") else 0,
                       "exchange": {0: "single GPU", 1: "energies via ncclAllGather", 2: "energies via peer-memory stores (push + wait kernels)",
@@ -445,6 +465,15 @@ def run_ours(args):
                     "unit": "GB/s", "frac": achieved / l2_peak, "frac_of_hbm_peak": achieved / hbm_peak}
     else:
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "peak_kind": hbm_kind, "unit": "GB/s", "frac": achieved / hbm_peak}
+    # fp64 pipe roofline of the same launch: flops counted by the code generator (fma = 2) against the nominal vector
+    # fp64 rate of the part (64 DFMA per SM and clock at the maximum SM clock; no measured fp64 peak exists in
+    # MEASURED_PEAKS.json)
+    flops_upd, _ = eng.kernel_costs()
+    sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    fp64_peak = sm_count * 64 * 2 * (clk.max_mhz or 1965) * 1e6 / 1e12
+    fp64_tflops = flops_upd * (N * or_block / launches_per_block) / (pass_ms * 1e-3) / 1e12
+    roofline.update(fp64={"flops_per_update": flops_upd, "achieved_tflops": fp64_tflops, "peak_tflops_nominal": fp64_peak,
+                          "frac": fp64_tflops / fp64_peak, "peak_kind": f"nominal: {sm_count} SMs x 64 DFMA/clk x max SM clock"})
     pm = eng.persist_info() if hasattr(eng, "persist_info") else (0, 0, 0)
     roofline.update(kernel=("csmc_persist (tile-resident multi-pass kernel: one launch per OR block)" if pm[0] else
                             "csmc_sweep_c<colour>_u0 (overrelaxation colour pass)"),

@@ -28,7 +28,7 @@ EXPORTS = [
     "csmc_metropolis", "csmc_metropolis_cone", "csmc_anneal_temperature", "csmc_anneal_temperature_cone", "csmc_set_temperatures",
     "csmc_set_sigma", "csmc_get_sigma",
     "csmc_cycles_async", "csmc_sync", "csmc_get_accepted", "csmc_pt_init", "csmc_comm_unique_id",
-    "csmc_comm_init", "csmc_comm_mode", "csmc_replica_blocks", "csmc_persist_info", "csmc_persist_check", "csmc_skew_schedule", "csmc_skew_info", "csmc_skew_geometry", "csmc_pt_run", "csmc_pt_exchange", "csmc_pt_get_slots", "csmc_pt_get_series",
+    "csmc_comm_init", "csmc_comm_mode", "csmc_replica_blocks", "csmc_persist_info", "csmc_persist_check", "csmc_kernel_costs", "csmc_skew_schedule", "csmc_skew_info", "csmc_skew_geometry", "csmc_pt_run", "csmc_pt_exchange", "csmc_pt_get_slots", "csmc_pt_get_series",
     "csmc_pt_get_stats", "csmc_pt_set_momenta", "csmc_pt_get_ssf",
 ]
 
@@ -76,6 +76,7 @@ def lib():
     L.csmc_sweep_groups.argtypes = [vp, P(i32), vp]
     L.csmc_replica_blocks.argtypes = [vp, P(i32), vp]
     L.csmc_persist_info.argtypes = [vp, P(i32), vp, P(i32), P(i32), vp]
+    L.csmc_kernel_costs.argtypes = [vp, P(dbl), P(dbl)]
     L.csmc_persist_check.argtypes = [P(CsmcModel), i32, i32, i32, i32, vp, i64, P(i64), vp, i64, vp]
     L.csmc_skew_schedule.argtypes = [i32, i32, i32, i32, vp, i64, P(i64)]
     L.csmc_skew_info.argtypes = [vp, P(i32), P(i32), P(i32), P(i32)]
@@ -308,6 +309,12 @@ class Engine:
         ms = (C.c_float * 2)()
         self._ck(self._L.csmc_persist_info(self._h, C.byref(t), g, C.byref(r), C.byref(sm), ms))
         return int(t.value), (int(g[0]), int(g[1])), int(r.value), int(sm.value), (float(ms[0]), float(ms[1]))
+
+    def kernel_costs(self):
+        """(fp64 flops per overrelaxation site update of the specialised kernels, algorithmic bytes per update)."""
+        f, b = C.c_double(), C.c_double()
+        self._ck(self._L.csmc_kernel_costs(self._h, C.byref(f), C.byref(b)))
+        return float(f.value), float(b.value)
 
     def replica_blocks(self):
         """(replica blocks in use, (ms unblocked, ms blocked) of the create-time probe; zeros if not measured)."""

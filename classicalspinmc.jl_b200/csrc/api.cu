@@ -593,6 +593,10 @@ void install_jit_module(csmc_handle *h, const JitModule &m) {
 bool want_persist(const csmc_handle *h) {
     const char *e = std::getenv("CSMC_PERSIST");
     if ((h->flags & CSMC_FLAG_NO_PERSIST) || (e && e[0] == '0')) return false;
+    if ((h->flags & CSMC_FLAG_PERSIST) || (e && e[0] == '1')) return true;
+    // an explicit request for the time-skewed strips or the fused full-sweep kernels is not overridden
+    const char *sk = std::getenv("CSMC_SKEW");
+    if ((h->flags & (CSMC_FLAG_SKEW | CSMC_FLAG_FUSED)) || (sk && sk[0] == '1')) return false;
     return true;
 }
 
@@ -1400,6 +1404,13 @@ int32_t csmc_persist_check(const csmc_model *model, int32_t n_replicas, int32_t 
     if (source && source_cap > 0) { std::strncpy(source, src.c_str(), (size_t)source_cap - 1); source[source_cap - 1] = 0; }
     if (log && log_cap > 0) { std::strncpy(log, lg.c_str(), (size_t)log_cap - 1); log[log_cap - 1] = 0; }
     if (!e.empty()) return fail(nullptr, CSMC_ERR_UNSUPPORTED, e);
+    return CSMC_OK;
+}
+
+int32_t csmc_kernel_costs(const csmc_handle *h, double *flops_per_or_update, double *bytes_per_update) {
+    NEED(h);
+    if (flops_per_or_update) *flops_per_or_update = h->jit ? h->jit_plan.flops_or_update : 0.0;
+    if (bytes_per_update) *bytes_per_update = 24.0 * (h->hm.n_colours + 1);
     return CSMC_OK;
 }
 

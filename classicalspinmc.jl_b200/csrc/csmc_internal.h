@@ -124,6 +124,7 @@ struct JitPlan {
     int skew_rows = 0;           // CTA-tile rows along dimension 0
     int skew_tiles_per_row = 0;  // CTA tiles per tile row (grid.x = rows * tiles_per_row)
     int skew_reach = 0;          // tile rows a site's neighbours can be away (>= 1)
+    double flops_or_update = 0.0;   // out: fp64 flops of one overrelaxation site update (fma = 2), averaged over the sites
     // tile-resident persistent kernel (jit.cpp emit_persist, api.cu enqueue_persist): one CTA per SM keeps a tile of the
     // lattice (plus halo) in shared memory for a whole sequence of sweeps and exchanges only halos through L2
     int persist_replicas = 0;    // in: replicas of the handle (0: do not generate the kernel)

@@ -45,6 +45,8 @@ struct Gen {
     std::vector<std::vector<LiveSlot>> seg_live;   // per segment: live interaction slots (filled by segment())
     std::vector<int> seg_preload;             // per segment: neighbours preloaded into registers
     std::vector<int> seg_split;               // per segment: warps a site's slots are split over (1, 2, 4)
+    std::vector<long> seg_flops;              // per segment: fp64 flops of one neighbour-field evaluation (fma = 2; a literal +-1 coefficient = 1)
+    long flops_cur = 0;
     std::vector<double> ktab;                 // coefficients placed in the constant bank
     std::map<uint64_t, int> kslot;
     // interaction coefficient as an operand: simple values stay literals (the compiler folds +-1 into
@@ -173,11 +175,16 @@ struct Gen {
         static const bool staged = !(std::getenv("CSMC_JIT_CONTRACT") && std::string(std::getenv("CSMC_JIT_CONTRACT")) == "outer");
         // sum_k x_k * y_k (+ init) as an explicit fma chain: the rounding order is fixed by the generator, so
         // the same term rounds identically in every kernel it is inlined into
-        auto chain = [](const std::vector<std::pair<std::string, std::string>> &xy, const std::string &init) {
+        auto chain = [this](const std::vector<std::pair<std::string, std::string>> &xy, const std::string &init) {
             std::string e = init;
-            for (const auto &p : xy) e = e.empty() ? p.first + " * " + p.second : "fma(" + p.first + ", " + p.second + ", " + e + ")";
+            for (const auto &p : xy) {
+                const bool unit = p.first == lit(1.0) || p.first == lit(-1.0);   // folded into an add / a negation by the compiler
+                flops_cur += e.empty() ? (unit ? 0 : 1) : (unit ? 1 : 2);
+                e = e.empty() ? p.first + " * " + p.second : "fma(" + p.first + ", " + p.second + ", " + e + ")";
+            }
             return e;
         };
+        flops_cur = 0;
         using Terms = std::vector<std::pair<std::string, std::string>>;
         auto emit_accumulate = [&](const HostTerm &t) {
             const double *C = hm.coefs.data() + t.coef;
@@ -314,6 +321,8 @@ struct Gen {
                 o << "      }\n";
             }
         o << "    }\n};\n\n";
+        seg_flops.resize(hm.segs.size(), 0);
+        seg_flops[s] = flops_cur;
     }
 
     // neighbour class and supercell shift of neighbour k of term t seen from class hs
@@ -764,6 +773,16 @@ struct Gen {
             for (size_t s = 0; s < hm.segs.size(); ++s) segment((int)s);   // fills ktab
             std::string segs = o.str();
             o.swap(head);
+            {   // fp64 flops of one overrelaxation update, averaged over the sites: neighbour field + F = g - h (3) + s.F (5)
+                // + F.F (5) + 2 * / (2) + the reflection (6); an on-site term adds 3 dot products and 3 doublings (18)
+                double f = 0.0;
+                long n = 0;
+                for (size_t s = 0; s < hm.segs.size(); ++s) {
+                    f += (double)hm.segs[s].count * ((double)seg_flops[s] + 21.0 + (hm.onsite_coef[hm.segs[s].basis] >= 0 ? 18.0 : 0.0));
+                    n += hm.segs[s].count;
+                }
+                plan.flops_or_update = n ? f / (double)n : 0.0;
+            }
             o << "#define NPAD " << hm.npad << "\n";
             o << "#define SPIN_S " << lit(hm.S) << "\n";
             o << kJitPrelude << "\n";

@@ -194,6 +194,11 @@ int32_t csmc_skew_schedule(int32_t n_rows, int32_t n_passes, int32_t reach, int3
  * (pass kernels / persistent kernel; zeros if not measured).  Any pointer may be NULL. */
 int32_t csmc_persist_info(const csmc_handle *h, int32_t *tiles, int32_t grid[2], int32_t *replicas_per_launch,
                           int32_t *smem_bytes, float ms[2]);
+/* Roofline inputs of the handle's runtime-specialised kernels, counted by the code generator: fp64 flops of one
+ * overrelaxation site update (neighbour field over the unrolled bilinear / cubic / quartic terms + the reflection
+ * s <- -s + 2 (s.F)/(F.F) F, src/monte_carlo.jl:126-139; fma = 2 flops, averaged over the sites; 0 without specialised
+ * kernels) and the algorithmic bytes per single-spin update, 24 (C + 1) for C colours.  Either pointer may be NULL. */
+int32_t csmc_kernel_costs(const csmc_handle *h, double *flops_per_or_update, double *bytes_per_update);
 /* host-only (no GPU needed): plans -- and with compile != 0 compiles for sm_100a -- the tile-resident kernel of `model`
  * for n_replicas replicas on a device with n_sms SMs and smem_max bytes of opt-in shared memory per CTA (0: B200's 148 /
  * 227 KiB).  info = {usable, tiles per replica, tiles along dim 0, dim 1, tile extent (supercells) along dim 0, dim 1,

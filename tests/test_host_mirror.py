@@ -1,5 +1,6 @@
 """CPU tests of the host-side mirror of the reference's Julia layer: UnitCell / Lattice tables,
 parameter buffer, observables (binning), output-file layout, parallel-tempering bookkeeping."""
+import math
 import os
 import warnings
 
@@ -264,3 +265,37 @@ def test_on_disk_orientation_is_what_hdf5_jl_produces(tmp_path):
     assert np.asarray(h5._get(g, "spin_correlations/SSF")).shape == (4, 9)     # Julia 9 x N_k
     assert np.array_equal(h5._get_jl(g, "spin_correlations/SSF"), S)
     g.close()
+
+
+def test_log_binning_hand_computed_known_answers():
+    """The logarithmic binning behind specific_heat / susceptibility error bars (src/observables.jl:32-63 through
+    BinningAnalysis.jl's ErrorPropagator) on a series small enough to do by hand: x = 1..8, pushed as (x, x^2).
+      level 0: 8 values          mean 9/2, unbiased variance 6      -> std error sqrt(6/8)
+      level 1: 3/2 7/2 11/2 15/2 (pair means)  variance 20/3        -> std error sqrt((20/3)/4)
+      level 2: 5/2 13/2                         variance 8           -> std error sqrt(8/2) = 2
+      level 3: 9/2 (a single bin: no variance)
+    second argument x^2: level-0 mean 204/8 = 51/2; cov(x, x^2) at level 0 = (1296 - 36 * 204 / 8) / 7 = 54.
+    First-order propagation of f = <x^2> - <x>^2 (the numerator of c and chi): gradient (-2 <x>, 1) = (-9, 1), so
+    var f = 81 var(x) - 18 cov(x, x^2) + var(x^2) with var(x^2) = (8772 - 204^2 / 8) / 7 = 510: 81*6 - 18*54 + 510 = 24."""
+    from classicalspinmc.jl_b200.observables import ErrorPropagator, std_error_tweak
+    ep = ErrorPropagator(2)
+    for x in range(1, 9):
+        ep.push(float(x), float(x * x))
+    assert ep.count[:5].tolist() == [8, 4, 2, 1, 0]
+    assert ep.mean(1) == 4.5 and ep.mean(2) == 25.5
+    assert np.isclose(ep.covmat(0)[0, 0], 6.0) and np.isclose(ep.covmat(1)[0, 0], 20.0 / 3.0) and np.isclose(ep.covmat(2)[0, 0], 8.0)
+    assert np.isclose(ep.std_error(1, 0), math.sqrt(6.0 / 8.0))
+    assert np.isclose(ep.std_error(1, 1), math.sqrt(20.0 / 3.0 / 4.0))
+    assert np.isclose(ep.std_error(1, 2), 2.0)
+    assert math.isnan(ep.std_error(1, 3))
+    assert np.isclose(ep.covmat(0)[0, 1], 54.0) and np.isclose(ep.covmat(0)[1, 1], 510.0)
+    grad = lambda m: np.array([-2.0 * m[0], 1.0])
+    assert np.isclose(ep.var(grad, 0), 24.0)
+    assert np.isclose(std_error_tweak(ep, grad, 0), math.sqrt(24.0 / 8.0))
+    # fewer than 32 bins at every level: the "reliable level" falls back to the unbinned one
+    assert ep.reliable_level() == 0
+    # with 64 * 32 values the highest level that still has >= 32 bins is level 6 (2048 / 2^6 = 32)
+    big = ErrorPropagator(2)
+    for x in range(2048):
+        big.push(float(x % 7), float((x % 7) ** 2))
+    assert big.count[6] == 32 and big.count[7] == 16 and big.reliable_level() == 6

@@ -57,14 +57,19 @@ def main():
         eng.set_temperatures(np.geomspace(0.5, 2.0, R))
         N, C = eng.N, eng.n_colours
         balg = B_ALG.get(C, 24.0 * (C + 1))
+        flops_upd = eng.kernel_costs()[0]
+        fp64_peak = torch.cuda.get_device_properties(0).multi_processor_count * 64 * 2 * 1.965e9 / 1e12   # nominal
         out = {"workload": spec, "N": N, "R": R, "colours": C, "mode": eng.kernel_mode, "groups": eng.sweep_groups(),
-               "persist": eng.persist_info(), "blocks": eng.replica_blocks()[0]}
+               "persist": eng.persist_info(), "blocks": eng.replica_blocks()[0], "flops_per_or_update": flops_upd}
         for label, orc, mc in (("or", 1, 0), ("or2", 2, 0), ("or10", 10, 0), ("or40", 40, 0), ("metro", 0, 1), ("metro2", 0, 2), ("metro10", 0, 10), ("cycle10+1", 10, 1)):
             n = max(args.n // max(orc + mc, 1), 5)
             dt = time_cycles(eng, stream, n, orc, mc)
             upd = n * (orc + mc) * N * R
             out[label] = {"Gupd_s": upd / dt / 1e9, "us_per_pass": dt / (n * (orc + mc) * C) * 1e6,
                           "GBs_alg": upd * balg / dt / 1e9, "frac": upd * balg / dt / 1e9 / peak}
+            if mc == 0:
+                out[label]["fp64_tflops"] = upd * flops_upd / dt / 1e12
+                out[label]["fp64_frac_nominal"] = upd * flops_upd / dt / 1e12 / fp64_peak
         if args.ssf:
             # equal-time structure factor: n_k wavevectors x N sites (src/spin_correlations.jl:6-43)
             import time

@@ -28,6 +28,11 @@ WANT = [
     ("smsp__warp_issue_stalled_wait_per_warp_active.pct", "stall wait %"),
     ("smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct", "stall lg_throttle %"),
     ("smsp__warp_issue_stalled_not_selected_per_warp_active.pct", "stall not_selected %"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "shared-memory wavefronts"),
+    ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "shared-memory bank conflicts"),
+    ("sm__cycles_elapsed.max", "SM cycles"),
+    ("launch__occupancy_limit_registers", "occupancy limit (registers)"),
+    ("launch__shared_mem_per_block_dynamic", "dynamic shared memory"),
 ]
 
 
@@ -43,6 +48,13 @@ def main():
         for key, label in WANT:
             if key in idx:
                 print(f"  {label:26s} {r[idx[key]]:>16s} {units[idx[key]]}")
+        # warp-state sampling: where the warps spent their time (share of all samples)
+        samp = {h[len("smsp__pcsamp_warps_issue_stalled_"):]: float(r[i]) for h, i in idx.items()
+                if h.startswith("smsp__pcsamp_warps_issue_stalled_") and not h.endswith("_not_issued") and r[i] not in ("", "n/a")}
+        tot = sum(samp.values())
+        if tot > 0:
+            top = sorted(samp.items(), key=lambda kv: -kv[1])[:8]
+            print("  warp-state samples         " + ", ".join(f"{k} {100.0 * v / tot:.0f} %" for k, v in top))
 
 
 if __name__ == "__main__":
