@@ -191,10 +191,14 @@ void launch_sweep_pass(csmc_handle *h, int colour, const SweepArgs &a, cudaStrea
     dim3 grid(h->pass_blocks[colour], nseg, nrep), block(TPB);
     if (h->jit) {
         // multi-dimensional CTA tiles over supercell coordinates, classes fused per thread (jit.cpp)
-        void *args[] = {(void *)&h->d_spins, (void *)&a};
+        SweepArgs a_full = a;          // a whole-grid launch of kernels built with a tile range covers every tile
+        if (n_tiles < 0) { a_full.tile_off = 0; a_full.tile_end = h->jit_plan.tiles[colour]; }
+        void *args[] = {(void *)&h->d_spins, (void *)&a_full};
         cudaLaunchConfig_t cfg{};
         // n_tiles >= 0: only the CTA tiles [a.tile_off, a.tile_off + n_tiles) (time-skewed strips, kernels built with CSMC_SKEW)
-        cfg.gridDim = dim3(n_tiles >= 0 ? n_tiles : h->jit_plan.tiles[colour], (UPD >= UPD_METRO ? h->jit_plan.groups_metro : h->jit_plan.groups)[colour], nrep);
+        const int tpc = (size_t)(colour * 4 + UPD) < h->jit_plan.tiles_per_cta.size() ? std::max(1, h->jit_plan.tiles_per_cta[colour * 4 + UPD]) : 1;
+        const int tiles = n_tiles >= 0 ? n_tiles : h->jit_plan.tiles[colour];
+        cfg.gridDim = dim3((tiles + tpc - 1) / tpc, (UPD >= UPD_METRO ? h->jit_plan.groups_metro : h->jit_plan.groups)[colour], nrep);
         cfg.blockDim = dim3(h->jit_plan.sweep_tpb);
         cfg.stream = stream;
         cudaLaunchAttribute attr[1];
@@ -338,6 +342,7 @@ void enqueue_skewed(csmc_handle *h, const SweepOp *seq, const std::vector<SkewLa
             SweepArgs a = sweep_args(h, op.ctr_off, op.device_ctr);
             a.rep0 = rep;
             a.tile_off = L.row0 * tpr;
+            a.tile_end = (L.row0 + L.nrows) * tpr;
             switch (op.upd) {
             case UPD_OR: launch_sweep_pass<UPD_OR>(h, colour, a, h->stream, 1, L.nrows * tpr); break;
             case UPD_DET: launch_sweep_pass<UPD_DET>(h, colour, a, h->stream, 1, L.nrows * tpr); break;
@@ -671,6 +676,10 @@ std::string load_persist_module(csmc_handle *h) {
         return e;
     }
     *h->persist_err = 0;
+    {   // in use only when asked for or when the create-time probe finds it faster than the pass kernels (autotune_pdl)
+        const char *e = std::getenv("CSMC_PERSIST");
+        h->persist_off = !((h->flags & CSMC_FLAG_PERSIST) != 0 || (e && e[0] == '1'));
+    }
     if (std::getenv("CSMC_PERSIST_PROF") && cudaMalloc((void **)&h->d_persist_prof, sizeof(unsigned long long) * 8 * 1024) != cudaSuccess) { cudaGetLastError(); h->d_persist_prof = nullptr; }
     h->persist_plan = plan;
     if (const char *e = std::getenv("CSMC_PERSIST_MIN_SWEEPS")) h->persist_min_sweeps = std::max(1, std::atoi(e));
@@ -1142,7 +1151,8 @@ static int autotune_pdl(csmc_handle *h) {
     const bool groups_from_env = std::getenv("CSMC_SWEEP_GROUPS") != nullptr;
     if (!groups_from_env) h->n_groups = 1;
     // the tile-resident kernel is timed last, against the best configuration of the pass kernels
-    const bool persist_candidate = h->jit_persist && !h->persist_off;
+    const bool persist_candidate = h->jit_persist != nullptr;
+    const bool persist_forced = persist_candidate && !h->persist_off;
     h->persist_off = true;
     for (int v = 0; v < 2; ++v) {
         install_jit_module(h, *mods[v]);
@@ -1194,8 +1204,7 @@ static int autotune_pdl(csmc_handle *h) {
         drop_graphs(h);
     }
     if (persist_candidate) {
-        const char *e = std::getenv("CSMC_PERSIST");
-        const bool forced = (h->flags & CSMC_FLAG_PERSIST) != 0 || (e && e[0] == '1');
+        const bool forced = persist_forced;
         h->tune_persist_ms[0] = best_so_far;
         h->persist_off = false;
         drop_graphs(h);

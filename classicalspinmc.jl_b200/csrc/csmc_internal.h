@@ -113,6 +113,7 @@ void reference_tables(const csmc_model *m, int64_t *bil, int64_t *cub, int64_t *
 // runtime specialisation (jit.cpp): model -> CUDA C++ source -> sm_100a cubin (NVRTC); "" on success
 struct JitPlan {
     std::vector<int> tiles, groups, groups_metro;
+    std::vector<int> tiles_per_cta;   // [colour * 4 + update kind]: consecutive tiles one CTA handles (CSMC_JIT_TPC experiment)
     bool resident = false;
     int sweep_tpb = 256;
     bool want_fused = false;     // in: also generate the fused full-sweep kernels (CSMC_FLAG_FUSED)

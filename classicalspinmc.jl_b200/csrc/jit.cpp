@@ -288,6 +288,22 @@ struct Gen {
                 o << "        }\n";
             }
         o << "    }\n";
+        // the same addresses as load(), as L1 prefetches (no destination registers): a CTA that handles several tiles pulls
+        // the next tile's operands into L1 while it works on the current one
+        o << "    static __device__ __forceinline__ void prefetch(const double *__restrict__ sx, const double *__restrict__ sy, const double *__restrict__ sz,\n"
+             "            int m0, int m1, int m2) {\n";
+        if (preload)
+            for (const auto &lv : live) {
+                const HostTerm &t = *lv.t;
+                o << "        { // slot " << lv.bit << "\n";
+                if (!hm.periodic) o << "          bool okt = true;\n";
+                for (int k = 0; k < t.kind - 1; ++k) neighbour(hs, t, k);
+                if (!hm.periodic) o << "          if (okt) {\n";
+                for (int k = 0; k < t.kind - 1; ++k) o << "          pf_l1(sx + j" << k << "); pf_l1(sy + j" << k << "); pf_l1(sz + j" << k << ");\n";
+                if (!hm.periodic) o << "          }\n";
+                o << "        }\n";
+            }
+        o << "    }\n";
         // phase 2 (PRELOAD): unrolled neighbour field from registers: a* bilinear, b* cubic, c* quartic accumulators
         o << "    template <int PART> static __device__ __forceinline__ void field(const double (&nb)[PRELOAD ? 3 * NNB + 1 : 1], unsigned ok,\n"
              "            double &a0, double &a1, double &a2, double &b0, double &b1, double &b2, double &c0, double &c1, double &c2) {\n";
@@ -890,28 +906,57 @@ struct Gen {
                 }
             } else {
             plan.groups[c] = 0;
+            // CSMC_JIT_TPC (experiment): a CTA handles TPC consecutive tiles one after the other; with CSMC_JIT_PREFETCH=1 it
+            // prefetches the next tile's operands into L1 right after issuing the current tile's loads, so that a pass
+            // that needs two waves of CTAs pays the L2 latency once
+            const int tpc_or = std::max(1, env_int("CSMC_JIT_TPC", 1)), tpc_mc = std::max(1, env_int("CSMC_JIT_TPC_METRO", 1));
+            const bool do_pf = env_int("CSMC_JIT_PREFETCH", 1) != 0;
+            plan.tiles_per_cta.resize(hm.n_colours * 4, 1);
+            const int n_tiles_c = NT[0] * NT[1] * NT[2];
             for (int u = 0; u < 4; ++u) {
                 const int G = std::min(nseg, u >= 2 ? fuse_mc : fuse_or);
                 const int ngroups = (nseg + G - 1) / G;
+                const int TPC = (SPc > 1) ? 1 : (u >= 2 ? tpc_mc : tpc_or);
+                plan.tiles_per_cta[c * 4 + u] = TPC;
                 if (u == 0) plan.groups[c] = ngroups;
                 if (u == 2) plan.groups_metro.resize(hm.n_colours), plan.groups_metro[c] = ngroups;
                 o << "extern \"C\" __global__ void __launch_bounds__(" << sw_tpb << ", " << (u >= 2 ? mb_mc : mb_or) << ") csmc_sweep_c" << c << "_u" << u << "(double *spins, const SweepArgs a) {\n";
                 o << "#ifdef CSMC_PDL\n#if CSMC_PDL == 1\n    pdl_launch_dependents();\n#endif\n    pdl_wait();\n#endif\n";
-                o << "    const int rep = blockIdx.z + a.rep0;\n    int t = blockIdx.x + CSMC_TILE_OFF(a);\n";
-                o << "    const int t2 = t % " << NT[2] << "; t /= " << NT[2] << "; const int t1 = t % " << NT[1] << "; const int t0 = t / " << NT[1] << ";\n";
+                o << "    const int rep = blockIdx.z + a.rep0;\n";
                 o << "    const int l2 = threadIdx.x & " << (T[2] - 1) << ", l1 = (threadIdx.x >> " << ilog2(T[2]) << ") & " << (T[1] - 1)
                   << ", l0 = threadIdx.x >> " << (ilog2(T[2]) + ilog2(T[1])) << ";\n";
-                o << "    const int m0 = t0 * " << T[0] << " + l0, m1 = t1 * " << T[1] << " + l1, m2 = t2 * " << T[2] << " + l2;\n";
+                auto coords = [&](const std::string &tv, const std::string &sfx) {
+                    o << "        int tq" << sfx << " = " << tv << ";\n";
+                    o << "        const int t2" << sfx << " = tq" << sfx << " % " << NT[2] << "; tq" << sfx << " /= " << NT[2] << "; const int t1" << sfx << " = tq" << sfx << " % " << NT[1]
+                      << "; const int t0" << sfx << " = tq" << sfx << " / " << NT[1] << ";\n";
+                    o << "        const int m0" << sfx << " = t0" << sfx << " * " << T[0] << " + l0, m1" << sfx << " = t1" << sfx << " * " << T[1] << " + l1, m2" << sfx << " = t2" << sfx << " * " << T[2] << " + l2;\n";
+                };
+                if (TPC == 1) {
+                    o << "    {\n";
+                    coords("(int)blockIdx.x + CSMC_TILE_OFF(a)", "");
+                } else {
+                    o << "    const int t_end = CSMC_TILE_END(a, " << n_tiles_c << ");\n";
+                    o << "    for (int it = 0; it < " << TPC << "; ++it) {\n";
+                    o << "        const int t_cur = ((int)blockIdx.x * " << TPC << " + it) + CSMC_TILE_OFF(a);\n";
+                    o << "        if (t_cur >= t_end) break;\n";
+                    coords("t_cur", "");
+                }
                 o << "    switch (blockIdx.y) {\n";
                 for (int g = 0; g < ngroups; ++g) {
                     o << "    case " << g << ": {\n";
                     for (int s = s0 + g * G; s < std::min(s1, s0 + (g + 1) * G); ++s) o << "        Site<Seg" << s << "> d" << s << "; site_load(d" << s << ", spins, rep, m0, m1, m2);\n";
+                    if (TPC > 1 && do_pf) {
+                        o << "        if (it + 1 < " << TPC << " && t_cur + 1 < t_end) {\n";
+                        coords("t_cur + 1", "n");
+                        for (int s = s0 + g * G; s < std::min(s1, s0 + (g + 1) * G); ++s) o << "        site_prefetch<Seg" << s << ">(spins, rep, m0n, m1n, m2n);\n";
+                        o << "        }\n";
+                    }
                     o << "        int n_acc = 0;\n";
                     for (int s = s0 + g * G; s < std::min(s1, s0 + (g + 1) * G); ++s) o << "        n_acc += site_finish<" << u << ">(d" << s << ", spins, rep, a) ? 1 : 0;\n";
                     if (u >= 2) o << "        count_accepted(n_acc, rep, a);\n";
                     o << "    } break;\n";
                 }
-                o << "    default: break;\n    }\n#if defined(CSMC_PDL) && CSMC_PDL == 2\n    pdl_launch_dependents();\n#endif\n}\n";
+                o << "    default: break;\n    }\n    }\n#if defined(CSMC_PDL) && CSMC_PDL == 2\n    pdl_launch_dependents();\n#endif\n}\n";
             }
             }
             o << "extern \"C\" __global__ void __launch_bounds__(TPB) csmc_energy_c" << c << "(const double *spins, double *__restrict__ partials, int n_partials, int partial_base) {\n";

@@ -31,13 +31,15 @@ struct SweepArgs {
     int rep0;
 #ifdef CSMC_SKEW
     int tile_off;   // first CTA tile of this launch (time-skewed strips, api.cu); the host struct always carries it
-    int pad_;
+    int tile_end;   // one past its last tile
 #endif
 };
 #ifdef CSMC_SKEW
 #define CSMC_TILE_OFF(a) ((a).tile_off)
+#define CSMC_TILE_END(a, total) ((a).tile_end)
 #else
 #define CSMC_TILE_OFF(a) 0
+#define CSMC_TILE_END(a, total) (total)
 #endif
 
 // by-value argument of csmc_persist (csmc_internal.h mirrors it)
@@ -147,6 +149,19 @@ __device__ __forceinline__ void site_load(Site<SEG> &d, const double *spins, int
         d.pos = SEG::pos(m0, m1, m2);
         d.s0 = sx[d.pos]; d.s1 = sy[d.pos]; d.s2 = sz[d.pos];
         if (SEG::PRELOAD) SEG::template load<NC, PART>(sx, sy, sz, m0, m1, m2, d.nb, d.ok);
+    }
+}
+
+__device__ __forceinline__ void pf_l1(const double *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// the operands site_load would read for (m0, m1, m2), as L1 prefetches
+template <class SEG>
+__device__ __forceinline__ void site_prefetch(const double *spins, int rep, int m0, int m1, int m2) {
+    const double *sx = spins + (size_t)rep * (3ull * NPAD), *sy = sx + NPAD, *sz = sy + NPAD;
+    if (SEG::valid(m0, m1, m2)) {
+        const int pos = SEG::pos(m0, m1, m2);
+        pf_l1(sx + pos); pf_l1(sy + pos); pf_l1(sz + pos);
+        if (SEG::PRELOAD) SEG::prefetch(sx, sy, sz, m0, m1, m2);
     }
 }
 

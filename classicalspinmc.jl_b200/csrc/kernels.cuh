@@ -31,7 +31,7 @@ struct SweepArgs {
     int replica_base;                    // global index of local replica 0
     int rep0;                            // first local replica of this launch (replica groups on separate streams)
     int tile_off;                        // first CTA tile of this launch: read only by runtime-specialised kernels built
-    int pad_;                            // with CSMC_SKEW (time-skewed strips); every other kernel's SweepArgs ends at rep0
+    int tile_end;                        // with CSMC_SKEW (time-skewed strips): [tile_off, tile_end); every other kernel's SweepArgs ends at rep0
 };
 static_assert(sizeof(SweepArgs) == 64, "SweepArgs layout (jit_prelude.h mirrors it)");
 
