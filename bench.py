@@ -41,6 +41,15 @@ L2_NOTE = ("GPU arm: L2 flushed between timed steps (256 MiB memset), the lattic
            "it exceeds 64 MiB; CPU arm: not applicable")
 
 
+_T0 = time.perf_counter()
+
+
+def progress(msg):
+    """stage marker on stderr (rank 0): tells where a multi-rank run is if it ever stalls"""
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(f"[bench {time.perf_counter() - _T0:7.1f} s] {msg}", file=sys.stderr, flush=True)
+
+
 def workload_model(name, L=None):
     from classicalspinmc.jl_b200 import workloads
     try:
@@ -311,9 +320,11 @@ def pt_records(world, rank, local_rank, stream, args):
     from classicalspinmc.jl_b200 import parallel
     out = {}
     for wl in ("C3", "C4"):
+        progress(f"parallel tempering {wl} on {world} GPU(s)")
         rec = run_pt(wl, None, world, rank, local_rank, stream, args.pt_steps, 1, args.sweeps_per_step)
         if world > 1:
             if rank == 0:
+                progress(f"parallel tempering {wl}, single-GPU point on rank 0")
                 one = run_pt(wl, None, world, rank, local_rank, stream, args.pt_steps, 1, args.sweeps_per_step, single=True)
                 rec["single_gpu_value"] = one["value"]
                 rec["pt_efficiency"] = rec["value"] / (world * one["value"])
@@ -326,6 +337,7 @@ def pt_records(world, rank, local_rank, stream, args):
     if world > 1:
         checks = {}
         for split in ("even", "uneven"):
+            progress(f"bit-identity check of the sharded run ({split} replica blocks)")
             checks[split] = parallel.pt_selfcheck(world, rank, local_rank, split)
         ident = {"ok": all(c["ok"] for c in checks.values()), **checks}
     return out, ident
@@ -342,7 +354,7 @@ def l2_copy_peak(torch, stream, n_bytes=12 << 20, reps=50):
         b.copy_(a)
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g, stream=stream):
+    with torch.cuda.graph(g, stream=stream, capture_error_mode="thread_local"):   # other threads (NCCL watchdog, clock sampler) may call CUDA
         for _ in range(reps):
             b.copy_(a)
     g.replay()
@@ -412,6 +424,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value") --------------------------------------------------------
+    progress(f"{args.workload}: engine ready, timing {args.steps} steps")
     for _ in range(max(args.warmup, 3)):
         eng.cycles_async(args.cycles_per_step, orc_, mc_)
     barrier()
@@ -435,16 +448,19 @@ def run_ours(args):
 
     # ---- dominant kernel: the overrelaxation colour pass, timed live inside the same graph shape as `value`
     # (replays of the `orc_`-sweep OR block of the cycle graph, no Metropolis sweeps) -------------------------
-    def time_or_block(e, or_sweeps, reps):
+    def time_or_block(e, or_sweeps, reps, sync=barrier):
+        """ms per replay of an `or_sweeps`-sweep OR block.  `sync` must be the local torch.cuda.synchronize when only
+        one rank takes the measurement (a collective barrier there would never be matched by the other ranks)."""
         e.cycles_async(max(reps // 5, 2), or_sweeps, 0)
-        barrier()
+        sync()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         flush.zero_()
         a.record(stream)
         e.cycles_async(reps, or_sweeps, 0)
         b.record(stream)
-        barrier()
+        sync()
         return a.elapsed_time(b) / reps          # ms per block
+    progress("dominant kernel inside the OR block graph")
     or_block = max(orc_, 1)
     block_ms = time_or_block(eng, or_block, 100)
     l_before = eng.launches
@@ -484,6 +500,7 @@ def run_ours(args):
                     traffic_note="ncu flushes caches between replays: cold-cache figure (whole lattice read once); steady state ~0")
 
     # ---- end to end through the C-ABI with HOST buffers ---------------------------------------------------
+    progress("end to end with host buffers")
     host_in = torch.empty((N, 3), dtype=torch.float64).pin_memory()
     host_out = torch.empty((N, 3), dtype=torch.float64).pin_memory()
     host_in.copy_(torch.from_numpy(eng.get_spins()))
@@ -517,12 +534,13 @@ def run_ours(args):
 
     # ---- the same kernel family where it is HBM-bound: C2 at L=4096, pass by pass ------------------------------
     roofline_hbm = None
-    if args.workload == "C2" and not args.no_hbm_point and rank == 0:
+    if args.workload == "C2" and not args.no_hbm_point and world == 1:      # a single-GPU property: measured at N = 1 only
+        progress("HBM-bound point: C2 at L=4096")
         md4, _ = workload_model("C2", 4096)
         e4 = _lib.Engine(md4, n_replicas=1, seed=1, device=local_rank, stream=stream.cuda_stream, flags=_abi.FLAG_NO_AUTOTUNE)
         e4.randomize(7)
         e4.set_temperatures(1.0)
-        ms4 = time_or_block(e4, 1, 40) / 2        # one sweep per graph: pass-by-pass order (no strips), 2 launches
+        ms4 = time_or_block(e4, 1, 40, sync=torch.cuda.synchronize) / 2   # one sweep per graph: pass by pass (no strips), 2 launches
         b4 = 72.0 * e4.N / 2
         a4 = b4 / (ms4 * 1e-3) / 1e9
         roofline_hbm = {"bound": "hbm", "workload": "C2 at L=4096 (384 MiB of spins, 3x the L2)", "kernel": "csmc_sweep_c<colour>_u0 (overrelaxation colour pass)",
@@ -540,8 +558,6 @@ def run_ours(args):
         roofline_hbm["cycle_updates_per_s"] = 10 * (orc_ + mc_) * e4.N / (a.elapsed_time(b) * 1e-3)
         roofline_hbm["cycle_time_skewed_strips"] = bool(e4.skew_info()[0])
         e4.close()
-    if world > 1:
-        dist.barrier()
 
     pt, ident = (None, None)
     if not args.no_pt:
@@ -564,6 +580,7 @@ def run_ours(args):
             line["pt_bit_identical"] = ident["ok"]
             line["pt_bit_identical_detail"] = ident
         if world == 1 and not args.no_cpu_baseline:
+            progress("CPU baseline legs")
             threads = args.cpu_threads or (os.cpu_count() or 1)
             n_ref = max(2 * args.ref_cycles, 8)          # ~5-10 s of CPU work per leg
             v, u, dtc = cpu_cycles(md, 1.0, orc_, mc_, n_ref, threads)

@@ -287,14 +287,6 @@ function parallel_tempering!(mc::MonteCarlo, saveIC::Vector{Int64}=Int64[]; alg:
         update_observables!(mc.observables_all[r], E[base+r, k], M[base+r, k])
     end
     download!(mc)          # configurations stay with their replicas; replica r sits in slot slots[base+r]
-    # the reference leaves at every rank the configuration that sits at that rank's temperature (it swaps
-    # configurations, src/monte_carlo.jl:336-347): re-order the local copies by slot where the slot is local
-    let slots = pt_slots(e, n_slots), byslot = Dict(slots[base+r] => mc.replica_spins[r] for r in 1:R)
-        if all(haskey(byslot, base + r - 1) for r in 1:R)      # single process: every slot is local
-            mc.replica_spins = [byslot[base+r-1] for r in 1:R]
-            mc.lattice.spins = mc.replica_spins[1]
-        end
-    end
     if out
         slots = pt_slots(e, n_slots)
         for r in 1:R
@@ -305,6 +297,14 @@ function parallel_tempering!(mc::MonteCarlo, saveIC::Vector{Int64}=Int64[]; alg:
         for r in 1:R
             # observables: accumulated per temperature slot; slot base+r-1 was measured on this process
             write_observables(slotfile(base + r - 1), mc.observables_all[r], T_all[base+r], mc.lattice.size)
+        end
+    end
+    # the reference leaves at every rank the configuration that sits at that rank's temperature (it swaps
+    # configurations, src/monte_carlo.jl:336-347): re-order the local copies by slot where the slot is local
+    let slots = pt_slots(e, n_slots), byslot = Dict(slots[base+r] => mc.replica_spins[r] for r in 1:R)
+        if all(haskey(byslot, base + r - 1) for r in 1:R)      # single process: every slot is local
+            mc.replica_spins = [byslot[base+r-1] for r in 1:R]
+            mc.lattice.spins = mc.replica_spins[1]
         end
     end
     rank == 0 && @printf("Simulation finished on %s.\n", Dates.format(Dates.now(), "dd u yyyy HH:MM:SS"))
