@@ -321,11 +321,11 @@ def pt_records(world, rank, local_rank, stream, args):
     out = {}
     for wl in ("C3", "C4"):
         progress(f"parallel tempering {wl} on {world} GPU(s)")
-        rec = run_pt(wl, None, world, rank, local_rank, stream, args.pt_steps, 1, args.sweeps_per_step)
+        rec = run_pt(wl, None, world, rank, local_rank, stream, args.pt_steps, 2, args.sweeps_per_step)
         if world > 1:
             if rank == 0:
                 progress(f"parallel tempering {wl}, single-GPU point on rank 0")
-                one = run_pt(wl, None, world, rank, local_rank, stream, args.pt_steps, 1, args.sweeps_per_step, single=True)
+                one = run_pt(wl, None, world, rank, local_rank, stream, args.pt_steps, 2, args.sweeps_per_step, single=True)
                 rec["single_gpu_value"] = one["value"]
                 rec["pt_efficiency"] = rec["value"] / (world * one["value"])
             dist.barrier()
@@ -613,7 +613,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pt", action="store_true", help="skip the parallel-tempering records (C3, C4) and the bit-identity check")
     ap.add_argument("--no-hbm-point", action="store_true", help="skip the L=4096 HBM-bound measurement of the dominant kernel")
-    ap.add_argument("--pt-steps", type=int, default=3, help="timed steps of the parallel-tempering records")
+    ap.add_argument("--pt-steps", type=int, default=5, help="timed steps of the parallel-tempering records")
     ap.add_argument("--sweeps-per-step", type=int, default=550, help="PT workloads: sweeps per timed step")
     ap.add_argument("--replicas", type=int, default=None, help="PT workloads: total replicas")
     args = ap.parse_args()

@@ -114,3 +114,17 @@ def test_persistent_kernel_in_parallel_tempering_is_bit_identical():
     assert np.array_equal(a[0][0], b[0][0]) and np.array_equal(a[0][1], b[0][1]) and np.array_equal(a[1], b[1])
     assert np.array_equal(a[2][0], b[2][0]) and np.array_equal(a[2][1], b[2][1])
     assert all(np.array_equal(x, y) for x, y in zip(a[3], b[3]))
+
+
+def test_generator_reports_flops_per_update():
+    """csmc_kernel_costs: the code generator's own count of fp64 flops per overrelaxation update (fma = 2, a literal
+    +-1 coefficient = 1) feeds the fp64 roofline of bench.py.  Square Heisenberg J = -1: 4 neighbours x 3 additions + 21
+    for F = g - h, s.F, F.F, the division and the reflection (src/monte_carlo.jl:126-139)."""
+    eng = _lib.Engine(ModelData(models.square_heisenberg(), (192, 192), 1.0), flags=BASE | FLAG_NO_PERSIST)
+    flops, nbytes = eng.kernel_costs()
+    assert flops == 33.0 and nbytes == 72.0
+    eng = _lib.Engine(ModelData(models.triangular_multispin(), (192, 176), 1.0), flags=BASE | FLAG_NO_PERSIST)
+    flops, nbytes = eng.kernel_costs()
+    # 4 quartic slots x 3 x (27 + 9 + 3) fma + 3 cubic slots x 3 x (9 + 3) fma + 6 x 3 additions + 21, minus the first
+    # multiply of each chain: about a thousand flops per site
+    assert 900.0 < flops < 1100.0 and nbytes == 120.0
