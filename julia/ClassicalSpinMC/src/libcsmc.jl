@@ -184,3 +184,20 @@ function pt_sigma_by_slot(e::Engine, n_slots, base, R)
     end
     return allgather_sigma(sig)
 end
+
+# --- introspection added in round 2 ---------------------------------------------------------------------------
+# (tiles per replica of the tile-resident persistent kernel (0: not in use), tiles along dims 0 / 1, replicas per launch,
+#  shared memory per CTA, create-time probe ms: pass kernels / persistent kernel)
+function persist_info(e::Engine)
+    tiles = Ref{Int32}(0); nrep = Ref{Int32}(0); smem = Ref{Int32}(0)
+    grid = zeros(Int32, 2); ms = zeros(Float32, 2)
+    check(e, ccall((:csmc_persist_info, libcsmc), Int32, (Ptr{Cvoid}, Ref{Int32}, Ptr{Int32}, Ref{Int32}, Ref{Int32}, Ptr{Float32}),
+                   e.ptr, tiles, grid, nrep, smem, ms))
+    return (tiles=Int(tiles[]), grid=(Int(grid[1]), Int(grid[2])), replicas_per_launch=Int(nrep[]), smem=Int(smem[]), probe_ms=(ms[1], ms[2]))
+end
+# (fp64 flops per overrelaxation update counted by the code generator, algorithmic bytes per update) — roofline inputs
+function kernel_costs(e::Engine)
+    f = Ref{Float64}(0.0); b = Ref{Float64}(0.0)
+    check(e, ccall((:csmc_kernel_costs, libcsmc), Int32, (Ptr{Cvoid}, Ref{Float64}, Ref{Float64}), e.ptr, f, b))
+    return f[], b[]
+end

@@ -239,3 +239,41 @@ def test_time_skewed_order_with_a_metropolis_sweep_in_the_oracle():
         sel = sites[(colour == p % n_col) & (row_of >= row0) & (row_of < row0 + nrows)]
         acc_skew += run(s_skew, sel, kinds[p // n_col])
     assert np.array_equal(s_skew, s_ref) and acc_skew == acc_ref and 0 < acc_ref < md.n_sites
+
+
+@pytest.mark.parametrize("workload,replicas,colours", [("C2", 1, 2), ("C3", 8, 2), ("C3", 64, 2), ("C4", 16, 4), ("C5", 1, 4)])
+def test_persistent_kernel_tiling_plan(workload, replicas, colours):
+    """csmc_persist_check (host only): the tiling of the tile-resident persistent kernel for the BASELINE workloads on a
+    B200 (148 SMs, 227 KiB of shared memory per CTA): the tiles cover the supercell grid exactly, one launch never needs
+    more CTAs than there are SMs (co-residency of the cooperative launch), and the padded tiles of every class fit the
+    shared memory."""
+    from classicalspinmc.jl_b200 import workloads
+    md, _ = workloads.workload_model(workload)
+    info, src, _ = _lib.persist_check(md, replicas, compile=False)
+    assert info["usable"]
+    assert info["tiles"] == info["g0"] * info["g1"] and info["tiles"] * info["replicas_per_launch"] <= 148
+    assert 1 <= info["replicas_per_launch"] <= replicas
+    assert info["smem"] + 1024 <= 227 * 1024
+    col, ncol, structured, _ = _lib.plan(md)
+    assert ncol == colours and structured
+    # supercell extents along the two tiled dimensions: lattice extent / colouring period; g tiles of extent w cover them
+    m = re.search(r"tiles of (\d+) x (\d+) x (\d+) supercells per replica \(padded (\d+) x (\d+)\)", src)
+    assert m and (int(m.group(1)), int(m.group(2))) == (info["w0"], info["w1"])
+    per = [p for p in (1, 2) if md.shape[0] % p == 0]
+    M0 = [md.shape[0] // p for p in per]
+    assert any((info["g0"] - 1) * info["w0"] < M <= info["g0"] * info["w0"] for M in M0)
+    assert "csmc_persist" in src and "st_release_gpu" in src and "persist_wait" in src
+
+
+def test_persistent_kernel_compiles_and_rejects_what_it_cannot_tile():
+    from classicalspinmc.jl_b200 import workloads
+    info, _, log = _lib.persist_check(ModelData(models.kitaev_honeycomb(J3=0.25), (64, 48), 1.0), 3, compile=True)
+    assert info["usable"] and "error" not in log.lower()
+    # a lattice whose replica does not fit the SMs' shared memory: 384 MiB of spins
+    md, _ = workloads.workload_model("C2", 4096)
+    assert not _lib.persist_check(md, 1, compile=False)[0]["usable"]
+    # open boundaries are left to the pass kernels
+    assert not _lib.persist_check(ModelData(models.square_heisenberg(), (64, 64), 1.0, "open"), 1, compile=False)[0]["usable"]
+    # a device with few SMs still gets a plan (more, smaller launches are not needed: tiles grow until they fit)
+    few = _lib.persist_check(ModelData(models.square_heisenberg(), (256, 256), 1.0), 4, n_sms=16, compile=False)[0]
+    assert few["usable"] and few["tiles"] * few["replicas_per_launch"] <= 16
