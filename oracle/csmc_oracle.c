@@ -13,7 +13,8 @@
  *       :6 (|s| == S), test/mctests.jl:49,57 (annealed E/N rounds to -0.6444);
  *   - cubic / quartic contractions (Einsum.jl 0.4.1, not vendored; src/hamiltonian.jl:46-48,
  *     62-64,114,127,180,193): no reference test touches them -> "parity unpinned"; restated
- *     from the formulae as written and checked for self-consistency.
+ *     from the formulae as written, checked for self-consistency and against an independent
+ *     numpy restatement of the same reference lines (tests/test_oracle_golden.py).
  *   - RNG: the reference uses Julia's task-local Xoshiro256++, unseeded in its tests, so no
  *     stream is pinned.  Reference-order drivers here use xoshiro256++; the colour-order
  *     Metropolis uses the same counter-based Philox4x32-10 stream as the CUDA kernels so the two

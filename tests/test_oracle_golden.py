@@ -199,3 +199,115 @@ def test_forward_error_bound_covers_a_differently_rounded_build(name, builder, s
         a.sweep_tracked(s, order, 0, kappa)
     b.overrelax(t, order, 2)
     assert np.all(np.abs(s - t).max(axis=1) <= 1e-12 * S * kappa)
+
+
+def _numpy_multispin_reference(uc, shape, bc, spins):
+    """An independent, literal numpy restatement of the reference's cubic / quartic code — table construction with
+    `permutedims` (src/lattice.jl:209-283, first matching branch) and the `@einsum` lines of get_local_field and energy
+    (src/hamiltonian.jl:46-48, 62-64, 180, 193) — for 2-D lattices: the arithmetic that lives in Einsum.jl, for which
+    the reference holds no test vector.  Returns (cubic + quartic part of the field [N, 3], of the site energy [N])."""
+    import itertools
+    nb = len(uc.basis)
+    L1, L2 = shape
+    indices = sorted((b, i1, i2) for b in range(1, nb + 1) for i1 in range(1, L1 + 1) for i2 in range(1, L2 + 1))   # :29-33
+    lookup = {t: p for p, t in enumerate(indices)}
+
+    def BC(index, off):                                                      # :101-109
+        out = []
+        for d, L in enumerate(shape):
+            v = index[1 + d] + off[d]
+            if bc == "periodic":
+                v = (v - 1) % L + 1
+            out.append(v)
+        return tuple(out)
+
+    def find(b, cell):
+        return lookup.get((b,) + cell)                                       # findfirst(...) or nothing (open bc)
+
+    N = len(indices)
+    F = np.zeros((N, 3))
+    E = np.zeros(N)
+    for p, index in enumerate(indices):
+        s = spins[p]
+        for (b1, b2, b3, J, oj, ok) in uc.cubic:                            # :209-237
+            J = np.asarray(J)
+            oj, ok = np.array(oj), np.array(ok)
+            if index[0] not in (b1, b2, b3):
+                continue
+            if b1 == index[0]:
+                bj, bk = b2, b3
+            elif b2 == index[0]:
+                bj, bk = b1, b3
+                ok = ok - oj
+                oj = oj * -1
+                J = np.transpose(J, (1, 0, 2))                               # permutedims(J, [2, 1, 3])
+            else:
+                bj, bk = b2, b1
+                oj = oj - ok
+                ok = ok * -1
+                J = np.transpose(J, (2, 1, 0))                               # permutedims(J, [3, 2, 1])
+            j, k = find(bj, BC(index, oj)), find(bk, BC(index, ok))
+            if j is None or k is None:
+                continue
+            sj, sk = spins[j], spins[k]
+            for x in range(3):
+                F[p, x] += np.einsum("ab,a,b->", J[x], sj, sk)               # @einsum Hx += C[1, a, b] * sj[a] * sk[b]
+            E[p] += np.einsum("abc,a,b,c->", J, s, sj, sk)                   # @einsum E += C[a, b, c] * s[a] * sj[b] * sk[c]
+        for (b1, b2, b3, b4, J, oj, ok, ol) in uc.quartic:                   # :243-283
+            J = np.asarray(J)
+            oj, ok, ol = np.array(oj), np.array(ok), np.array(ol)
+            if index[0] not in (b1, b2, b3, b4):
+                continue
+            if b1 == index[0]:
+                bj, bk, bl = b2, b3, b4
+            elif b2 == index[0]:
+                bj, bk, bl = b1, b3, b4
+                oj = oj * -1
+                ok = ok + oj
+                ol = ol + oj
+                J = np.transpose(J, (1, 0, 2, 3))                            # [2, 1, 3, 4]
+            elif b3 == index[0]:
+                bj, bk, bl = b2, b1, b4
+                ok = ok * -1
+                ol = ol + ok
+                oj = oj + ok
+                J = np.transpose(J, (2, 1, 0, 3))                            # [3, 2, 1, 4]
+            else:
+                bj, bk, bl = b2, b3, b1
+                ol = ol * -1
+                oj = oj + ol
+                ok = ok + ol
+                J = np.transpose(J, (3, 1, 2, 0))                            # [4, 2, 3, 1]
+            j, k, l = find(bj, BC(index, oj)), find(bk, BC(index, ok)), find(bl, BC(index, ol))
+            if j is None or k is None or l is None:
+                continue
+            sj, sk, sl = spins[j], spins[k], spins[l]
+            for x in range(3):
+                F[p, x] += np.einsum("abc,a,b,c->", J[x], sj, sk, sl)        # @einsum Hx += R[1, a, b, c] * sj[a] * sk[b] * sl[c]
+            E[p] += np.einsum("abcd,a,b,c,d->", J, s, sj, sk, sl)
+    return F, E
+
+
+@pytest.mark.parametrize("name,builder,shape,bc,S", [
+    ("mixed-basis-4x6", lambda: models.mixed_basis_multispin(), (4, 6), "periodic", 0.8),
+    ("mixed-basis-open-5x3", lambda: models.mixed_basis_multispin(), (5, 3), "open", 0.8),
+    ("triangular-multispin-6x4", lambda: models.triangular_multispin(), (6, 4), "periodic", 1.0),
+])
+def test_cubic_and_quartic_terms_against_a_literal_numpy_restatement(name, builder, shape, bc, S):
+    """Pins the oracle's cubic / quartic arithmetic (every perspective branch, both boundary conditions) against an
+    independent numpy restatement of the reference's lines; the bilinear / on-site / Zeeman part is taken out by
+    evaluating the oracle on the same model without multi-spin terms."""
+    uc = builder()
+    md = ModelData(uc, shape, S, bc)
+    lat = orc.OracleLattice(md)
+    s = lat.randomize(seed=9)
+    uc0 = builder()
+    uc0.cubic.clear()
+    uc0.quartic.clear()
+    lat0 = orc.OracleLattice(ModelData(uc0, shape, S, bc))
+    F = lat.local_field_all(s) - lat0.local_field_all(s)
+    E = lat.site_energy_all(s) - lat0.site_energy_all(s)
+    F_ref, E_ref = _numpy_multispin_reference(uc, shape, bc, s)
+    assert np.abs(F_ref).max() > 1e-3 and np.abs(E_ref).max() > 1e-3          # the terms are really there
+    assert np.abs(F - F_ref).max() <= 1e-13 * max(1.0, np.abs(F_ref).max())
+    assert np.abs(E - E_ref).max() <= 1e-13 * max(1.0, np.abs(E_ref).max())
