@@ -1179,12 +1179,21 @@ static int autotune_pdl(csmc_handle *h) {
     }
     // replica blocks (enqueue_sweep_seq): all replicas per pass, or block by block so that a block stays in L2
     if (!std::getenv("CSMC_REPLICA_BLOCKS") && replica_blocks_wanted(h) > 1) {
+        // candidates: the count the L2 budget asks for and one more (slightly smaller blocks leave room for the other
+        // colours' lines and the write-backs: C3 x 64 replicas runs 3 % faster in 4 blocks of 48 MiB than in 3 of 64 MiB)
         h->tune_blocks_ms[0] = best_so_far;
-        h->n_blocks = replica_blocks_wanted(h);
-        drop_graphs(h);
-        int rc = probe(h->tune_blocks_ms[1]); if (rc) return rc;
-        if (h->tune_blocks_ms[1] < 0.97f * best_so_far) best_so_far = h->tune_blocks_ms[1];
-        else h->n_blocks = 1;
+        h->tune_blocks_ms[1] = 1e30f;
+        const int want = replica_blocks_wanted(h);
+        int best_nb = 1;
+        for (int cand = want; cand <= std::min(want + 1, h->R); ++cand) {
+            float ms = 0.f;
+            h->n_blocks = cand;
+            drop_graphs(h);
+            int rc = probe(ms); if (rc) return rc;
+            h->tune_blocks_ms[1] = std::min(h->tune_blocks_ms[1], ms);
+            if (ms < 0.97f * h->tune_blocks_ms[0] && ms < best_so_far) { best_so_far = ms; best_nb = cand; }
+        }
+        h->n_blocks = best_nb;
         drop_graphs(h);
     }
     // replica groups on separate streams (enqueue_sweep_seq): 1, 2 or 4 concurrent chains

@@ -176,8 +176,9 @@ int32_t csmc_sweep_groups(const csmc_handle *h, int32_t *groups, float ms[3]);
 /* Replica blocks: when the spins of all replicas of the handle exceed the L2 budget (64 MiB; CSMC_L2_BLOCK_MB),
  * a sequence of sweeps enqueued at once (the OR block + Metropolis sweep between two exchanges) can run block
  * by block -- all sweeps for the first replicas, then for the next -- so that each block is read from HBM once
- * and stays L2-resident for every colour pass of the sequence.  csmc_create times both and keeps the faster
- * (ms[0] all replicas per pass, ms[1] blocked; 0 when not probed); CSMC_REPLICA_BLOCKS=n forces n blocks.
+ * and stays L2-resident for every colour pass of the sequence.  csmc_create times the unblocked order against the
+ * block count the budget asks for and one more, and keeps the fastest (ms[0] all replicas per pass, ms[1] the
+ * faster blocked candidate; 0 when not probed); CSMC_REPLICA_BLOCKS=n forces n blocks.
  * Results do not depend on it (replicas are independent between exchanges). */
 int32_t csmc_replica_blocks(const csmc_handle *h, int32_t *blocks, float ms[2]);
 /* Time-skewed strips (CSMC_FLAG_SKEW).  csmc_skew_schedule is host-only: the launch plan for n_passes colour passes

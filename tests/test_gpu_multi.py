@@ -36,10 +36,8 @@ def test_sharded_parallel_tempering_is_bit_identical_to_single_gpu(world, split)
                                                       (8, "even", "passes", 2), (8, "uneven", "resident", 1)])
 def test_peer_memory_gather_is_bit_identical_to_single_gpu(world, split, kernels, peer):
     """CSMC_PEER_GATHER=1 / 2: the measurement records travel by stores into CUDA-IPC-mapped peer memory instead of
-    ncclAllGather (csmc_comm_mode 2 / 3).  The 2-GPU cases were run on a B200 pair in round 1
-    (profiles/r1c_peer_2gpu.log); the 8-GPU cases have not been run yet: CSMC_TEST_PEER_GATHER=1 includes them."""
-    if world > 2 and os.environ.get("CSMC_TEST_PEER_GATHER") != "1":
-        pytest.skip("8-GPU peer-memory gather tests are opt-in until run once (CSMC_TEST_PEER_GATHER=1)")
+    ncclAllGather (csmc_comm_mode 2 / 3).  Run on a B200 pair in round 1 (profiles/r1c_peer_2gpu.log) and on 8 B200s in
+    round 2 (profiles/r2j_pytest_multi_8gpu.log)."""
     if _n_gpus() < world:
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",

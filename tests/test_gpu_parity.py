@@ -368,8 +368,8 @@ def test_replica_blocks_autotune_reports_both_timings(monkeypatch):
     md = ModelData(models.kitaev_honeycomb(), (128, 128), 1.0)
     eng = _lib.Engine(md, n_replicas=8, seed=5, flags=FLAG_JIT | FLAG_NO_RESIDENT)
     blocks, ms = eng.replica_blocks()
-    assert ms[0] > 0 and ms[1] > 0 and blocks in (1, 6)
-    assert (blocks == 6) == (ms[1] < 0.97 * ms[0])
+    assert ms[0] > 0 and ms[1] > 0 and blocks in (1, 6, 7)     # candidates: the count the budget asks for and one more
+    assert (blocks > 1) == (ms[1] < 0.97 * ms[0])             # ms[1]: the faster of the blocked candidates
 
 
 SKEW_CASES = [("square-256", models.square_heisenberg, (256, 256), 1.0),

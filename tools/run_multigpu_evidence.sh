@@ -6,7 +6,7 @@ set -u
 tag=${1:-r2}
 out=gpurun_out
 mkdir -p $out
-export CSMC_TEST_PEER_GATHER=1
+
 timeout 900 python -m pytest tests/test_gpu_multi.py -q -k "4-even or 8-even or 8-uneven" > $out/${tag}_pytest_multi_8gpu.log 2>&1
 tail -4 $out/${tag}_pytest_multi_8gpu.log
 run() { # name, env, args...
