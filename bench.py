@@ -497,7 +497,9 @@ def run_ours(args):
                     us_per_launch=pass_ms * 1e3, us_per_colour_pass=block_ms * 1e3 / (or_block * n_col),
                     algorithmic_bytes_per_launch=bytes_per_launch,
                     traffic=ncu_traffic(f"{cfg['workload']}:{cfg['L']}" + (":persist" if pm[0] else "")),
-                    traffic_note="ncu flushes caches between replays: cold-cache figure (whole lattice read once); steady state ~0")
+                    traffic_steady_state=ncu_traffic(f"{cfg['workload']}:{cfg['L']}:steady"),
+                    traffic_note="`traffic`: isolated launch with caches flushed by ncu (the whole lattice is read once); "
+                                 "`traffic_steady_state`: the same launch inside a running cycle with the lattice L2-resident")
 
     # ---- end to end through the C-ABI with HOST buffers ---------------------------------------------------
     progress("end to end with host buffers")

@@ -14,6 +14,10 @@ WANT = [
     ("l1tex__t_bytes.sum", "L1 bytes"),
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram % of peak"),
     ("lts__t_sector_hit_rate.pct", "L2 hit %"),
+    ("lts__t_sectors.sum", "L2 sectors (32 B)"),
+    ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 throughput % of peak"),
+    ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "L1 throughput % of peak"),
+    ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "LSU pipe %"),
     ("l1tex__t_sector_hit_rate.pct", "L1 hit %"),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue active %"),
