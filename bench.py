@@ -148,11 +148,27 @@ def ncu_traffic(key):
 
 
 # ---- CPU legs (the only places bench.py executes anything under oracle/) ---------------------------------------------
+_CPU_BUILD = {"flags": None}
+
+
+def cpu_lattice(md):
+    """The oracle lattice of the timed CPU legs: the performance build (-O3 -march=native, compiled on this box); if no
+    compiler is available here, the shipped checker build (-O3 -march=x86-64-v3 -ffp-contract=off) is timed instead and
+    `cpu_baseline.sample` says so."""
+    from oracle import oracle as orc
+    try:
+        lat = orc.OracleLattice(md, fast=True)
+        _CPU_BUILD["flags"] = "gcc " + orc.FAST_CFLAGS
+    except Exception as e:                                   # no gcc on the box, read-only tree, ...
+        lat = orc.OracleLattice(md)
+        _CPU_BUILD["flags"] = f"checker build -O3 -march=x86-64-v3 -ffp-contract=off (performance build unavailable: {type(e).__name__})"
+    return lat
+
+
 def cpu_cycles(md, T, or_per_cycle, metro_per_cycle, n_cycles, threads):
     """The oracle's restatement of the reference algorithm (random-site Metropolis with two energy() evaluations,
     sequential overrelaxation), performance build, timed on the host cores: `threads` independent replicas."""
-    from oracle import oracle as orc
-    lat = orc.OracleLattice(md, fast=True)
+    lat = cpu_lattice(md)
     spins = np.concatenate([lat.randomize(seed=12345, replica=r) for r in range(threads)])
     t0 = time.perf_counter()
     updates = lat.cycles(spins, threads, T, n_cycles, or_per_cycle, metro_per_cycle)
@@ -164,8 +180,7 @@ def cpu_pt(md, T_all, sweeps, threads, swap_rate=50, rate=10, seed=3):
     """The oracle's restatement of the reference parallel-tempering loop (src/monte_carlo.jl:289-349: OR every
     sweep, random-site Metropolis + total_energy every `rate`-th, configuration-swapping exchange every
     `swap_rate`-th), one temperature per host thread as examples/parallel_tempering/README.txt:17."""
-    from oracle import oracle as orc
-    lat = orc.OracleLattice(md, fast=True)
+    lat = cpu_lattice(md)
     R = len(T_all)
     spins = np.concatenate([lat.randomize(seed=12345, replica=r) for r in range(R)])
     t0 = time.perf_counter()
@@ -176,8 +191,10 @@ def cpu_pt(md, T_all, sweeps, threads, swap_rate=50, rate=10, seed=3):
 
 
 def cpu_flags():
-    from oracle import oracle as orc
-    return "gcc " + orc.FAST_CFLAGS
+    if _CPU_BUILD["flags"] is None:
+        from oracle import oracle as orc
+        return "gcc " + orc.FAST_CFLAGS
+    return _CPU_BUILD["flags"]
 
 
 def run_reference(args):
@@ -199,14 +216,14 @@ def run_reference(args):
         one, warm = sweeps, 10
         sample = (f"reference parallel-tempering loop, {len(T_all)} temperatures on {threads} host threads, {sweeps} sweeps per "
                   f"step (swap 50, OR 10, total_energy after every Metropolis sweep, configurations swapped); "
-                  f"C restatement, not Julia; {cpu_flags()}")
+                  f"C restatement, not Julia; ")
     else:
         def step(n):
             return cpu_cycles(md, 1.0, args.or_per_cycle, args.metro_per_cycle, n, threads)
         one, warm = args.ref_cycles, 1
         sample = (f"{threads} independent replicas (one per host thread, as one MPI rank per temperature) x "
                   f"{one} cycle(s) of the {cfg['workload']} lattice per step; reference algorithm unchanged "
-                  f"(C restatement, not Julia); {cpu_flags()}")
+                  f"(C restatement, not Julia); ")
     for _ in range(args.warmup):          # untimed: a short pass (pages in the lattice and the thread pool)
         step(warm)
     tot_u, tot_t = 0.0, 0.0
@@ -215,6 +232,7 @@ def run_reference(args):
         tot_u += u
         tot_t += dt
     value = tot_u / max(tot_t, 1e-30)
+    sample += cpu_flags()            # known once the library has been built / loaded
     line = {"impl": "reference", "metric": "single-spin updates/sec (Metropolis+overrelax)" + (", parallel tempering" if pt else ""),
             "value": value,
             "unit": "updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
