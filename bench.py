@@ -516,6 +516,7 @@ def run_ours(args):
                     algorithmic_bytes_per_launch=bytes_per_launch,
                     traffic=ncu_traffic(f"{cfg['workload']}:{cfg['L']}" + (":persist" if pm[0] else "")),
                     traffic_steady_state=ncu_traffic(f"{cfg['workload']}:{cfg['L']}:steady"),
+                    ncu_steady_state=ncu_traffic(f"{cfg['workload']}:{cfg['L']}:ncu_steady_state"),
                     traffic_note="`traffic`: isolated launch with caches flushed by ncu (the whole lattice is read once); "
                                  "`traffic_steady_state`: the same launch inside a running cycle with the lattice L2-resident")
 
