@@ -158,6 +158,7 @@ struct csmc_handle {
         unsigned long long timeout_ns = 30000000000ULL;
     } peer;
 
+    bool capture_open = false;   // a stream capture this handle began has not been ended (a call failed in between)
     std::string err;
     long long launches = 0;
 };
@@ -1249,14 +1250,12 @@ int32_t csmc_reference_tables(const csmc_model *model, int64_t *bil, int64_t *cu
 int32_t csmc_destroy(csmc_handle *h) {
     if (!h) return CSMC_OK;
     cudaSetDevice(h->device);
-    if (h->stream) {   // a call that failed inside a stream capture must not leave the stream capturing
-        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
-        if (cudaStreamIsCapturing(h->stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone) {
-            cudaGraph_t g = nullptr;
-            cudaStreamEndCapture(h->stream, &g);
-            if (g) cudaGraphDestroy(g);
-        }
+    if (h->stream && h->capture_open) {   // a capture this handle began must not outlive it (never ends a caller's own capture)
+        cudaGraph_t g = nullptr;
+        cudaStreamEndCapture(h->stream, &g);
+        if (g) cudaGraphDestroy(g);
         cudaGetLastError();
+        h->capture_open = false;
     }
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (auto &kv : h->cycle_graphs) cudaGraphExecDestroy(kv.second.exec);
@@ -1660,8 +1659,10 @@ static int build_cycle_graph(csmc_handle *h, int orc, int mc, const csmc_handle:
     for (int s = 0; s < orc; ++s) seq.push_back({UPD_OR, 0ULL, false});
     for (int s = 0; s < mc; ++s) seq.push_back({UPD_METRO, (unsigned long long)s, true});
     CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    h->capture_open = true;
     enqueue_sweep_seq(h, seq.data(), (int)seq.size(), fused);
     if (mc > 0) { k_add_u64<<<1, 1, 0, h->stream>>>(h->d_ctr, (unsigned long long)mc); h->launches++; }
+    h->capture_open = false;
     CK(cudaStreamEndCapture(h->stream, &graph));
     const long long launches = h->launches - before;
     h->launches = before;  // capture enqueues nothing
@@ -1731,7 +1732,9 @@ static int enqueue_or_block(csmc_handle *h, int n) {
         const long long before = h->launches;
         sweep_groups(h, 2);   // streams / events of the replica groups exist before the capture starts
         CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        h->capture_open = true;
         enqueue_sweep_seq(h, seq.data(), n, fused);
+        h->capture_open = false;
         CK(cudaStreamEndCapture(h->stream, &graph));
         h->or_graph_launches[n] = h->launches - before;
         h->launches = before;
