@@ -594,8 +594,9 @@ void install_jit_module(csmc_handle *h, const JitModule &m) {
 }
 
 // ---- tile-resident persistent kernel (jit.cpp emit_persist) ---------------------------------------------------
-// on request (CSMC_FLAG_PERSIST, CSMC_PERSIST=1), never with CSMC_FLAG_NO_PERSIST / CSMC_PERSIST=0, otherwise for every
-// eagerly specialised handle; whether sweep sequences then run on it is decided by the create-time autotune
+// Built on request only: CSMC_FLAG_PERSIST / CSMC_PERSIST=1 use it whenever it applies, CSMC_PERSIST=probe builds it and
+// lets the create-time autotune time it against the pass kernels.  By default it is not even compiled: on every workload
+// measured it lost to the pass kernels, and its NVRTC build costs 1.6 s (C2) to 6 s (C5) per model.
 bool want_persist(const csmc_handle *h) {
     const char *e = std::getenv("CSMC_PERSIST");
     if ((h->flags & CSMC_FLAG_NO_PERSIST) || (e && e[0] == '0')) return false;
@@ -603,7 +604,7 @@ bool want_persist(const csmc_handle *h) {
     // an explicit request for the time-skewed strips or the fused full-sweep kernels is not overridden
     const char *sk = std::getenv("CSMC_SKEW");
     if ((h->flags & (CSMC_FLAG_SKEW | CSMC_FLAG_FUSED)) || (sk && sk[0] == '1')) return false;
-    return true;
+    return e && (e[0] == 'p' || e[0] == 'a');      // "probe" / "auto"
 }
 
 void persist_release(csmc_handle *h) {

@@ -111,8 +111,9 @@ typedef struct csmc_opts {
                                      pass -- instead of streaming the lattice through L2 once per pass.  Results are  \
                                      bit-identical (csmc_skew_schedule, csmc_skew_info)                               */
 #define CSMC_FLAG_NO_PERSIST 512  /* never use the tile-resident persistent kernel (also CSMC_PERSIST=0)              */
-#define CSMC_FLAG_PERSIST 1024    /* use it whenever it applies, without the create-time timing against the per-colour \
-                                     pass kernels (also CSMC_PERSIST=1).  The tile-resident kernel (csmc_persist_info)    \
+#define CSMC_FLAG_PERSIST 1024    /* build and use it whenever it applies (also CSMC_PERSIST=1; CSMC_PERSIST=probe builds it \
+                                     and lets the create-time probe choose between it and the per-colour pass kernels;   \
+                                     default: not built -- it lost to the pass kernels on every measured workload).  The tile-resident kernel (csmc_persist_info)    \
                                      runs a whole sequence of sweeps in ONE cooperative launch: every CTA (one per SM)    \
                                      keeps a tile of the lattice plus its halo in shared memory for all colour passes of  \
                                      the sequence, stores the sites other tiles read to the global spin array after each  \
